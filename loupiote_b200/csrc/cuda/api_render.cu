@@ -1,0 +1,901 @@
+// C ABI: Device, SceneGPU, ProbeGPU, Renderer.  Host orchestration of the wavefront
+// pipeline; mirrors Renderer::raytrace's frame state machine
+// [ref crates/lib/src/renderer.rs:392-549] and ASVGF::render [ref render/asvgf.rs:250-291].
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../host/api_common.hpp"
+#include "../host/scene.hpp"
+#include "kernels.cuh"
+#include "svgf.cuh"
+
+using namespace lp;
+
+#define CUDA_CHECK(expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      return lp::fail(_e == cudaErrorMemoryAllocation ? LP_ERR_OOM : LP_ERR_CUDA,         \
+                      std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    }                                                                                     \
+  } while (0)
+
+namespace {
+
+// gpu::Buffer<T> [ref albedo_backend::gpu::Buffer, renderer.rs:233-241]: RAII cudaMalloc.
+template <typename T>
+struct DevBuf {
+  T *ptr = nullptr;
+  size_t count = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)&ptr, n * sizeof(T));
+    if (e == cudaSuccess) count = n;
+    return e;
+  }
+  cudaError_t upload(const void *src, size_t n, cudaStream_t s) {
+    cudaError_t e = alloc(n);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+}  // namespace
+
+struct lp_device {
+  int ordinal = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  cudaDeviceProp prop{};
+};
+
+struct lp_scene_gpu {
+  lp_device *dev = nullptr;
+  DevBuf<float4> nodes, tris, instances, vertices, materials, emission, lights;
+  DevBuf<uint32_t> indices, active_lights;
+  SceneDev sc{};
+  size_t node_bytes = 0, tri_bytes = 0, total_bytes = 0;
+  uint32_t max_depth = 0;
+};
+
+struct lp_probe {
+  lp_device *dev = nullptr;
+  DevBuf<uchar4> texels;
+  uint32_t w = 0, h = 0;
+};
+
+namespace {
+struct PingPong {
+  DevBuf<float4> radiance;
+  DevBuf<uint4> gbuffer;
+  DevBuf<float2> moments;
+  DevBuf<float> history;
+};
+}  // namespace
+
+struct lp_renderer {
+  lp_device *dev = nullptr;
+  lp_scene_gpu *sg = nullptr;
+  lp_probe *probe = nullptr;
+  uint32_t width = 0, height = 0;  // internal (downsampled) size
+  uint32_t tiles_x = 0, slots_per_sample = 0, wave_samples = 0, n_slots = 0;
+  float downsample = 0.5f;
+  bool accumulate = false;
+  lp_blit_mode mode = LP_BLIT_PAHTRACE;
+  bool frame_back = true;
+  bool svgf_back = true;
+  bool use_noise = false;
+  lp_render_config cfg{};
+  uint32_t seed_cursor = 0;
+  uint32_t samples_accumulated = 0;
+  float prev_w2s[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  lp_camera camera{};
+
+  // per-slot path state + queues
+  DevBuf<float4> ray_o, ray_d, thr, rad, hit;
+  DevBuf<uint32_t> hit_inst, queue0, queue1;
+  DevBuf<float4> sl_o, sl_d, sl_c, se_o, se_d, se_c;
+  DevBuf<uint32_t> counts;
+  DevBuf<Counters> counters;
+  // render targets
+  DevBuf<float4> accum;  // main target: RGBA32F sum, alpha = sample count
+  DevBuf<float4> scratch;
+  DevBuf<uchar4> ldr;
+  DevBuf<uint32_t> fh_inst, fh_prim;
+  DevBuf<float> fh_t;
+  // ASVGF resources [ref asvgf.rs:9-152]
+  PingPong pp[2];
+  DevBuf<float2> motion;
+  DevBuf<float4> temp;
+  DevBuf<uchar4> noise;
+  uint32_t noise_w = 0, noise_h = 0;
+
+  // Queries [ref renderer.rs:321,444-517]
+  static constexpr int kMaxQueries = 10;
+  cudaEvent_t ev[kMaxQueries][2] = {};
+  std::vector<std::string> q_labels;
+  std::vector<const char *> q_label_ptrs;
+  std::vector<double> q_ms;
+  int q_open = -1;
+
+  int grid_extend = 0, grid_extend_stats = 0, grid_connect = 0, grid_connect_stats = 0,
+      grid_shade = 0;
+};
+
+namespace {
+
+uint32_t downsampled(uint32_t v, float f) { return std::max(1u, (uint32_t)((float)v * f)); }
+
+lp_status allocate_targets(lp_renderer *r) {
+  const uint32_t w = r->width, h = r->height;
+  const size_t P = (size_t)w * h;
+  r->tiles_x = (w + 7) / 8;
+  const uint32_t tiles_y = (h + 3) / 4;
+  r->slots_per_sample = r->tiles_x * tiles_y * 32u;
+  // samples in flight per wave: enough slots to keep 148 SMs busy in the deep bounces,
+  // capped at 8M slots (~1.6 GB of path state)
+  const uint32_t spp = std::max(1u, r->cfg.spp_per_call);
+  uint32_t ws = std::max(1u, (8u << 20) / r->slots_per_sample);
+  r->wave_samples = std::min(spp, ws);
+  r->n_slots = r->slots_per_sample * r->wave_samples;
+  const size_t S = r->n_slots;
+  CUDA_CHECK(r->ray_o.alloc(S));
+  CUDA_CHECK(r->ray_d.alloc(S));
+  CUDA_CHECK(r->thr.alloc(S));
+  CUDA_CHECK(r->rad.alloc(S));
+  CUDA_CHECK(r->hit.alloc(S));
+  CUDA_CHECK(r->hit_inst.alloc(S));
+  CUDA_CHECK(r->queue0.alloc(S));
+  CUDA_CHECK(r->queue1.alloc(S));
+  CUDA_CHECK(r->sl_o.alloc(S));
+  CUDA_CHECK(r->sl_d.alloc(S));
+  CUDA_CHECK(r->sl_c.alloc(S));
+  CUDA_CHECK(r->se_o.alloc(S));
+  CUDA_CHECK(r->se_d.alloc(S));
+  CUDA_CHECK(r->se_c.alloc(S));
+  CUDA_CHECK(r->counts.alloc(kCntTotal));
+  if (!r->counters.ptr) {
+    CUDA_CHECK(r->counters.alloc(1));
+    CUDA_CHECK(cudaMemsetAsync(r->counters.ptr, 0, sizeof(Counters), r->dev->stream));
+  }
+  CUDA_CHECK(r->accum.alloc(P));
+  CUDA_CHECK(r->scratch.alloc(P));
+  CUDA_CHECK(r->ldr.alloc(P));
+  CUDA_CHECK(r->fh_inst.alloc(P));
+  CUDA_CHECK(r->fh_prim.alloc(P));
+  CUDA_CHECK(r->fh_t.alloc(P));
+  for (int k = 0; k < 2; ++k) {
+    CUDA_CHECK(r->pp[k].radiance.alloc(P));
+    CUDA_CHECK(r->pp[k].gbuffer.alloc(P));
+    CUDA_CHECK(r->pp[k].moments.alloc(P));
+    CUDA_CHECK(r->pp[k].history.alloc(P));
+    CUDA_CHECK(cudaMemsetAsync(r->pp[k].radiance.ptr, 0, P * sizeof(float4), r->dev->stream));
+    CUDA_CHECK(cudaMemsetAsync(r->pp[k].gbuffer.ptr, 0xFF, P * sizeof(uint4), r->dev->stream));
+    CUDA_CHECK(cudaMemsetAsync(r->pp[k].moments.ptr, 0, P * sizeof(float2), r->dev->stream));
+    CUDA_CHECK(cudaMemsetAsync(r->pp[k].history.ptr, 0, P * sizeof(float), r->dev->stream));
+  }
+  CUDA_CHECK(r->motion.alloc(P));
+  CUDA_CHECK(r->temp.alloc(P));
+  CUDA_CHECK(cudaMemsetAsync(r->accum.ptr, 0, P * sizeof(float4), r->dev->stream));
+  CUDA_CHECK(cudaMemsetAsync(r->fh_inst.ptr, 0xFF, P * sizeof(uint32_t), r->dev->stream));
+  CUDA_CHECK(cudaMemsetAsync(r->fh_prim.ptr, 0xFF, P * sizeof(uint32_t), r->dev->stream));
+  CUDA_CHECK(cudaMemsetAsync(r->fh_t.ptr, 0, P * sizeof(float), r->dev->stream));
+  r->samples_accumulated = 0;
+  return LP_OK;
+}
+
+template <typename K>
+int persistent_grid(K kernel, int block, int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  return per_sm * sm_count;
+}
+
+void camera_from_view(const float view[16], uint32_t w, uint32_t h, float v_fov, lp_camera &cam,
+                      CameraDev &cd) {
+  std::memset(&cam, 0, sizeof(cam));
+  for (int a = 0; a < 3; ++a) {
+    cam.right[a] = view[a];
+    cam.up[a] = view[4 + a];
+    cam.forward[a] = view[8 + a];
+    cam.origin[a] = view[12 + a];
+  }
+  cam.v_fov = v_fov;
+  cam.width = w;
+  cam.height = h;
+  cam.tan_half_fov = tanf(0.5f * v_fov);
+  const float fw = (float)w, fh = (float)h;
+  const float aspect = fw / fh;
+  for (int a = 0; a < 3; ++a) {
+    cd.origin[a] = cam.origin[a];
+    cd.right[a] = cam.right[a];
+    cd.up[a] = cam.up[a];
+    cd.forward[a] = cam.forward[a];
+  }
+  cd.tan_x = cam.tan_half_fov * aspect;
+  cd.tan_y = cam.tan_half_fov;
+  cd.inv_w2 = 2.0f / fw;
+  cd.inv_h2 = 2.0f / fh;
+  cd.width = w;
+  cd.height = h;
+}
+
+// perspective(near, far) * view^-1 [ref renderer.rs:542-546]; +z-forward clip space.
+void world_to_screen(const lp_camera &cam, const float view[16], float znear, float zfar,
+                     float out[16]) {
+  float inv[16];
+  invert_affine(view, inv);
+  const float aspect = (float)cam.width / (float)cam.height;
+  float P[16] = {0};
+  P[0] = 1.0f / (cam.tan_half_fov * aspect);
+  P[5] = 1.0f / cam.tan_half_fov;
+  P[10] = zfar / (zfar - znear);
+  P[14] = -(znear * zfar) / (zfar - znear);
+  P[11] = 1.0f;
+  for (int c = 0; c < 4; ++c)
+    for (int rr = 0; rr < 4; ++rr) {
+      float acc = 0.0f;
+      for (int k = 0; k < 4; ++k) acc += P[4 * k + rr] * inv[4 * c + k];
+      out[4 * c + rr] = acc;
+    }
+}
+
+void query_start(lp_renderer *r, const char *label) {
+  if ((int)r->q_labels.size() >= lp_renderer::kMaxQueries) return;
+  const int i = (int)r->q_labels.size();
+  r->q_labels.emplace_back(label);
+  cudaEventRecord(r->ev[i][0], r->dev->stream);
+  r->q_open = i;
+}
+void query_end(lp_renderer *r) {
+  if (r->q_open < 0) return;
+  cudaEventRecord(r->ev[r->q_open][1], r->dev->stream);
+  r->q_open = -1;
+}
+
+__global__ void gather_sample_kernel(const float4 *__restrict__ rad, float4 *__restrict__ out,
+                                     uint32_t w, uint32_t h, uint32_t tiles_x) {
+  const uint32_t n = w * h;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = rad[pixel_to_slot(i % w, i / w, tiles_x)];
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ Device
+LP_API lp_status lp_device_create(int cuda_ordinal, lp_device **out) {
+  if (!out) return fail(LP_ERR_INVALID_ARG, "out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(LP_ERR_CUDA, std::string("no CUDA device available (this library has no CPU "
+                                         "fallback): ") + cudaGetErrorString(e));
+  if (cuda_ordinal < 0 || cuda_ordinal >= n) return fail(LP_ERR_INVALID_ARG, "bad CUDA ordinal");
+  CUDA_CHECK(cudaSetDevice(cuda_ordinal));
+  lp_device *d = new (std::nothrow) lp_device();
+  if (!d) return fail(LP_ERR_OOM, "out of host memory");
+  d->ordinal = cuda_ordinal;
+  if ((e = cudaGetDeviceProperties(&d->prop, cuda_ordinal)) != cudaSuccess) {
+    delete d;
+    return fail(LP_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (d->prop.major < 10) {
+    const std::string name = d->prop.name;
+    delete d;
+    return fail(LP_ERR_CUDA, "device '" + name + "' is not sm_100 class; kernels are built for sm_100a only");
+  }
+  d->sm_count = d->prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete d;
+    return fail(LP_ERR_CUDA, cudaGetErrorString(e));
+  }
+  *out = d;
+  return LP_OK;
+}
+
+LP_API lp_status lp_device_destroy(lp_device *dev) {
+  if (!dev) return LP_OK;
+  cudaSetDevice(dev->ordinal);
+  if (dev->stream) {
+    cudaStreamSynchronize(dev->stream);
+    cudaStreamDestroy(dev->stream);
+  }
+  delete dev;
+  return LP_OK;
+}
+
+LP_API lp_status lp_device_stream(lp_device *dev, void **out_cuda_stream) {
+  if (!dev || !out_cuda_stream) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  *out_cuda_stream = (void *)dev->stream;
+  return LP_OK;
+}
+
+LP_API lp_status lp_device_synchronize(lp_device *dev) {
+  if (!dev) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(dev->ordinal));
+  CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+  return LP_OK;
+}
+
+LP_API lp_status lp_device_info(lp_device *dev, char *name, size_t name_cap, int *sm_count,
+                                int *cc_major, int *cc_minor, size_t *total_mem) {
+  if (!dev) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (name && name_cap) {
+    std::strncpy(name, dev->prop.name, name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (sm_count) *sm_count = dev->sm_count;
+  if (cc_major) *cc_major = dev->prop.major;
+  if (cc_minor) *cc_minor = dev->prop.minor;
+  if (total_mem) *total_mem = dev->prop.totalGlobalMem;
+  return LP_OK;
+}
+
+// ------------------------------------------------------------------ SceneGPU / ProbeGPU
+LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp_scene_gpu **out) {
+  if (!scene || !dev || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  Scene &s = scene_of(scene);
+  try {
+    s.build_derived();
+  } catch (const std::exception &e) {
+    return fail(LP_ERR_ACCEL_BUILD, e.what());
+  }
+  if (s.gpu_max_depth + 2 > (uint32_t)kStackSize)
+    return fail(LP_ERR_ACCEL_BUILD, "BVH too deep for the traversal stack");
+  CUDA_CHECK(cudaSetDevice(dev->ordinal));
+  lp_scene_gpu *g = new (std::nothrow) lp_scene_gpu();
+  if (!g) return fail(LP_ERR_OOM, "out of host memory");
+  g->dev = dev;
+  cudaStream_t st = dev->stream;
+  std::vector<uint32_t> active;
+  for (uint32_t i = 0; i < s.lights.size(); ++i)
+    if (s.lights[i].intensity > 0.0f) active.push_back(i);
+  cudaError_t e = cudaSuccess;
+  auto up = [&](auto &buf, const void *src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = buf.upload(src, bytes / sizeof(*buf.ptr), st);
+  };
+  up(g->nodes, s.gpu_nodes.data(), s.gpu_nodes.size() * sizeof(GpuNode));
+  up(g->tris, s.primitives.data(), s.primitives.size() * sizeof(lp_bvh_primitive));
+  up(g->instances, s.gpu_instances.data(), s.gpu_instances.size() * sizeof(GpuInstance));
+  up(g->vertices, s.vertices.data(), s.vertices.size() * sizeof(lp_vertex));
+  up(g->materials, s.materials.data(), s.materials.size() * sizeof(lp_material));
+  up(g->emission, s.emission.data(), s.emission.size() * 16);
+  up(g->lights, s.lights.data(), s.lights.size() * sizeof(lp_light));
+  up(g->indices, s.indices.data(), s.indices.size() * sizeof(uint32_t));
+  up(g->active_lights, active.data(), active.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    delete g;
+    return fail(e == cudaErrorMemoryAllocation ? LP_ERR_OOM : LP_ERR_CUDA, cudaGetErrorString(e));
+  }
+  SceneDev &sc = g->sc;
+  sc.nodes = g->nodes.ptr;
+  sc.tris = g->tris.ptr;
+  sc.instances = g->instances.ptr;
+  sc.vertices = g->vertices.ptr;
+  sc.indices = g->indices.ptr;
+  sc.materials = g->materials.ptr;
+  sc.emission = g->emission.ptr;
+  sc.lights = g->lights.ptr;
+  sc.active_lights = g->active_lights.ptr;
+  sc.n_active_lights = (uint32_t)active.size();
+  sc.n_materials = (uint32_t)s.materials.size();
+  sc.tlas_root = s.gpu_tlas_root;
+  g->node_bytes = s.gpu_nodes.size() * sizeof(GpuNode);
+  g->tri_bytes = s.primitives.size() * sizeof(lp_bvh_primitive);
+  g->total_bytes = g->node_bytes + g->tri_bytes + s.gpu_instances.size() * sizeof(GpuInstance) +
+                   s.vertices.size() * sizeof(lp_vertex) + s.indices.size() * 4 +
+                   s.materials.size() * 48 + s.lights.size() * sizeof(lp_light);
+  g->max_depth = s.gpu_max_depth;
+  *out = g;
+  return LP_OK;
+}
+
+LP_API lp_status lp_scene_gpu_destroy(lp_scene_gpu *sg) {
+  if (sg) cudaSetDevice(sg->dev->ordinal);
+  delete sg;
+  return LP_OK;
+}
+
+LP_API lp_status lp_scene_gpu_stats(const lp_scene_gpu *sg, size_t *node_bytes, size_t *tri_bytes,
+                                    size_t *total_bytes, uint32_t *max_depth) {
+  if (!sg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (node_bytes) *node_bytes = sg->node_bytes;
+  if (tri_bytes) *tri_bytes = sg->tri_bytes;
+  if (total_bytes) *total_bytes = sg->total_bytes;
+  if (max_depth) *max_depth = sg->max_depth;
+  return LP_OK;
+}
+
+LP_API lp_status lp_probe_new(lp_device *dev, const uint8_t *rgbe8, uint32_t width, uint32_t height,
+                              lp_probe **out) {
+  if (!dev || !rgbe8 || !out || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
+  CUDA_CHECK(cudaSetDevice(dev->ordinal));
+  lp_probe *p = new (std::nothrow) lp_probe();
+  if (!p) return fail(LP_ERR_OOM, "out of host memory");
+  p->dev = dev;
+  p->w = width;
+  p->h = height;
+  cudaError_t e = p->texels.upload(rgbe8, (size_t)width * height, dev->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(LP_ERR_CUDA, cudaGetErrorString(e));
+  }
+  *out = p;
+  return LP_OK;
+}
+
+LP_API lp_status lp_probe_destroy(lp_probe *probe) {
+  if (probe) cudaSetDevice(probe->dev->ordinal);
+  delete probe;
+  return LP_OK;
+}
+
+// ------------------------------------------------------------------ Renderer
+LP_API void lp_render_config_default(lp_render_config *cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->max_bounces = 3;  // STATIC/MOVING_NUM_BOUNCES [ref renderer.rs:398-399]
+  cfg->spp_per_call = 1;
+  cfg->seed = 0;
+  cfg->atrous_iterations = 4;
+  cfg->jitter = 1;
+  cfg->russian_roulette = 0;
+  cfg->sample_offset = 0;
+  cfg->sample_stride = 1;
+  cfg->v_fov = 0.78539816339f;  // 45 degrees
+  cfg->count_stats = 0;
+}
+
+LP_API lp_status lp_renderer_new(lp_device *dev, uint32_t width, uint32_t height,
+                                 lp_renderer **out) {
+  if (!dev || !out || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
+  CUDA_CHECK(cudaSetDevice(dev->ordinal));
+  lp_renderer *r = new (std::nothrow) lp_renderer();
+  if (!r) return fail(LP_ERR_OOM, "out of host memory");
+  r->dev = dev;
+  lp_render_config_default(&r->cfg);
+  r->downsample = 0.5f;  // [ref renderer.rs:225]
+  r->width = downsampled(width, r->downsample);
+  r->height = downsampled(height, r->downsample);
+  for (int i = 0; i < lp_renderer::kMaxQueries; ++i)
+    for (int k = 0; k < 2; ++k)
+      if (cudaEventCreate(&r->ev[i][k]) != cudaSuccess) {
+        delete r;
+        return fail(LP_ERR_CUDA, "cudaEventCreate failed");
+      }
+  r->grid_extend = persistent_grid(extend_kernel<false>, 128, dev->sm_count);
+  r->grid_extend_stats = persistent_grid(extend_kernel<true>, 128, dev->sm_count);
+  r->grid_connect = persistent_grid(connect_kernel<false>, 128, dev->sm_count);
+  r->grid_connect_stats = persistent_grid(connect_kernel<true>, 128, dev->sm_count);
+  r->grid_shade = persistent_grid(shade_kernel, 128, dev->sm_count);
+  lp_status st = allocate_targets(r);
+  if (st != LP_OK) {
+    lp_renderer_destroy(r);
+    return st;
+  }
+  *out = r;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_destroy(lp_renderer *r) {
+  if (!r) return LP_OK;
+  cudaSetDevice(r->dev->ordinal);
+  cudaStreamSynchronize(r->dev->stream);
+  for (int i = 0; i < lp_renderer::kMaxQueries; ++i)
+    for (int k = 0; k < 2; ++k)
+      if (r->ev[i][k]) cudaEventDestroy(r->ev[i][k]);
+  delete r;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_set_resources(lp_renderer *r, lp_scene_gpu *sg,
+                                           lp_probe *probe_or_null) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  r->sg = sg;
+  r->probe = probe_or_null;
+  r->samples_accumulated = 0;  // frame_count = 1 [ref renderer.rs:724]
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_resize(lp_renderer *r, lp_scene_gpu *sg, lp_probe *probe_or_null,
+                                    uint32_t width, uint32_t height) {
+  if (!r || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  r->width = downsampled(width, r->downsample);
+  r->height = downsampled(height, r->downsample);
+  lp_status st = allocate_targets(r);
+  if (st != LP_OK) return st;
+  return lp_renderer_set_resources(r, sg, probe_or_null);
+}
+
+LP_API lp_status lp_renderer_set_config(lp_renderer *r, const lp_render_config *cfg) {
+  if (!r || !cfg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (cfg->max_bounces < 1 || cfg->max_bounces > kMaxBounces)
+    return fail(LP_ERR_INVALID_ARG, "max_bounces must be in [1, 32]");
+  if (cfg->spp_per_call < 1) return fail(LP_ERR_INVALID_ARG, "spp_per_call must be >= 1");
+  if (!(cfg->v_fov > 0.0f && cfg->v_fov < 3.1f)) return fail(LP_ERR_INVALID_ARG, "bad v_fov");
+  const bool realloc = cfg->spp_per_call != r->cfg.spp_per_call;
+  r->cfg = *cfg;
+  if (r->cfg.sample_stride == 0) r->cfg.sample_stride = 1;
+  r->seed_cursor = 0;
+  if (realloc) {
+    CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+    CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+    return allocate_targets(r);
+  }
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_get_config(const lp_renderer *r, lp_render_config *cfg) {
+  if (!r || !cfg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  *cfg = r->cfg;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform[16]) {
+  if (!r || !view_transform) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  r->frame_back = !r->frame_back;  // [ref renderer.rs:401]
+  if (!r->sg) return LP_OK;        // silently returns without resources [ref renderer.rs:403-422]
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  cudaStream_t st = r->dev->stream;
+  const lp_render_config &cfg = r->cfg;
+
+  FrameParams P{};
+  P.sc = r->sg->sc;
+  P.sc.env_color[0] = cfg.env_color[0];
+  P.sc.env_color[1] = cfg.env_color[1];
+  P.sc.env_color[2] = cfg.env_color[2];
+  if (r->probe) {
+    P.sc.probe = r->probe->texels.ptr;
+    P.sc.probe_w = r->probe->w;
+    P.sc.probe_h = r->probe->h;
+  }
+  P.sc.env_on = (r->probe != nullptr) || cfg.env_color[0] > 0.0f || cfg.env_color[1] > 0.0f ||
+                cfg.env_color[2] > 0.0f;
+  camera_from_view(view_transform, r->width, r->height, cfg.v_fov, r->camera, P.cam);
+  P.ps.ray_o = r->ray_o.ptr;
+  P.ps.ray_d = r->ray_d.ptr;
+  P.ps.thr = r->thr.ptr;
+  P.ps.rad = r->rad.ptr;
+  P.ps.hit = r->hit.ptr;
+  P.ps.hit_inst = r->hit_inst.ptr;
+  P.queue[0] = r->queue0.ptr;
+  P.queue[1] = r->queue1.ptr;
+  P.sq_light = ShadowQueue{r->sl_o.ptr, r->sl_d.ptr, r->sl_c.ptr};
+  P.sq_env = ShadowQueue{r->se_o.ptr, r->se_d.ptr, r->se_c.ptr};
+  P.counts = r->counts.ptr;
+  P.counters = r->counters.ptr;
+  P.n_pixels = r->width * r->height;
+  P.slots_per_sample = r->slots_per_sample;
+  P.tiles_x = r->tiles_x;
+  P.sample_stride = cfg.sample_stride;
+  P.seed = cfg.seed;
+  P.jitter = cfg.jitter;
+  P.max_bounces = cfg.max_bounces;
+  P.rr_start = cfg.russian_roulette;
+  P.accum = r->accum.ptr;
+  P.fh_inst = r->fh_inst.ptr;
+  P.fh_prim = r->fh_prim.ptr;
+  P.fh_t = r->fh_t.ptr;
+  std::memcpy(P.prev_w2s, r->prev_w2s, sizeof(P.prev_w2s));
+
+  const bool svgf = r->mode != LP_BLIT_PAHTRACE;
+  if (svgf) r->svgf_back = !r->svgf_back;  // asvgf.start() [ref renderer.rs:466-467, asvgf.rs:236]
+  const int cur = r->svgf_back ? 1 : 0;
+  P.write_gbuffer = svgf ? 1 : 0;
+  P.gbuffer = r->pp[cur].gbuffer.ptr;
+  P.motion = r->motion.ptr;
+
+  r->q_labels.clear();
+  const bool stats = cfg.count_stats != 0;
+  const int sm = r->dev->sm_count;
+  uint32_t remaining = cfg.spp_per_call;
+  bool first_wave = true;
+  while (remaining > 0) {
+    const uint32_t S = std::min(remaining, r->wave_samples);
+    P.samples_in_wave = S;
+    P.n_slots = r->slots_per_sample * S;
+    P.sample_base = cfg.sample_offset + r->seed_cursor * cfg.sample_stride;
+    P.overwrite_accum = (first_wave && r->samples_accumulated == 0) ? 1 : 0;
+    CUDA_CHECK(cudaMemsetAsync(r->counts.ptr, 0, kCntTotal * sizeof(uint32_t), st));
+
+    if (first_wave) query_start(r, "ray generation");  // [ref renderer.rs:444]
+    generate_kernel<<<sm * 8, 256, 0, st>>>(P);
+    if (first_wave) query_end(r);
+    for (uint32_t b = 0; b < cfg.max_bounces; ++b) {
+      if (first_wave && b == 0) query_start(r, "primary intersection");  // [ref :457]
+      if (first_wave && b == 1) query_start(r, "bounces");
+      if (stats) extend_kernel<true><<<r->grid_extend_stats, 128, 0, st>>>(P, b);
+      else extend_kernel<false><<<r->grid_extend, 128, 0, st>>>(P, b);
+      if (first_wave && b == 0) {
+        query_end(r);
+        query_start(r, "shading 0");  // [ref :471]
+      }
+      shade_kernel<<<r->grid_shade, 128, 0, st>>>(P, b);
+      if (P.sc.n_active_lights) {
+        if (stats) connect_kernel<true><<<r->grid_connect_stats, 128, 0, st>>>(P, b, 0);
+        else connect_kernel<false><<<r->grid_connect, 128, 0, st>>>(P, b, 0);
+      }
+      if (P.sc.env_on) {
+        if (stats) connect_kernel<true><<<r->grid_connect_stats, 128, 0, st>>>(P, b, 1);
+        else connect_kernel<false><<<r->grid_connect, 128, 0, st>>>(P, b, 1);
+      }
+      if (first_wave && b == 0) query_end(r);
+    }
+    if (first_wave && cfg.max_bounces > 1) query_end(r);
+    finalize_counts_kernel<<<1, 32, 0, st>>>(P);
+
+    if (r->mode == LP_BLIT_PAHTRACE) {
+      if (first_wave) query_start(r, "accumulation");
+      accumulate_kernel<<<sm * 8, 256, 0, st>>>(P);  // [ref renderer.rs:523-538]
+      if (first_wave) query_end(r);
+    }
+    r->seed_cursor += S;
+    remaining -= S;
+    first_wave = false;
+  }
+
+  const uint32_t n = P.n_pixels;
+  if (r->mode == LP_BLIT_DENOISED_PATHRACE || r->mode == LP_BLIT_TEMPORAL) {
+    query_start(r, "asvgf");  // [ref renderer.rs:515]
+    const int prev = 1 - cur;
+    SvgfTemporalParams T{};
+    T.w = r->width;
+    T.h = r->height;
+    T.tiles_x = r->tiles_x;
+    T.sample_rad = r->rad.ptr;
+    T.gb_cur = r->pp[cur].gbuffer.ptr;
+    T.gb_prev = r->pp[prev].gbuffer.ptr;
+    T.motion = r->motion.ptr;
+    T.prev_rad = r->pp[prev].radiance.ptr;
+    T.prev_mom = r->pp[prev].moments.ptr;
+    T.prev_hist = r->pp[prev].history.ptr;
+    T.out_rad = r->pp[cur].radiance.ptr;
+    T.out_mom = r->pp[cur].moments.ptr;
+    T.out_hist = r->pp[cur].history.ptr;
+    svgf_temporal_kernel<<<sm * 8, 256, 0, st>>>(T);
+    if (r->mode == LP_BLIT_DENOISED_PATHRACE) {
+      // a-trous ping-pong between `temp` and the main target [ref asvgf.rs:277-290]
+      const float4 *src = r->pp[cur].radiance.ptr;
+      for (uint32_t it = 0; it < cfg.atrous_iterations; ++it) {
+        float4 *dst = (it & 1u) ? r->accum.ptr : r->temp.ptr;
+        svgf_atrous_kernel<<<sm * 8, 256, 0, st>>>(r->width, r->height, src,
+                                                   r->pp[cur].gbuffer.ptr, it, dst);
+        src = dst;
+      }
+      svgf_composite_kernel<<<sm * 8, 256, 0, st>>>(n, src, r->pp[cur].gbuffer.ptr, r->accum.ptr);
+    }
+    query_end(r);
+  }
+
+  if (r->mode == LP_BLIT_PAHTRACE) {
+    if (r->accumulate) r->samples_accumulated += cfg.spp_per_call;  // frame_count += 1 [ref :535-537]
+    else r->samples_accumulated = 0;
+  }
+  // prev_model_to_screen = perspective(0.01, 100) * view^-1 [ref renderer.rs:542-546]
+  world_to_screen(r->camera, view_transform, 0.01f, 100.0f, r->prev_w2s);
+  CUDA_CHECK(cudaGetLastError());
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_reset_accumulation(lp_renderer *r) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  r->samples_accumulated = 0;  // frame_count = 1 [ref renderer.rs:610]
+  r->accumulate = false;       // [ref renderer.rs:611]
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_set_blit_mode(lp_renderer *r, lp_blit_mode mode) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if ((int)mode < 0 || (int)mode > LP_BLIT_MOTION_VECTOR)
+    return fail(LP_ERR_INVALID_ARG, "unknown blit mode");
+  r->mode = mode;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_use_noise_texture(lp_renderer *r, int flag) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  r->use_noise = flag != 0;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_upload_noise_texture(lp_renderer *r, const uint8_t *data,
+                                                  uint32_t width, uint32_t height,
+                                                  uint32_t bytes_per_row) {
+  if (!r || !data || !width || !height || bytes_per_row < width * 4u)
+    return fail(LP_ERR_INVALID_ARG, "bad argument");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  CUDA_CHECK(r->noise.alloc((size_t)width * height));
+  CUDA_CHECK(cudaMemcpy2DAsync(r->noise.ptr, (size_t)width * 4, data, bytes_per_row,
+                               (size_t)width * 4, height, cudaMemcpyHostToDevice, r->dev->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  r->noise_w = width;
+  r->noise_h = height;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_get_size(const lp_renderer *r, uint32_t *width, uint32_t *height) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (width) *width = r->width;
+  if (height) *height = r->height;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_set_accumulate(lp_renderer *r, int flag) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  r->accumulate = flag != 0;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_get_accumulate(const lp_renderer *r, int *flag) {
+  if (!r || !flag) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  *flag = r->accumulate ? 1 : 0;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_set_downsample_factor(lp_renderer *r, float factor) {
+  if (!r || !(factor > 0.0f) || factor > 4.0f) return fail(LP_ERR_INVALID_ARG, "bad factor");
+  r->downsample = factor;  // takes effect at the next resize [ref renderer.rs:203,333]
+  return LP_OK;
+}
+
+LP_API uint32_t lp_renderer_max_ssbo_element_in_bytes(void) {
+  // max(Ray = 2 x float4 + throughput/radiance 2 x float4, Intersection, Camera, PerDraw)
+  return 64u;
+}
+
+LP_API lp_status lp_renderer_read_pixels(lp_renderer *r, uint8_t *out, size_t cap) {
+  if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  const size_t n = (size_t)r->width * r->height;
+  if (cap < n * 4) return fail(LP_ERR_READBACK, "output buffer too small");
+  if (cudaSetDevice(r->dev->ordinal) != cudaSuccess) return fail(LP_ERR_READBACK, "cudaSetDevice");
+  tonemap_kernel<<<r->dev->sm_count * 8, 256, 0, r->dev->stream>>>(r->accum.ptr, r->ldr.ptr,
+                                                                   (uint32_t)n);
+  cudaError_t e = cudaMemcpyAsync(out, r->ldr.ptr, n * 4, cudaMemcpyDeviceToHost, r->dev->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(r->dev->stream);
+  if (e != cudaSuccess) return fail(LP_ERR_READBACK, cudaGetErrorString(e));
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_queries(lp_renderer *r, const char *const **labels, const double **ms,
+                                     size_t *count) {
+  if (!r || !count) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  r->q_ms.assign(r->q_labels.size(), 0.0);
+  r->q_label_ptrs.clear();
+  for (size_t i = 0; i < r->q_labels.size(); ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r->ev[i][0], r->ev[i][1]) == cudaSuccess) r->q_ms[i] = t;
+    r->q_label_ptrs.push_back(r->q_labels[i].c_str());
+  }
+  if (labels) *labels = r->q_label_ptrs.data();
+  if (ms) *ms = r->q_ms.data();
+  *count = r->q_labels.size();
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_read_accum_f32(lp_renderer *r, float *out, size_t cap_floats) {
+  if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  const size_t n = (size_t)r->width * r->height;
+  if (cap_floats < n * 4) return fail(LP_ERR_READBACK, "output buffer too small");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  normalize_kernel<<<r->dev->sm_count * 8, 256, 0, r->dev->stream>>>(r->accum.ptr, r->scratch.ptr,
+                                                                     (uint32_t)n);
+  CUDA_CHECK(cudaMemcpyAsync(out, r->scratch.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost,
+                             r->dev->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_read_first_hit(lp_renderer *r, uint32_t *instance, uint32_t *primitive,
+                                            float *t, size_t cap_pixels) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  const size_t n = (size_t)r->width * r->height;
+  if (cap_pixels < n) return fail(LP_ERR_READBACK, "output buffer too small");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  cudaStream_t st = r->dev->stream;
+  if (instance) CUDA_CHECK(cudaMemcpyAsync(instance, r->fh_inst.ptr, n * 4, cudaMemcpyDeviceToHost, st));
+  if (primitive) CUDA_CHECK(cudaMemcpyAsync(primitive, r->fh_prim.ptr, n * 4, cudaMemcpyDeviceToHost, st));
+  if (t) CUDA_CHECK(cudaMemcpyAsync(t, r->fh_t.ptr, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_ray_counters(lp_renderer *r, lp_ray_counters *out, int reset) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  cudaStream_t st = r->dev->stream;
+  if (out) {
+    Counters c;
+    CUDA_CHECK(cudaMemcpyAsync(&c, r->counters.ptr, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    out->primary = c.rays[0];
+    out->bounce = c.rays[1];
+    out->shadow = c.rays[2];
+    for (int k = 0; k < 3; ++k) {
+      out->n_int[k] = c.n_int[k];
+      out->n_tri[k] = c.n_tri[k];
+      out->n_inst[k] = c.n_inst[k];
+    }
+  }
+  if (reset) CUDA_CHECK(cudaMemsetAsync(r->counters.ptr, 0, sizeof(Counters), st));
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_accum_device_ptr(lp_renderer *r, void **dev_ptr, size_t *count_floats,
+                                              uint32_t *samples) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (dev_ptr) *dev_ptr = r->accum.ptr;
+  if (count_floats) *count_floats = (size_t)r->width * r->height * 4;
+  if (samples) *samples = r->samples_accumulated;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_set_sample_count(lp_renderer *r, uint32_t samples) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  r->samples_accumulated = samples;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_camera(const lp_renderer *r, lp_camera *out,
+                                    float prev_world_to_screen[16]) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (out) *out = r->camera;
+  if (prev_world_to_screen) std::memcpy(prev_world_to_screen, r->prev_w2s, 64);
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_read_aux(lp_renderer *r, int which, void *out, size_t cap_bytes) {
+  if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  const size_t n = (size_t)r->width * r->height;
+  const int cur = r->svgf_back ? 1 : 0;
+  const void *src = nullptr;
+  size_t bytes = 0;
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  switch (which) {
+    case 0: src = r->pp[cur].radiance.ptr; bytes = n * 16; break;
+    case 1: src = r->pp[cur].moments.ptr; bytes = n * 8; break;
+    case 2: src = r->pp[cur].history.ptr; bytes = n * 4; break;
+    case 3: src = r->pp[cur].gbuffer.ptr; bytes = n * 16; break;
+    case 4: src = r->motion.ptr; bytes = n * 8; break;
+    case 5:
+      gather_sample_kernel<<<r->dev->sm_count * 8, 256, 0, r->dev->stream>>>(
+          r->rad.ptr, r->scratch.ptr, r->width, r->height, r->tiles_x);
+      src = r->scratch.ptr;
+      bytes = n * 16;
+      break;
+    default: return fail(LP_ERR_INVALID_ARG, "unknown aux buffer");
+  }
+  if (cap_bytes < bytes) return fail(LP_ERR_READBACK, "output buffer too small");
+  CUDA_CHECK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, r->dev->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  return LP_OK;
+}
+
+}  // extern "C"

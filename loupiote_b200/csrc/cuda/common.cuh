@@ -1,0 +1,114 @@
+// Device-side data model and small math helpers shared by all kernels.
+// The library is compiled with -fmad=false: a fused multiply-add only happens where the
+// code says __fmaf_rn, so the intersection arithmetic is bit-identical to the spec
+// (DESIGN.md "Arithmetic contract") regardless of compiler version.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "loupiote.h"
+
+namespace lp {
+
+constexpr uint32_t kLeaf = 0x80000000u;
+constexpr uint32_t kNoChildRef = 0x7FFFFFFFu;
+constexpr uint32_t kSentinel = 0x7FFFFFFEu;
+constexpr uint32_t kLightInstance = 0xFFFFFFFEu;
+constexpr int kStackSize = 64;
+
+#define LP_PI 3.14159265358979323846f
+#define LP_INV_PI 0.31830988618379067154f
+
+// Scene buffers as the kernels see them (all 16-byte vector loads).
+struct SceneDev {
+  const float4 *nodes;      // 4 x float4 per 64-byte node
+  const float4 *tris;       // 3 x float4 per triangle (leaf order)
+  const float4 *instances;  // 8 x float4 per 128-byte instance
+  const float4 *vertices;   // 2 x float4 per vertex
+  const uint32_t *indices;
+  const float4 *materials;  // 2 x float4 per material
+  const float4 *emission;   // 1 x float4 per material
+  const float4 *lights;     // 4 x float4 per light
+  const uint32_t *active_lights;
+  uint32_t n_active_lights;
+  uint32_t n_materials;
+  uint32_t tlas_root;  // child reference
+  int env_on;
+  float env_color[3];
+  const uchar4 *probe;
+  uint32_t probe_w, probe_h;
+};
+
+struct CameraDev {
+  float origin[3];
+  float right[3];
+  float up[3];
+  float forward[3];
+  float tan_x, tan_y;    // tan_half_fov*aspect, tan_half_fov
+  float inv_w2, inv_h2;  // 2/width, 2/height
+  uint32_t width, height;
+};
+
+// Per-slot path state, structure of arrays. slot = local_sample * n_pixels + pixel.
+struct PathState {
+  float4 *ray_o;      // origin.xyz, unused
+  float4 *ray_d;      // direction.xyz, unused
+  float4 *thr;        // throughput.rgb, pdf of the BSDF sample that made this ray (-1: camera)
+  float4 *rad;        // radiance.rgb, cosine pdf of this ray's direction (env MIS)
+  float4 *hit;        // t, u, v, primitive bits
+  uint32_t *hit_inst;
+};
+
+struct ShadowQueue {
+  float4 *o_tmax;    // origin.xyz, tmax
+  float4 *d_slot;    // direction.xyz, slot bits
+  float4 *contrib;   // rgb
+};
+
+struct Counters {
+  // [0] primary, [1] bounce, [2] shadow
+  unsigned long long rays[3];
+  unsigned long long n_int[3], n_tri[3], n_inst[3];
+};
+
+// ------------------------------------------------------------------ float3 helpers
+struct f3 {
+  float x, y, z;
+};
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 operator-(f3 a) { return f3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+  return f3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ f3 normalize(f3 v) {
+  const float l = sqrtf(dot(v, v));
+  const float r = 1.0f / l;
+  return f3{v.x * r, v.y * r, v.z * r};
+}
+__device__ __forceinline__ float sel(f3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+  return fminf(fmaxf(x, lo), hi);
+}
+
+// pcg4d (Jarzynski & Olano 2020): stateless hash of (pixel, sample, block, seed)
+__device__ __forceinline__ uint4 rng4(uint32_t pixel, uint32_t sample, uint32_t block,
+                                      uint32_t seed) {
+  uint32_t x = pixel, y = sample, z = block, w = seed;
+  x = x * 1664525u + 1013904223u;
+  y = y * 1664525u + 1013904223u;
+  z = z * 1664525u + 1013904223u;
+  w = w * 1664525u + 1013904223u;
+  x += y * w; y += z * x; z += x * y; w += y * z;
+  x ^= x >> 16; y ^= y >> 16; z ^= z >> 16; w ^= w >> 16;
+  x += y * w; y += z * x; z += x * y; w += y * z;
+  return make_uint4(x, y, z, w);
+}
+__device__ __forceinline__ float u01(uint32_t x) {
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+}  // namespace lp

@@ -1,0 +1,234 @@
+// Surface fetch, Lambert+GGX BSDF (metallic workflow), sampling, packing helpers.
+// Replaces the arithmetic of albedo_rtx `shading.comp` (ShadingPass / PrimaryRayPass,
+// [ref crates/lib/src/renderer.rs:471-508]); spec in DESIGN.md, literature per the
+// reference README (README.md:36-42): UE4 real shading (Karis), PBRT, Heitz 2018 VNDF.
+#pragma once
+#include "common.cuh"
+#include "traverse.cuh"
+
+namespace lp {
+
+struct Surface {
+  f3 p, ng, ns, base, emission;
+  float metallic, alpha;
+};
+
+__device__ __forceinline__ void fetch_surface(const SceneDev &sc, const Hit &hit, f3 d,
+                                              Surface &sf, uint32_t &material_out) {
+  const float4 *ip = sc.instances + 8u * (size_t)hit.inst;
+  const float4 w0 = __ldg(ip), w1 = __ldg(ip + 1), w2 = __ldg(ip + 2);
+  const float4 m0 = __ldg(ip + 3), m1 = __ldg(ip + 4), m2 = __ldg(ip + 5);
+  const float4 ids = __ldg(ip + 6);
+  const uint32_t material = __float_as_uint(ids.y);
+  const uint32_t index_offset = __float_as_uint(ids.z);
+  const uint32_t vertex_offset = __float_as_uint(ids.w);
+  const uint32_t *idx = sc.indices + index_offset + 3u * hit.prim;
+  const uint32_t i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
+  const float4 *vp = sc.vertices + 2u * (size_t)vertex_offset;
+  const float4 a0 = __ldg(vp + 2u * i0), a1 = __ldg(vp + 2u * i0 + 1);
+  const float4 b0 = __ldg(vp + 2u * i1), b1 = __ldg(vp + 2u * i1 + 1);
+  const float4 c0 = __ldg(vp + 2u * i2), c1 = __ldg(vp + 2u * i2 + 1);
+  const float bu = hit.u, bv = hit.v, bw = 1.0f - hit.u - hit.v;
+  const f3 po = mk3(__fmaf_rn(bw, a0.x, __fmaf_rn(bu, b0.x, bv * c0.x)),
+                    __fmaf_rn(bw, a0.y, __fmaf_rn(bu, b0.y, bv * c0.y)),
+                    __fmaf_rn(bw, a0.z, __fmaf_rn(bu, b0.z, bv * c0.z)));
+  const f3 no = mk3(__fmaf_rn(bw, a1.x, __fmaf_rn(bu, b1.x, bv * c1.x)),
+                    __fmaf_rn(bw, a1.y, __fmaf_rn(bu, b1.y, bv * c1.y)),
+                    __fmaf_rn(bw, a1.z, __fmaf_rn(bu, b1.z, bv * c1.z)));
+  const f3 e1 = mk3(b0.x - a0.x, b0.y - a0.y, b0.z - a0.z);
+  const f3 e2 = mk3(c0.x - a0.x, c0.y - a0.y, c0.z - a0.z);
+  const f3 go = cross(e1, e2);
+  sf.p = xform_point(m0, m1, m2, po);
+  // normals: inverse transpose = columns of world->object
+  sf.ng = normalize(mk3(__fmaf_rn(w0.x, go.x, __fmaf_rn(w1.x, go.y, w2.x * go.z)),
+                        __fmaf_rn(w0.y, go.x, __fmaf_rn(w1.y, go.y, w2.y * go.z)),
+                        __fmaf_rn(w0.z, go.x, __fmaf_rn(w1.z, go.y, w2.z * go.z))));
+  if (dot(no, no) > 0.0f) {
+    sf.ns = normalize(mk3(__fmaf_rn(w0.x, no.x, __fmaf_rn(w1.x, no.y, w2.x * no.z)),
+                          __fmaf_rn(w0.y, no.x, __fmaf_rn(w1.y, no.y, w2.y * no.z)),
+                          __fmaf_rn(w0.z, no.x, __fmaf_rn(w1.z, no.y, w2.z * no.z))));
+  } else {
+    sf.ns = sf.ng;
+  }
+  if (dot(sf.ng, d) > 0.0f) sf.ng = -sf.ng;
+  if (dot(sf.ns, sf.ng) < 0.0f) sf.ns = -sf.ns;
+  const uint32_t mi = material < sc.n_materials ? material : 0u;
+  const float4 c = __ldg(sc.materials + 2u * mi), pr = __ldg(sc.materials + 2u * mi + 1);
+  const float4 em = __ldg(sc.emission + mi);
+  sf.base = mk3(c.x, c.y, c.z);
+  sf.emission = mk3(em.x, em.y, em.z);
+  sf.metallic = clampf(pr.y, 0.0f, 1.0f);
+  const float rough = clampf(pr.x, 0.0f, 1.0f);
+  sf.alpha = fmaxf(rough * rough, 1e-3f);
+  material_out = mi;
+}
+
+__device__ __forceinline__ void onb(f3 n, f3 &t, f3 &b) {
+  const float sign = copysignf(1.0f, n.z);
+  const float a = -1.0f / (sign + n.z);
+  const float bb = n.x * n.y * a;
+  t = mk3(1.0f + sign * n.x * n.x * a, sign * bb, -sign * n.x);
+  b = mk3(bb, sign + n.y * n.y * a, -n.y);
+}
+
+__device__ __forceinline__ float luminance(f3 c) {
+  return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z;
+}
+__device__ __forceinline__ float pow5(float x) {
+  const float x2 = x * x;
+  return x2 * x2 * x;
+}
+__device__ __forceinline__ float ggx_g1(float ndx, float a2) {
+  return 2.0f * ndx / (ndx + sqrtf(a2 + (1.0f - a2) * ndx * ndx));
+}
+
+__device__ __forceinline__ float lobe_probability(const Surface &sf, float ndv) {
+  const float k = pow5(1.0f - ndv);
+  const float inv_m = 1.0f - sf.metallic;
+  const f3 F0 = mk3(0.04f + (sf.base.x - 0.04f) * sf.metallic,
+                    0.04f + (sf.base.y - 0.04f) * sf.metallic,
+                    0.04f + (sf.base.z - 0.04f) * sf.metallic);
+  const f3 diff = mk3(sf.base.x * inv_m, sf.base.y * inv_m, sf.base.z * inv_m);
+  const f3 Fv = mk3(F0.x + (1.0f - F0.x) * k, F0.y + (1.0f - F0.y) * k, F0.z + (1.0f - F0.z) * k);
+  const float ws = luminance(Fv), wd = luminance(diff);
+  return wd > 0.0f ? clampf(ws / (ws + wd), 0.1f, 0.9f) : 1.0f;
+}
+
+// f (without the cosine) and the combined sampling pdf of the lobe mixture
+__device__ __forceinline__ void bsdf_eval(const Surface &sf, f3 wo, f3 wi, f3 &f, float &pdf) {
+  const float ndl = dot(sf.ns, wi);
+  const float ndv = fmaxf(dot(sf.ns, wo), 1e-4f);
+  f = mk3(0.0f, 0.0f, 0.0f);
+  pdf = 0.0f;
+  if (!(ndl > 0.0f)) return;
+  const f3 h = normalize(wo + wi);
+  const float ndh = fmaxf(dot(sf.ns, h), 0.0f);
+  const float vdh = fmaxf(dot(wo, h), 0.0f);
+  const float a2 = sf.alpha * sf.alpha;
+  const float dd = ndh * ndh * (a2 - 1.0f) + 1.0f;
+  const float D = a2 / (LP_PI * dd * dd);
+  const float g1v = ggx_g1(ndv, a2), g1l = ggx_g1(ndl, a2);
+  const float fc = pow5(1.0f - vdh);
+  const float inv_m = 1.0f - sf.metallic;
+  const f3 F0 = mk3(0.04f + (sf.base.x - 0.04f) * sf.metallic,
+                    0.04f + (sf.base.y - 0.04f) * sf.metallic,
+                    0.04f + (sf.base.z - 0.04f) * sf.metallic);
+  const f3 diff = mk3(sf.base.x * inv_m, sf.base.y * inv_m, sf.base.z * inv_m);
+  const float spec = D * g1v * g1l / (4.0f * ndl * ndv);
+  f.x = diff.x * LP_INV_PI + (F0.x + (1.0f - F0.x) * fc) * spec;
+  f.y = diff.y * LP_INV_PI + (F0.y + (1.0f - F0.y) * fc) * spec;
+  f.z = diff.z * LP_INV_PI + (F0.z + (1.0f - F0.z) * fc) * spec;
+  const float ps = lobe_probability(sf, ndv);
+  const float pdf_spec = g1v * D / (4.0f * ndv);
+  const float pdf_diff = ndl * LP_INV_PI;
+  pdf = ps * pdf_spec + (1.0f - ps) * pdf_diff;
+}
+
+__device__ __forceinline__ f3 cosine_sample(f3 n, float u1, float u2) {
+  f3 t, b;
+  onb(n, t, b);
+  const float r = sqrtf(u1), phi = 2.0f * LP_PI * u2;
+  float s, c;
+  sincosf(phi, &s, &c);
+  const float x = r * c, y = r * s, z = sqrtf(fmaxf(0.0f, 1.0f - u1));
+  return mk3(x * t.x + y * b.x + z * n.x, x * t.y + y * b.y + z * n.y,
+             x * t.z + y * b.z + z * n.z);
+}
+
+__device__ __forceinline__ bool bsdf_sample(const Surface &sf, f3 wo, float ul, float u1, float u2,
+                                            f3 &wi) {
+  const float ndv = fmaxf(dot(sf.ns, wo), 1e-4f);
+  const float ps = lobe_probability(sf, ndv);
+  if (ul < ps) {
+    f3 t, b;
+    onb(sf.ns, t, b);
+    const float a = sf.alpha;
+    const f3 v = mk3(dot(wo, t), dot(wo, b), fmaxf(dot(wo, sf.ns), 1e-4f));
+    const f3 vh = normalize(mk3(a * v.x, a * v.y, v.z));
+    const float lensq = vh.x * vh.x + vh.y * vh.y;
+    f3 T1 = mk3(1.0f, 0.0f, 0.0f);
+    if (lensq > 0.0f) {
+      const float il = 1.0f / sqrtf(lensq);
+      T1 = mk3(-vh.y * il, vh.x * il, 0.0f);
+    }
+    const f3 T2 = cross(vh, T1);
+    const float r = sqrtf(u1), phi = 2.0f * LP_PI * u2;
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    const float p1 = r * cs;
+    float p2 = r * sn;
+    const float sv = 0.5f * (1.0f + vh.z);
+    p2 = (1.0f - sv) * sqrtf(fmaxf(0.0f, 1.0f - p1 * p1)) + sv * p2;
+    const float pz = sqrtf(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2));
+    const f3 nh = mk3(p1 * T1.x + p2 * T2.x + pz * vh.x, p1 * T1.y + p2 * T2.y + pz * vh.y,
+                      p1 * T1.z + p2 * T2.z + pz * vh.z);
+    const f3 hl = normalize(mk3(a * nh.x, a * nh.y, fmaxf(0.0f, nh.z)));
+    const f3 h = mk3(hl.x * t.x + hl.y * b.x + hl.z * sf.ns.x, hl.x * t.y + hl.y * b.y + hl.z * sf.ns.y,
+                     hl.x * t.z + hl.y * b.z + hl.z * sf.ns.z);
+    const float vdh = dot(wo, h);
+    wi = mk3(2.0f * vdh * h.x - wo.x, 2.0f * vdh * h.y - wo.y, 2.0f * vdh * h.z - wo.z);
+  } else {
+    wi = cosine_sample(sf.ns, u1, u2);
+  }
+  return dot(sf.ns, wi) > 0.0f && dot(sf.ng, wi) > 0.0f;
+}
+
+__device__ __forceinline__ f3 rgbe_decode(uchar4 p) {
+  if (p.w == 0) return mk3(0.0f, 0.0f, 0.0f);
+  const float f = ldexpf(1.0f, (int)p.w - (128 + 8));
+  return mk3((float)p.x * f, (float)p.y * f, (float)p.z * f);
+}
+
+__device__ __forceinline__ f3 env_radiance(const SceneDev &sc, f3 d) {
+  if (sc.probe) {
+    const float u = atan2f(d.z, d.x) * (0.5f * LP_INV_PI) + 0.5f;
+    const float v = acosf(clampf(d.y, -1.0f, 1.0f)) * LP_INV_PI;
+    const uint32_t x = (uint32_t)fminf(u * (float)sc.probe_w, (float)(sc.probe_w - 1));
+    const uint32_t y = (uint32_t)fminf(v * (float)sc.probe_h, (float)(sc.probe_h - 1));
+    return rgbe_decode(__ldg(sc.probe + (size_t)y * sc.probe_w + x));
+  }
+  return mk3(sc.env_color[0], sc.env_color[1], sc.env_color[2]);
+}
+
+__device__ __forceinline__ float power_heuristic(float a, float b) {
+  const float a2 = a * a, b2 = b * b;
+  return a2 / (a2 + b2);
+}
+
+__device__ __forceinline__ uint32_t pack_normal(f3 n) {
+  const float inv = 1.0f / (fabsf(n.x) + fabsf(n.y) + fabsf(n.z));
+  float px = n.x * inv, py = n.y * inv;
+  if (n.z < 0.0f) {
+    const float ox = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f);
+    const float oy = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f);
+    px = ox;
+    py = oy;
+  }
+  const int ix = (int)floorf(clampf(px, -1.0f, 1.0f) * 32767.0f + 0.5f);
+  const int iy = (int)floorf(clampf(py, -1.0f, 1.0f) * 32767.0f + 0.5f);
+  return ((uint32_t)ix & 0xFFFFu) | (((uint32_t)iy & 0xFFFFu) << 16);
+}
+__device__ __forceinline__ f3 unpack_normal(uint32_t p) {
+  const float x = (float)(short)(p & 0xFFFFu) * (1.0f / 32767.0f);
+  const float y = (float)(short)(p >> 16) * (1.0f / 32767.0f);
+  const float z = 1.0f - fabsf(x) - fabsf(y);
+  float nx = x, ny = y;
+  if (z < 0.0f) {
+    nx = (1.0f - fabsf(y)) * (x >= 0.0f ? 1.0f : -1.0f);
+    ny = (1.0f - fabsf(x)) * (y >= 0.0f ? 1.0f : -1.0f);
+  }
+  return normalize(mk3(nx, ny, z));
+}
+__device__ __forceinline__ uint32_t pack_rgba8(f3 c) {
+  const uint32_t r = (uint32_t)floorf(clampf(c.x, 0.0f, 1.0f) * 255.0f + 0.5f);
+  const uint32_t g = (uint32_t)floorf(clampf(c.y, 0.0f, 1.0f) * 255.0f + 0.5f);
+  const uint32_t b = (uint32_t)floorf(clampf(c.z, 0.0f, 1.0f) * 255.0f + 0.5f);
+  return 0xFF000000u | r | (g << 8) | (b << 16);
+}
+__device__ __forceinline__ f3 unpack_albedo(uint32_t p) {
+  return mk3(fmaxf((float)(p & 0xFFu) * (1.0f / 255.0f), 0.03f),
+             fmaxf((float)((p >> 8) & 0xFFu) * (1.0f / 255.0f), 0.03f),
+             fmaxf((float)((p >> 16) & 0xFFu) * (1.0f / 255.0f), 0.03f));
+}
+
+}  // namespace lp

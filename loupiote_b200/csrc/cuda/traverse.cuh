@@ -1,0 +1,241 @@
+// Stack-based two-level BVH traversal + watertight ray/triangle intersection.
+// Replaces albedo_rtx IntersectorPass (closest hit) and the inline occlusion rays of
+// ShadingPass [ref crates/lib/src/renderer.rs:457-464,493-508].
+//
+// Arithmetic contract: every operation that decides a hit is spelled with
+// round-to-nearest intrinsics in a fixed order, so first-hit ids are bit-identical to the
+// CPU restatement: slab test = (lo-o)*idir per plane, far side padded by 1+2^-21;
+// triangle test = Woop/Benthin/Wald 2013 with a double-precision fallback on zero edge
+// functions; closest hit = lexicographic minimum of (t, instance, primitive).
+#pragma once
+#include "common.cuh"
+
+namespace lp {
+
+struct RayCtx {
+  f3 o, d, idir;
+  int kx, ky, kz;
+  float sx, sy, sz;
+};
+
+__device__ __forceinline__ float safe_rcp_dir(float d) {
+  const float dd = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
+  return __fdiv_rn(1.0f, dd);
+}
+
+__device__ __forceinline__ void ray_setup(RayCtx &r, f3 o, f3 d) {
+  r.o = o;
+  r.d = d;
+  r.idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  int kz = 0;
+  if (ay > ax) kz = 1;
+  if (az > fmaxf(ax, ay)) kz = 2;
+  int kx = kz == 2 ? 0 : kz + 1;
+  int ky = kx == 2 ? 0 : kx + 1;
+  const float dz = sel(d, kz);
+  if (dz < 0.0f) {
+    const int t = kx;
+    kx = ky;
+    ky = t;
+  }
+  r.kx = kx;
+  r.ky = ky;
+  r.kz = kz;
+  r.sx = __fdiv_rn(sel(d, kx), dz);
+  r.sy = __fdiv_rn(sel(d, ky), dz);
+  r.sz = __fdiv_rn(1.0f, dz);
+}
+
+// world -> object with the rows of a 3x4 matrix
+__device__ __forceinline__ f3 xform_point(float4 r0, float4 r1, float4 r2, f3 p) {
+  return mk3(__fmaf_rn(r0.x, p.x, __fmaf_rn(r0.y, p.y, __fmaf_rn(r0.z, p.z, r0.w))),
+             __fmaf_rn(r1.x, p.x, __fmaf_rn(r1.y, p.y, __fmaf_rn(r1.z, p.z, r1.w))),
+             __fmaf_rn(r2.x, p.x, __fmaf_rn(r2.y, p.y, __fmaf_rn(r2.z, p.z, r2.w))));
+}
+__device__ __forceinline__ f3 xform_vector(float4 r0, float4 r1, float4 r2, f3 v) {
+  return mk3(__fmaf_rn(r0.x, v.x, __fmaf_rn(r0.y, v.y, __fmul_rn(r0.z, v.z))),
+             __fmaf_rn(r1.x, v.x, __fmaf_rn(r1.y, v.y, __fmul_rn(r1.z, v.z))),
+             __fmaf_rn(r2.x, v.x, __fmaf_rn(r2.y, v.y, __fmul_rn(r2.z, v.z))));
+}
+
+__device__ __forceinline__ bool box_test(const RayCtx &r, f3 lo, f3 hi, float tmin, float tmax,
+                                         float &tnear) {
+  const float t0x = __fmul_rn(__fsub_rn(lo.x, r.o.x), r.idir.x);
+  const float t1x = __fmul_rn(__fsub_rn(hi.x, r.o.x), r.idir.x);
+  const float t0y = __fmul_rn(__fsub_rn(lo.y, r.o.y), r.idir.y);
+  const float t1y = __fmul_rn(__fsub_rn(hi.y, r.o.y), r.idir.y);
+  const float t0z = __fmul_rn(__fsub_rn(lo.z, r.o.z), r.idir.z);
+  const float t1z = __fmul_rn(__fsub_rn(hi.z, r.o.z), r.idir.z);
+  float tn = fmaxf(tmin, fminf(t0x, t1x));
+  float tf = fminf(tmax, fmaxf(t0x, t1x));
+  tn = fmaxf(tn, fminf(t0y, t1y));
+  tf = fminf(tf, fmaxf(t0y, t1y));
+  tn = fmaxf(tn, fminf(t0z, t1z));
+  tf = fminf(tf, fmaxf(t0z, t1z));
+  tnear = tn;
+  return tn <= __fmul_rn(tf, 1.0000004f);
+}
+
+__device__ __forceinline__ bool tri_test(const RayCtx &r, float4 p0, float4 p1, float4 p2,
+                                         float tmin, float tmax, float &t_out, float &u_out,
+                                         float &v_out) {
+  const f3 A = mk3(__fsub_rn(p0.x, r.o.x), __fsub_rn(p0.y, r.o.y), __fsub_rn(p0.z, r.o.z));
+  const f3 B = mk3(__fsub_rn(p1.x, r.o.x), __fsub_rn(p1.y, r.o.y), __fsub_rn(p1.z, r.o.z));
+  const f3 C = mk3(__fsub_rn(p2.x, r.o.x), __fsub_rn(p2.y, r.o.y), __fsub_rn(p2.z, r.o.z));
+  const float Akz = sel(A, r.kz), Bkz = sel(B, r.kz), Ckz = sel(C, r.kz);
+  const float Ax = __fmaf_rn(-r.sx, Akz, sel(A, r.kx)), Ay = __fmaf_rn(-r.sy, Akz, sel(A, r.ky));
+  const float Bx = __fmaf_rn(-r.sx, Bkz, sel(B, r.kx)), By = __fmaf_rn(-r.sy, Bkz, sel(B, r.ky));
+  const float Cx = __fmaf_rn(-r.sx, Ckz, sel(C, r.kx)), Cy = __fmaf_rn(-r.sy, Ckz, sel(C, r.ky));
+  float U = __fmaf_rn(Cx, By, -__fmul_rn(Cy, Bx));
+  float V = __fmaf_rn(Ax, Cy, -__fmul_rn(Ay, Cx));
+  float W = __fmaf_rn(Bx, Ay, -__fmul_rn(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
+    V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
+    W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  const float det = __fadd_rn(__fadd_rn(U, V), W);
+  if (det == 0.0f) return false;
+  const float Az = __fmul_rn(r.sz, Akz), Bz = __fmul_rn(r.sz, Bkz), Cz = __fmul_rn(r.sz, Ckz);
+  const float T = __fmaf_rn(U, Az, __fmaf_rn(V, Bz, __fmul_rn(W, Cz)));
+  const float rcp = __fdiv_rn(1.0f, det);
+  const float t = __fmul_rn(T, rcp);
+  if (!(t > tmin && t <= tmax)) return false;
+  t_out = t;
+  u_out = __fmul_rn(V, rcp);
+  v_out = __fmul_rn(W, rcp);
+  return true;
+}
+
+struct Hit {
+  float t, u, v;
+  uint32_t inst, prim;
+};
+
+__device__ __forceinline__ bool hit_better(float t, uint32_t inst, uint32_t prim, const Hit &h) {
+  if (t < h.t) return true;
+  if (t > h.t) return false;
+  if (inst != h.inst) return inst < h.inst;
+  return prim < h.prim;
+}
+
+// cnt[0] += interior nodes tested, cnt[1] += triangles tested, cnt[2] += instances entered
+template <bool ANY, bool STATS>
+__device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float tmin, float tmax,
+                                         Hit &hit, uint32_t *cnt) {
+  hit.t = tmax;
+  hit.u = hit.v = 0.0f;
+  hit.inst = LP_INVALID_INDEX;
+  hit.prim = LP_INVALID_INDEX;
+  uint32_t cur = sc.tlas_root;
+  if (cur == kNoChildRef) return false;
+
+  uint32_t stack[kStackSize];
+  int sp = 0;
+  RayCtx r;
+  ray_setup(r, wo, wd);
+  bool in_blas = false;
+  uint32_t inst = 0;
+
+  for (;;) {
+    if (!(cur & kLeaf)) {
+      const float4 *np = sc.nodes + 4u * (size_t)cur;
+      const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+      if (STATS) cnt[0]++;
+      const float limit = ANY ? tmax : hit.t;
+      float t0, t1;
+      const bool h0 = box_test(r, mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), tmin, limit, t0);
+      const bool h1 = box_test(r, mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), tmin, limit, t1);
+      const uint32_t c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
+      if (h0 && h1) {
+        const bool swap = t1 < t0;
+        stack[sp++] = swap ? c0 : c1;
+        cur = swap ? c1 : c0;
+        continue;
+      }
+      if (h0) {
+        cur = c0;
+        continue;
+      }
+      if (h1) {
+        cur = c1;
+        continue;
+      }
+    } else if (!in_blas) {
+      // TLAS leaf: enter the instance (ray -> object space, t is preserved)
+      inst = cur & 0x0FFFFFFFu;
+      const float4 *ip = sc.instances + 8u * (size_t)inst;
+      const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+      const uint32_t root = __float_as_uint(__ldg(ip + 6).x);
+      if (STATS) cnt[2]++;
+      ray_setup(r, xform_point(r0, r1, r2, wo), xform_vector(r0, r1, r2, wd));
+      stack[sp++] = kSentinel;
+      in_blas = true;
+      cur = root;
+      continue;
+    } else {
+      const uint32_t first = cur & 0x0FFFFFFFu;
+      const uint32_t count = ((cur >> 28) & 7u) + 1u;
+      for (uint32_t k = 0; k < count; ++k) {
+        const float4 *tp = sc.tris + 3u * (size_t)(first + k);
+        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+        if (STATS) cnt[1]++;
+        float t, u, v;
+        if (tri_test(r, p0, p1, p2, tmin, ANY ? tmax : hit.t, t, u, v)) {
+          if (ANY) return true;
+          const uint32_t prim = __float_as_uint(p0.w);
+          if (hit_better(t, inst, prim, hit)) {
+            hit.t = t;
+            hit.u = u;
+            hit.v = v;
+            hit.inst = inst;
+            hit.prim = prim;
+          }
+        }
+      }
+    }
+    // pop
+    if (sp == 0) break;
+    cur = stack[--sp];
+    if (cur == kSentinel) {
+      in_blas = false;
+      ray_setup(r, wo, wd);
+      if (sp == 0) break;
+      cur = stack[--sp];
+    }
+  }
+  return false;
+}
+
+// Analytic quad lights: front face only, never occluders.  Mirrors the expression order
+// of the CPU restatement so that t compares identically.
+__device__ __forceinline__ void lights_closest(const SceneDev &sc, f3 o, f3 d, float tmin,
+                                               Hit &hit) {
+  for (uint32_t i = 0; i < sc.n_active_lights; ++i) {
+    const uint32_t k = sc.active_lights[i];
+    const float4 *lp = sc.lights + 4u * (size_t)k;
+    const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+    const f3 c = mk3(l0.x, l0.y, l0.z), tg = mk3(l1.x, l1.y, l1.z), bt = mk3(l2.x, l2.y, l2.z);
+    const f3 n = cross(tg, bt);
+    const float denom = dot(n, d);
+    if (!(denom < 0.0f)) continue;
+    const f3 oc = c - o;
+    const float t = dot(n, oc) / denom;
+    if (!(t > tmin)) continue;
+    const f3 p = mk3(o.x + t * d.x - c.x, o.y + t * d.y - c.y, o.z + t * d.z - c.z);
+    const float a = dot(p, tg) / dot(tg, tg);
+    const float b = dot(p, bt) / dot(bt, bt);
+    if (fabsf(a) > 1.0f || fabsf(b) > 1.0f) continue;
+    if (hit_better(t, kLightInstance, k, hit)) {
+      hit.t = t;
+      hit.u = a;
+      hit.v = b;
+      hit.inst = kLightInstance;
+      hit.prim = k;
+    }
+  }
+}
+
+}  // namespace lp

@@ -1,0 +1,298 @@
+// Host scene: Scene::default, BLASArray::add_bvh[_indexed]/add_instance, TLAS build and
+// the re-layout of the canonical BVH2 into the 64-byte GPU node format.
+// [ref crates/lib/src/scene.rs:30-54, loaders/gltf.rs:91-105,141-145, loaders/binary.rs:49-61]
+#include "scene.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace lp {
+
+static const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+
+Scene::Scene() {
+  // Scene::default(): index 0 of every array is a dummy [ref scene.rs:37-54].
+  lp_material m{};
+  m.color[0] = m.color[1] = m.color[2] = m.color[3] = 1.f;
+  m.roughness = 1.f;
+  m.reflectivity = 0.f;
+  m.albedo_texture = LP_INVALID_INDEX;
+  m.mra_texture = LP_INVALID_INDEX;
+  materials.push_back(m);
+  emission.push_back({0.f, 0.f, 0.f, 0.f});
+  lp_blas_entry e{};
+  e.node_offset = 0;
+  e.node_count = 1;
+  e.primitive_offset = 0;
+  e.primitive_count = 0;
+  e.vertex_offset = 0;
+  e.vertex_count = 1;
+  e.index_offset = 0;
+  e.index_count = 0;
+  entries.push_back(e);
+  nodes.push_back(lp_bvh_node{});
+  primitives.push_back(lp_bvh_primitive{});
+  vertices.push_back(lp_vertex{});
+  lp_instance inst{};
+  std::memcpy(inst.model_to_world, kIdentity, sizeof(kIdentity));
+  std::memcpy(inst.world_to_model, kIdentity, sizeof(kIdentity));
+  instances.push_back(inst);
+  lp_light l{};  // Light::new(): inactive placeholder (intensity 0)
+  l.tangent[0] = 1.f;
+  l.bitangent[2] = 1.f;
+  l.color[0] = l.color[1] = l.color[2] = 1.f;
+  lights.push_back(l);
+}
+
+uint32_t Scene::add_bvh(const void *positions, size_t pstride, const void *normals, size_t nstride,
+                        const void *uvs, size_t uvstride, size_t vertex_count,
+                        const uint32_t *idx, size_t index_count) {
+  if (!positions || pstride < 12) throw std::invalid_argument("positions missing or stride < 12");
+  if (normals && nstride < 12) throw std::invalid_argument("normal stride < 12");
+  if (uvs && uvstride < 8) throw std::invalid_argument("uv stride < 8");
+  const size_t tri_count = idx ? index_count / 3 : vertex_count / 3;
+  if (tri_count >= (1u << 28)) throw std::invalid_argument("too many triangles in one BLAS");
+  if (idx)
+    for (size_t i = 0; i < tri_count * 3; ++i)
+      if (idx[i] >= vertex_count) throw std::invalid_argument("index out of range");
+
+  lp_blas_entry e{};
+  e.vertex_offset = (uint32_t)vertices.size();
+  e.vertex_count = (uint32_t)vertex_count;
+  e.index_offset = (uint32_t)indices.size();
+  e.index_count = (uint32_t)(tri_count * 3);
+  e.primitive_offset = (uint32_t)primitives.size();
+  e.primitive_count = (uint32_t)tri_count;
+  e.node_offset = (uint32_t)nodes.size();
+
+  const uint8_t *pp = (const uint8_t *)positions;
+  const uint8_t *np = (const uint8_t *)normals;
+  const uint8_t *tp = (const uint8_t *)uvs;
+  vertices.reserve(vertices.size() + vertex_count);
+  for (size_t i = 0; i < vertex_count; ++i) {
+    lp_vertex v{};
+    std::memcpy(v.position, pp + i * pstride, 12);
+    if (np) std::memcpy(v.normal, np + i * nstride, 12);
+    if (tp) {
+      float uv[2];
+      std::memcpy(uv, tp + i * uvstride, 8);
+      v.u = uv[0];
+      v.v = uv[1];
+    }
+    vertices.push_back(v);
+  }
+  indices.reserve(indices.size() + tri_count * 3);
+  for (size_t i = 0; i < tri_count * 3; ++i) indices.push_back(idx ? idx[i] : (uint32_t)i);
+
+  std::vector<BuildBox> boxes(tri_count);
+  const lp_vertex *vb = vertices.data() + e.vertex_offset;
+  const uint32_t *ib = indices.data() + e.index_offset;
+  for (size_t t = 0; t < tri_count; ++t) {
+    BuildBox b;
+    for (int a = 0; a < 3; ++a) {
+      const float p0 = vb[ib[3 * t]].position[a], p1 = vb[ib[3 * t + 1]].position[a],
+                  p2 = vb[ib[3 * t + 2]].position[a];
+      b.lo[a] = std::min(p0, std::min(p1, p2));
+      b.hi[a] = std::max(p0, std::max(p1, p2));
+      if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a]))
+        throw std::invalid_argument("non-finite vertex position");
+    }
+    boxes[t] = b;
+  }
+  std::vector<lp_bvh_node> tree;
+  std::vector<uint32_t> perm;
+  build_bvh2(boxes, 4, tree, perm);
+  e.node_count = (uint32_t)tree.size();
+  nodes.insert(nodes.end(), tree.begin(), tree.end());
+  primitives.reserve(primitives.size() + tri_count);
+  for (size_t k = 0; k < tri_count; ++k) {
+    const uint32_t t = perm[k];
+    lp_bvh_primitive p{};
+    std::memcpy(p.v0, vb[ib[3 * t]].position, 12);
+    std::memcpy(p.v1, vb[ib[3 * t + 1]].position, 12);
+    std::memcpy(p.v2, vb[ib[3 * t + 2]].position, 12);
+    std::memcpy(&p.v0[3], &t, 4);
+    primitives.push_back(p);
+  }
+  entries.push_back(e);
+  derived_dirty = true;
+  return (uint32_t)entries.size() - 1;
+}
+
+void Scene::add_instance(uint32_t blas, const float m[16], uint32_t material) {
+  lp_instance inst{};
+  std::memcpy(inst.model_to_world, m, 64);
+  invert_affine(m, inst.world_to_model);
+  inst.material = material;
+  inst.blas = blas;
+  instances.push_back(inst);
+  derived_dirty = true;
+}
+
+void Scene::set_instance_transform(uint32_t i, const float m[16]) {
+  std::memcpy(instances[i].model_to_world, m, 64);
+  invert_affine(m, instances[i].world_to_model);
+  derived_dirty = true;
+}
+
+namespace {
+
+inline void xform_point(const float m[16], const float p[3], float out[3]) {
+  for (int r = 0; r < 3; ++r) out[r] = m[r] * p[0] + m[4 + r] * p[1] + m[8 + r] * p[2] + m[12 + r];
+}
+
+struct LeafEncoder {
+  bool tlas;
+  uint32_t prim_base;  // global offset of the BLAS's first triangle
+  uint32_t operator()(const lp_bvh_node &n) const {
+    if (tlas) return kLeafBit | n.left_first;
+    return kLeafBit | ((n.count - 1u) << 28) | (prim_base + n.left_first);
+  }
+};
+
+inline void put_box(GpuNode &g, int slot, const lp_bvh_node *n) {
+  float lo[3], hi[3];
+  if (n) {
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = n->aabb_min[a];
+      hi[a] = n->aabb_max[a];
+    }
+  } else {
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = INFINITY;
+      hi[a] = -INFINITY;
+    }
+  }
+  if (slot == 0) {
+    g.q[0] = lo[0]; g.q[1] = lo[1]; g.q[2] = lo[2];
+    g.q[3] = hi[0]; g.q[4] = hi[1]; g.q[5] = hi[2];
+  } else {
+    g.q[6] = lo[0]; g.q[7] = lo[1]; g.q[8] = lo[2];
+    g.q[9] = hi[0]; g.q[10] = hi[1]; g.q[11] = hi[2];
+  }
+}
+
+// Re-lay one canonical tree out in BFS order (top levels contiguous -> they stay hot in
+// L2/L1).  `root_index` receives a child REFERENCE (interior index, leaf, or kNoChild for
+// an empty tree).  Returns the depth of the tree (root = 1).
+uint32_t relayout(const lp_bvh_node *tree, const LeafEncoder &enc, std::vector<GpuNode> &out,
+                  uint32_t &root_index) {
+  if (tree[0].count > 0) {  // single-leaf tree: the root reference IS the leaf
+    root_index = enc(tree[0]);
+    return 1;
+  }
+  if (tree[0].left_first == 0) {  // empty tree
+    root_index = kNoChild;
+    return 0;
+  }
+  root_index = (uint32_t)out.size();
+  const uint32_t base = root_index;
+  struct Item {
+    uint32_t canon, depth;
+  };
+  std::vector<Item> queue;
+  queue.push_back({0u, 1u});
+  uint32_t max_depth = 1;
+  // GPU index of the i-th queued interior node = base + i
+  for (size_t head = 0; head < queue.size(); ++head) {
+    const Item it = queue[head];
+    const lp_bvh_node &n = tree[it.canon];
+    GpuNode g{};
+    for (int c = 0; c < 2; ++c) {
+      const lp_bvh_node &ch = tree[n.left_first + c];
+      put_box(g, c, &ch);
+      if (ch.count > 0) {
+        g.child[c] = enc(ch);
+      } else {
+        g.child[c] = base + (uint32_t)queue.size();
+        queue.push_back({n.left_first + (uint32_t)c, it.depth + 1});
+      }
+      max_depth = std::max(max_depth, it.depth + 1);
+    }
+    out.push_back(g);
+  }
+  return max_depth;
+}
+
+}  // namespace
+
+void Scene::build_derived() {
+  if (!derived_dirty) return;
+  // ---- TLAS over instances that reference a non-empty BLAS
+  std::vector<BuildBox> boxes;
+  std::vector<uint32_t> ids;
+  for (uint32_t i = 0; i < instances.size(); ++i) {
+    const lp_instance &inst = instances[i];
+    if (inst.blas >= entries.size()) throw std::invalid_argument("instance references unknown BLAS");
+    const lp_blas_entry &e = entries[inst.blas];
+    if (e.primitive_count == 0) continue;
+    const lp_bvh_node &root = nodes[e.node_offset];
+    BuildBox b;
+    for (int a = 0; a < 3; ++a) {
+      b.lo[a] = FLT_MAX;
+      b.hi[a] = -FLT_MAX;
+    }
+    for (int c = 0; c < 8; ++c) {
+      const float p[3] = {(c & 1) ? root.aabb_max[0] : root.aabb_min[0],
+                          (c & 2) ? root.aabb_max[1] : root.aabb_min[1],
+                          (c & 4) ? root.aabb_max[2] : root.aabb_min[2]};
+      float w[3];
+      xform_point(inst.model_to_world, p, w);
+      for (int a = 0; a < 3; ++a) {
+        b.lo[a] = std::min(b.lo[a], w[a]);
+        b.hi[a] = std::max(b.hi[a], w[a]);
+      }
+    }
+    // pad by a few ulps: the box is transformed in float, the rays in float too.
+    for (int a = 0; a < 3; ++a) {
+      const float pad = 4.f * FLT_EPSILON * std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
+      b.lo[a] -= pad;
+      b.hi[a] += pad;
+    }
+    boxes.push_back(b);
+    ids.push_back(i);
+  }
+  std::vector<uint32_t> perm;
+  build_bvh2(boxes, 1, tlas, perm);
+  for (auto &n : tlas)
+    if (n.count > 0) n.left_first = ids[perm[n.left_first]];
+
+  // ---- GPU layout: [TLAS | BLAS 1 | BLAS 2 | ...], each tree in BFS order
+  gpu_nodes.clear();
+  gpu_nodes.reserve(tlas.size() + nodes.size());
+  LeafEncoder tenc{true, 0};
+  uint32_t tdepth = relayout(tlas.data(), tenc, gpu_nodes, gpu_tlas_root);
+  std::vector<uint32_t> blas_root(entries.size(), 0);
+  uint32_t bdepth = 0;
+  for (size_t e = 0; e < entries.size(); ++e) {
+    if (entries[e].primitive_count == 0) continue;
+    LeafEncoder benc{false, entries[e].primitive_offset};
+    uint32_t d = relayout(nodes.data() + entries[e].node_offset, benc, gpu_nodes, blas_root[e]);
+    bdepth = std::max(bdepth, d);
+  }
+  gpu_max_depth = tdepth + bdepth + 1;
+  if (primitives.size() >= (1u << 28)) throw std::invalid_argument("too many triangles (>= 2^28)");
+
+  gpu_instances.assign(instances.size(), GpuInstance{});
+  for (size_t i = 0; i < instances.size(); ++i) {
+    const lp_instance &s = instances[i];
+    GpuInstance &g = gpu_instances[i];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) {
+        g.w2o[4 * r + c] = s.world_to_model[4 * c + r];
+        g.o2w[4 * r + c] = s.model_to_world[4 * c + r];
+      }
+    const lp_blas_entry &e = entries[s.blas];
+    g.root = blas_root[s.blas];
+    g.material = s.material;
+    g.index_offset = e.index_offset;
+    g.vertex_offset = e.vertex_offset;
+    g.blas = s.blas;
+  }
+  derived_dirty = false;
+}
+
+}  // namespace lp

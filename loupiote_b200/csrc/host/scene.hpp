@@ -1,0 +1,89 @@
+// Host-side scene model: the B200 build's `Scene` / `BLASArray`
+// [ref crates/lib/src/scene.rs:30-54] plus the GPU re-layout of the canonical tree.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "loupiote.h"
+
+namespace lp {
+
+// 64-byte traversal node: both child boxes + child references, fetched as 4x LDG.128.
+//   q0 = {lo0.x, lo0.y, lo0.z, hi0.x}  q1 = {hi0.y, hi0.z, lo1.x, lo1.y}
+//   q2 = {lo1.z, hi1.x, hi1.y, hi1.z}  q3 = {child0, child1, 0, 0} (uint bits)
+// child reference: bit31 clear -> interior node (global index); bit31 set -> leaf:
+//   BLAS leaf: bits 30..28 = count-1, bits 27..0 = first triangle (global index)
+//   TLAS leaf: bits 27..0 = instance index.   LP_GPU_NO_CHILD = empty slot.
+struct GpuNode {
+  float q[12];
+  uint32_t child[2];
+  uint32_t pad[2];
+};
+static_assert(sizeof(GpuNode) == 64, "GpuNode must be 64 bytes");
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kNoChild = 0x7FFFFFFFu;
+
+// 128-byte instance record: rows of world->object and object->world 3x4 + ids.
+struct GpuInstance {
+  float w2o[12];
+  float o2w[12];
+  uint32_t root;          // child reference of the BLAS root (interior index or leaf)
+  uint32_t material;
+  uint32_t index_offset;  // global offset into indices (3 per triangle)
+  uint32_t vertex_offset; // global offset into vertices
+  uint32_t blas;
+  uint32_t pad[3];
+};
+static_assert(sizeof(GpuInstance) == 128, "GpuInstance must be 128 bytes");
+
+struct Image {
+  std::vector<uint8_t> data;
+  uint32_t width = 0, height = 0;
+};
+
+struct Scene {
+  std::vector<lp_material> materials;
+  std::vector<std::array<float, 4>> emission;
+  std::vector<lp_blas_entry> entries;
+  std::vector<lp_bvh_node> nodes;
+  std::vector<lp_bvh_primitive> primitives;
+  std::vector<lp_vertex> vertices;
+  std::vector<uint32_t> indices;
+  std::vector<lp_instance> instances;
+  std::vector<lp_light> lights;
+  std::vector<Image> images;
+
+  // derived (rebuilt lazily)
+  std::vector<lp_bvh_node> tlas;
+  std::vector<GpuNode> gpu_nodes;
+  std::vector<GpuInstance> gpu_instances;
+  uint32_t gpu_tlas_root = 0;  // child reference (interior index, leaf, or kNoChild)
+  uint32_t gpu_max_depth = 0;
+  bool derived_dirty = true;
+
+  Scene();
+  uint32_t add_bvh(const void *positions, size_t pstride, const void *normals, size_t nstride,
+                   const void *uvs, size_t uvstride, size_t vertex_count, const uint32_t *indices,
+                   size_t index_count);
+  void add_instance(uint32_t blas, const float m[16], uint32_t material);
+  void set_instance_transform(uint32_t instance, const float m[16]);
+  void build_derived();  // TLAS + GPU layout
+};
+
+// Binned-SAH BVH2 over boxes (16 bins, all three axes, traversal cost 1, intersection
+// cost 1).  `perm` receives the primitive order; nodes are appended to `out` with
+// child / primitive indices relative to the tree's own origin.
+struct BuildBox {
+  float lo[3], hi[3];
+};
+void build_bvh2(const std::vector<BuildBox> &boxes, uint32_t max_leaf, std::vector<lp_bvh_node> &out,
+                std::vector<uint32_t> &perm);
+
+void invert_affine(const float m[16], float inv[16]);
+
+lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string &err);
+lp_status load_binary(const char *path, Scene &scene, std::string &err);
+
+}  // namespace lp
