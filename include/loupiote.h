@@ -348,6 +348,17 @@ LP_API lp_status lp_renderer_camera(const lp_renderer *r, lp_camera *out,
  * 2 history (R32F), 3 gbuffer (RGBA32U), 4 motion (RG32F), 5 sample radiance (RGBA32F). */
 LP_API lp_status lp_renderer_read_aux(lp_renderer *r, int which, void *out, size_t cap_bytes);
 
+/* Measurement hooks.  Kernel classes: 0 = extend (closest hit), 1 = shade, 2 = connect
+ * (any hit), 3 = everything else (generate, accumulate, SVGF, tone-map).  Launch counts are
+ * always kept; per-launch CUDA-event timing (on the device stream) is opt-in.
+ * lp_renderer_kernel_times synchronises. */
+LP_API lp_status lp_renderer_set_kernel_timing(lp_renderer *r, int flag);
+LP_API lp_status lp_renderer_kernel_times(lp_renderer *r, double ms[4], uint64_t launches[4],
+                                          int reset);
+/* FP32 FMA throughput microbenchmark (TFLOP/s, best of `repeats`), the second roofline
+ * denominator of SURVEY 8(d). */
+LP_API lp_status lp_device_fp32_peak(lp_device *dev, int repeats, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,10 @@ _PROTOTYPES = {
     "lp_renderer_set_sample_count": (C.c_int, [_vp, C.c_uint32]),
     "lp_renderer_camera": (C.c_int, [_vp, C.POINTER(Camera), c_float_p]),
     "lp_renderer_read_aux": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t]),
+    "lp_renderer_set_kernel_timing": (C.c_int, [_vp, C.c_int]),
+    "lp_renderer_kernel_times": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                           C.c_int]),
+    "lp_device_fp32_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

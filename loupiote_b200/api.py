@@ -99,6 +99,11 @@ class Device:
     def synchronize(self) -> None:
         _check(_ffi.lib().lp_device_synchronize(self._h))
 
+    def fp32_peak_tflops(self, repeats: int = 5) -> float:
+        out = C.c_double()
+        _check(_ffi.lib().lp_device_fp32_peak(self._h, repeats, C.byref(out)))
+        return out.value
+
     def info(self) -> dict:
         name = C.create_string_buffer(256)
         sm, major, minor, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
@@ -475,6 +480,18 @@ class Renderer:
         _check(_ffi.lib().lp_renderer_ray_counters(self._h, C.byref(c), int(reset)))
         return {"primary": c.primary, "bounce": c.bounce, "shadow": c.shadow,
                 "n_int": list(c.n_int), "n_tri": list(c.n_tri), "n_inst": list(c.n_inst)}
+
+    KERNEL_CLASSES = ("extend", "shade", "connect", "other")
+
+    def set_kernel_timing(self, flag: bool) -> None:
+        _check(_ffi.lib().lp_renderer_set_kernel_timing(self._h, int(bool(flag))))
+
+    def kernel_times(self, reset: bool = False) -> dict:
+        """{class: (total ms, launches)} since the last reset; timing needs set_kernel_timing."""
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        _check(_ffi.lib().lp_renderer_kernel_times(self._h, ms, n, int(reset)))
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def accum_device_ptr(self):
         """(device pointer, float count, samples) of the FP32 SUM accumulator."""

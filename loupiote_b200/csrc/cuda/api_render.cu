@@ -134,6 +134,14 @@ struct lp_renderer {
   std::vector<double> q_ms;
   int q_open = -1;
 
+  // measurement hooks
+  bool kt_enabled = false;
+  std::vector<cudaEvent_t> kt_events;  // pairs
+  std::vector<int> kt_kind;
+  size_t kt_used = 0;
+  double kt_ms[4] = {0, 0, 0, 0};
+  uint64_t kt_launches[4] = {0, 0, 0, 0};
+
   int grid_extend = 0, grid_extend_stats = 0, grid_connect = 0, grid_connect_stats = 0,
       grid_shade = 0;
 };
@@ -269,6 +277,55 @@ void query_end(lp_renderer *r) {
   if (r->q_open < 0) return;
   cudaEventRecord(r->ev[r->q_open][1], r->dev->stream);
   r->q_open = -1;
+}
+
+constexpr size_t kKtPool = 2048;
+
+void kt_drain(lp_renderer *r) {
+  if (!r->kt_used) return;
+  cudaStreamSynchronize(r->dev->stream);
+  for (size_t i = 0; i < r->kt_used; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r->kt_events[2 * i], r->kt_events[2 * i + 1]) == cudaSuccess)
+      r->kt_ms[r->kt_kind[i]] += t;
+  }
+  r->kt_used = 0;
+}
+
+// Brackets one kernel launch: counts it and, when timing is on, wraps it in an event pair.
+struct KtScope {
+  lp_renderer *r;
+  bool timed;
+  KtScope(lp_renderer *rr, int kind) : r(rr), timed(false) {
+    r->kt_launches[kind]++;
+    if (!r->kt_enabled) return;
+    if (r->kt_events.empty()) {
+      r->kt_events.resize(2 * kKtPool, nullptr);
+      r->kt_kind.resize(kKtPool, 0);
+      for (auto &e : r->kt_events) cudaEventCreate(&e);
+    }
+    if (r->kt_used == kKtPool) kt_drain(r);
+    r->kt_kind[r->kt_used] = kind;
+    cudaEventRecord(r->kt_events[2 * r->kt_used], r->dev->stream);
+    timed = true;
+  }
+  ~KtScope() {
+    if (!timed) return;
+    cudaEventRecord(r->kt_events[2 * r->kt_used + 1], r->dev->stream);
+    r->kt_used++;
+  }
+};
+
+__global__ void fma_peak_kernel(float *out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+    a0 = __fmaf_rn(a0, b, c); a1 = __fmaf_rn(a1, b, c); a2 = __fmaf_rn(a2, b, c);
+    a3 = __fmaf_rn(a3, b, c); a4 = __fmaf_rn(a4, b, c); a5 = __fmaf_rn(a5, b, c);
+    a6 = __fmaf_rn(a6, b, c); a7 = __fmaf_rn(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 __global__ void gather_sample_kernel(const float4 *__restrict__ rad, float4 *__restrict__ out,
@@ -508,6 +565,8 @@ LP_API lp_status lp_renderer_destroy(lp_renderer *r) {
   for (int i = 0; i < lp_renderer::kMaxQueries; ++i)
     for (int k = 0; k < 2; ++k)
       if (r->ev[i][k]) cudaEventDestroy(r->ev[i][k]);
+  for (auto &e : r->kt_events)
+    if (e) cudaEventDestroy(e);
   delete r;
   return LP_OK;
 }
@@ -625,34 +684,39 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
     CUDA_CHECK(cudaMemsetAsync(r->counts.ptr, 0, kCntTotal * sizeof(uint32_t), st));
 
     if (first_wave) query_start(r, "ray generation");  // [ref renderer.rs:444]
-    generate_kernel<<<sm * 8, 256, 0, st>>>(P);
+    { KtScope k(r, 3); generate_kernel<<<sm * 8, 256, 0, st>>>(P); }
     if (first_wave) query_end(r);
     for (uint32_t b = 0; b < cfg.max_bounces; ++b) {
       if (first_wave && b == 0) query_start(r, "primary intersection");  // [ref :457]
       if (first_wave && b == 1) query_start(r, "bounces");
-      if (stats) extend_kernel<true><<<r->grid_extend_stats, 128, 0, st>>>(P, b);
-      else extend_kernel<false><<<r->grid_extend, 128, 0, st>>>(P, b);
+      {
+        KtScope k(r, 0);
+        if (stats) extend_kernel<true><<<r->grid_extend_stats, 128, 0, st>>>(P, b);
+        else extend_kernel<false><<<r->grid_extend, 128, 0, st>>>(P, b);
+      }
       if (first_wave && b == 0) {
         query_end(r);
         query_start(r, "shading 0");  // [ref :471]
       }
-      shade_kernel<<<r->grid_shade, 128, 0, st>>>(P, b);
+      { KtScope k(r, 1); shade_kernel<<<r->grid_shade, 128, 0, st>>>(P, b); }
       if (P.sc.n_active_lights) {
+        KtScope k(r, 2);
         if (stats) connect_kernel<true><<<r->grid_connect_stats, 128, 0, st>>>(P, b, 0);
         else connect_kernel<false><<<r->grid_connect, 128, 0, st>>>(P, b, 0);
       }
       if (P.sc.env_on) {
+        KtScope k(r, 2);
         if (stats) connect_kernel<true><<<r->grid_connect_stats, 128, 0, st>>>(P, b, 1);
         else connect_kernel<false><<<r->grid_connect, 128, 0, st>>>(P, b, 1);
       }
       if (first_wave && b == 0) query_end(r);
     }
     if (first_wave && cfg.max_bounces > 1) query_end(r);
-    finalize_counts_kernel<<<1, 32, 0, st>>>(P);
+    { KtScope k(r, 3); finalize_counts_kernel<<<1, 32, 0, st>>>(P); }
 
     if (r->mode == LP_BLIT_PAHTRACE) {
       if (first_wave) query_start(r, "accumulation");
-      accumulate_kernel<<<sm * 8, 256, 0, st>>>(P);  // [ref renderer.rs:523-538]
+      { KtScope k(r, 3); accumulate_kernel<<<sm * 8, 256, 0, st>>>(P); }  // [ref renderer.rs:523-538]
       if (first_wave) query_end(r);
     }
     r->seed_cursor += S;
@@ -678,17 +742,20 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
     T.out_rad = r->pp[cur].radiance.ptr;
     T.out_mom = r->pp[cur].moments.ptr;
     T.out_hist = r->pp[cur].history.ptr;
-    svgf_temporal_kernel<<<sm * 8, 256, 0, st>>>(T);
+    { KtScope k(r, 3); svgf_temporal_kernel<<<sm * 8, 256, 0, st>>>(T); }
     if (r->mode == LP_BLIT_DENOISED_PATHRACE) {
       // a-trous ping-pong between `temp` and the main target [ref asvgf.rs:277-290]
       const float4 *src = r->pp[cur].radiance.ptr;
       for (uint32_t it = 0; it < cfg.atrous_iterations; ++it) {
         float4 *dst = (it & 1u) ? r->accum.ptr : r->temp.ptr;
-        svgf_atrous_kernel<<<sm * 8, 256, 0, st>>>(r->width, r->height, src,
-                                                   r->pp[cur].gbuffer.ptr, it, dst);
+        {
+          KtScope k(r, 3);
+          svgf_atrous_kernel<<<sm * 8, 256, 0, st>>>(r->width, r->height, src,
+                                                     r->pp[cur].gbuffer.ptr, it, dst);
+        }
         src = dst;
       }
-      svgf_composite_kernel<<<sm * 8, 256, 0, st>>>(n, src, r->pp[cur].gbuffer.ptr, r->accum.ptr);
+      { KtScope k(r, 3); svgf_composite_kernel<<<sm * 8, 256, 0, st>>>(n, src, r->pp[cur].gbuffer.ptr, r->accum.ptr); }
     }
     query_end(r);
   }
@@ -774,8 +841,11 @@ LP_API lp_status lp_renderer_read_pixels(lp_renderer *r, uint8_t *out, size_t ca
   const size_t n = (size_t)r->width * r->height;
   if (cap < n * 4) return fail(LP_ERR_READBACK, "output buffer too small");
   if (cudaSetDevice(r->dev->ordinal) != cudaSuccess) return fail(LP_ERR_READBACK, "cudaSetDevice");
-  tonemap_kernel<<<r->dev->sm_count * 8, 256, 0, r->dev->stream>>>(r->accum.ptr, r->ldr.ptr,
-                                                                   (uint32_t)n);
+  {
+    KtScope k(r, 3);
+    tonemap_kernel<<<r->dev->sm_count * 8, 256, 0, r->dev->stream>>>(r->accum.ptr, r->ldr.ptr,
+                                                                     (uint32_t)n);
+  }
   cudaError_t e = cudaMemcpyAsync(out, r->ldr.ptr, n * 4, cudaMemcpyDeviceToHost, r->dev->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(r->dev->stream);
   if (e != cudaSuccess) return fail(LP_ERR_READBACK, cudaGetErrorString(e));
@@ -895,6 +965,57 @@ LP_API lp_status lp_renderer_read_aux(lp_renderer *r, int which, void *out, size
   if (cap_bytes < bytes) return fail(LP_ERR_READBACK, "output buffer too small");
   CUDA_CHECK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, r->dev->stream));
   CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_set_kernel_timing(lp_renderer *r, int flag) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  if (!flag) kt_drain(r);
+  r->kt_enabled = flag != 0;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_kernel_times(lp_renderer *r, double ms[4], uint64_t launches[4],
+                                          int reset) {
+  if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  kt_drain(r);
+  for (int k = 0; k < 4; ++k) {
+    if (ms) ms[k] = r->kt_ms[k];
+    if (launches) launches[k] = r->kt_launches[k];
+    if (reset) {
+      r->kt_ms[k] = 0.0;
+      r->kt_launches[k] = 0;
+    }
+  }
+  return LP_OK;
+}
+
+LP_API lp_status lp_device_fp32_peak(lp_device *dev, int repeats, double *tflops) {
+  if (!dev || !tflops) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(dev->ordinal));
+  const int blocks = dev->sm_count * 8, threads = 256, iters = 1 << 15;
+  DevBuf<float> out;
+  CUDA_CHECK(out.alloc((size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < std::max(1, repeats) + 1; ++rep) {
+    cudaEventRecord(e0, dev->stream);
+    fma_peak_kernel<<<blocks, threads, 0, dev->stream>>>(out.ptr, iters);
+    cudaEventRecord(e1, dev->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CUDA_CHECK(cudaGetLastError());
+  *tflops = best;
   return LP_OK;
 }
 
