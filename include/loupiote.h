@@ -163,7 +163,7 @@ typedef struct lp_render_config {
   float env_color[3];        /* constant environment radiance when no probe is bound */
   float v_fov;               /* radians */
   uint32_t count_stats;      /* 1: traversal kernels also count n_int/n_tri/n_inst */
-  uint32_t sort_rays;        /* reserved */
+  uint32_t traversal_variant;/* 0 = production kernels; >0 = measured alternatives */
 } lp_render_config;
 
 /* Device-side ray counters (metric = primary+bounce+shadow rays actually traced). */

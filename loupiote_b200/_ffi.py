@@ -73,7 +73,7 @@ class RenderConfig(C.Structure):
                 ("atrous_iterations", C.c_uint32), ("jitter", C.c_uint32),
                 ("russian_roulette", C.c_uint32), ("sample_offset", C.c_uint32),
                 ("sample_stride", C.c_uint32), ("env_color", C.c_float * 3),
-                ("v_fov", C.c_float), ("count_stats", C.c_uint32), ("sort_rays", C.c_uint32)]
+                ("v_fov", C.c_float), ("count_stats", C.c_uint32), ("traversal_variant", C.c_uint32)]
 
 
 class RayCounters(C.Structure):

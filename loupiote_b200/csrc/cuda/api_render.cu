@@ -14,6 +14,7 @@
 #include "../host/scene.hpp"
 #include "kernels.cuh"
 #include "svgf.cuh"
+#include "trace_persistent.cuh"
 
 using namespace lp;
 
@@ -142,8 +143,7 @@ struct lp_renderer {
   double kt_ms[4] = {0, 0, 0, 0};
   uint64_t kt_launches[4] = {0, 0, 0, 0};
 
-  int grid_extend = 0, grid_extend_stats = 0, grid_connect = 0, grid_connect_stats = 0,
-      grid_shade = 0;
+  int grid_shade = 0;
 };
 
 namespace {
@@ -277,6 +277,69 @@ void query_end(lp_renderer *r) {
   if (r->q_open < 0) return;
   cudaEventRecord(r->ev[r->q_open][1], r->dev->stream);
   r->q_open = -1;
+}
+
+// Launch of the traversal kernels.  cfg.traversal_variant selects the implementation:
+//   0 (default) one ray per thread, warps pull 32-ray batches from a global cursor
+//               (kernels.cuh) -- the fastest measured so far
+//   1..         persistent warps with per-lane ray replacement and postponed triangle /
+//               instance-entry phases (trace_persistent.cuh) at several settings; measured
+//               slower on B200 (DESIGN.md "Measured alternatives"), kept for tuning runs
+template <typename K>
+int cached_grid(K kernel, int sm_count) {
+  static int grid = 0;  // one per instantiation
+  if (!grid) grid = persistent_grid(kernel, 128, sm_count);
+  return grid;
+}
+
+template <int TRI_MIN, int ENTRY_MIN, int REFILL_MIN, int MIN_BLOCKS>
+void launch_persistent(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, int env,
+                       bool stats) {
+  cudaStream_t st = r->dev->stream;
+  const int sm = r->dev->sm_count;
+  if (any) {
+    if (stats) {
+      auto k = trace_kernel<true, true, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
+      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+    } else {
+      auto k = trace_kernel<true, false, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
+      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+    }
+  } else {
+    if (stats) {
+      auto k = trace_kernel<false, true, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
+      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+    } else {
+      auto k = trace_kernel<false, false, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
+      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+    }
+  }
+}
+
+void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, int env,
+                  bool stats) {
+  cudaStream_t st = r->dev->stream;
+  const int sm = r->dev->sm_count;
+  switch (r->cfg.traversal_variant) {
+    default:
+      if (any) {
+        if (stats) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
+        else connect_kernel<false><<<cached_grid(connect_kernel<false>, sm), 128, 0, st>>>(P, b, env);
+      } else {
+        if (stats) extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
+        else extend_kernel<false><<<cached_grid(extend_kernel<false>, sm), 128, 0, st>>>(P, b);
+      }
+      break;
+    case 2: launch_persistent<16, 4, 4, 8>(r, P, b, any, env, stats); break;
+    case 3: launch_persistent<8, 4, 4, 10>(r, P, b, any, env, stats); break;
+    case 4: launch_persistent<16, 8, 8, 10>(r, P, b, any, env, stats); break;
+    case 5: launch_persistent<12, 4, 8, 10>(r, P, b, any, env, stats); break;
+    case 6: launch_persistent<8, 2, 4, 12>(r, P, b, any, env, stats); break;
+    case 7: launch_persistent<4, 2, 2, 8>(r, P, b, any, env, stats); break;
+    case 8: launch_persistent<20, 8, 4, 10>(r, P, b, any, env, stats); break;
+    case 9: launch_persistent<12, 6, 12, 10>(r, P, b, any, env, stats); break;
+    case 1: launch_persistent<8, 4, 4, 8>(r, P, b, any, env, stats); break;
+  }
 }
 
 constexpr size_t kKtPool = 2048;
@@ -544,10 +607,6 @@ LP_API lp_status lp_renderer_new(lp_device *dev, uint32_t width, uint32_t height
         delete r;
         return fail(LP_ERR_CUDA, "cudaEventCreate failed");
       }
-  r->grid_extend = persistent_grid(extend_kernel<false>, 128, dev->sm_count);
-  r->grid_extend_stats = persistent_grid(extend_kernel<true>, 128, dev->sm_count);
-  r->grid_connect = persistent_grid(connect_kernel<false>, 128, dev->sm_count);
-  r->grid_connect_stats = persistent_grid(connect_kernel<true>, 128, dev->sm_count);
   r->grid_shade = persistent_grid(shade_kernel, 128, dev->sm_count);
   lp_status st = allocate_targets(r);
   if (st != LP_OK) {
@@ -691,8 +750,7 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
       if (first_wave && b == 1) query_start(r, "bounces");
       {
         KtScope k(r, 0);
-        if (stats) extend_kernel<true><<<r->grid_extend_stats, 128, 0, st>>>(P, b);
-        else extend_kernel<false><<<r->grid_extend, 128, 0, st>>>(P, b);
+        launch_trace(r, P, b, false, 0, stats);
       }
       if (first_wave && b == 0) {
         query_end(r);
@@ -701,13 +759,11 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
       { KtScope k(r, 1); shade_kernel<<<r->grid_shade, 128, 0, st>>>(P, b); }
       if (P.sc.n_active_lights) {
         KtScope k(r, 2);
-        if (stats) connect_kernel<true><<<r->grid_connect_stats, 128, 0, st>>>(P, b, 0);
-        else connect_kernel<false><<<r->grid_connect, 128, 0, st>>>(P, b, 0);
+        launch_trace(r, P, b, true, 0, stats);
       }
       if (P.sc.env_on) {
         KtScope k(r, 2);
-        if (stats) connect_kernel<true><<<r->grid_connect_stats, 128, 0, st>>>(P, b, 1);
-        else connect_kernel<false><<<r->grid_connect, 128, 0, st>>>(P, b, 1);
+        launch_trace(r, P, b, true, 1, stats);
       }
       if (first_wave && b == 0) query_end(r);
     }

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128) extend_kernel(const __grid_constant__ Fra
       if (d.w >= 0.0f) {
         Hit hit;
         const f3 wo = mk3(o.x, o.y, o.z), wd = mk3(d.x, d.y, d.z);
-        traverse<false, STATS>(P.sc, wo, wd, 0.0f, INFINITY, hit, cnt);
+        traverse<false, STATS>(P.sc, wo, wd, INFINITY, hit, cnt);
         if (P.sc.n_active_lights) lights_closest(P.sc, wo, wd, 0.0f, hit);
         P.ps.hit[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
         P.ps.hit_inst[slot] = hit.inst;
@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(128) connect_kernel(const __grid_constant__ Fr
     if (idx < n) {
       const float4 o = q.o_tmax[idx], d = q.d_slot[idx];
       Hit hit;
-      const bool occluded = traverse<true, STATS>(P.sc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z),
-                                                  0.0f, o.w, hit, cnt);
+      const bool occluded =
+          traverse<true, STATS>(P.sc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), o.w, hit, cnt);
       if (!occluded) {
         const uint32_t slot = __float_as_uint(d.w);
         const float4 c = q.contrib[idx];

@@ -2,31 +2,48 @@
 // Replaces albedo_rtx IntersectorPass (closest hit) and the inline occlusion rays of
 // ShadingPass [ref crates/lib/src/renderer.rs:457-464,493-508].
 //
-// Arithmetic contract: every operation that decides a hit is spelled with
-// round-to-nearest intrinsics in a fixed order, so first-hit ids are bit-identical to the
-// CPU restatement: slab test = (lo-o)*idir per plane, far side padded by 1+2^-21;
-// triangle test = Woop/Benthin/Wald 2013 with a double-precision fallback on zero edge
-// functions; closest hit = lexicographic minimum of (t, instance, primitive).
+// Arithmetic contract: every operation that DECIDES a hit is spelled with
+// round-to-nearest intrinsics in a fixed order, so first-hit ids and (t,u,v) are
+// bit-identical to the CPU restatement:
+//   triangle test = Woop/Benthin/Wald 2013 (shear constants Sz = 1/d[kz], Sx = d[kx]*Sz,
+//                   Sy = d[ky]*Sz) with a double-precision fallback on zero edge functions;
+//   closest hit   = lexicographic minimum of (t, instance, primitive).
+// The slab test only has to be CONSERVATIVE (it decides what is visited, never what is
+// hit).  EXACT = true is the oracle's slab test ((lo-o)*idir with idir = 1/d correctly
+// rounded, far side padded by 1+2^-21): used by the STATS kernels so the canonical
+// traversal counters equal the oracle's.  EXACT = false uses MUFU reciprocals (<= 1 ulp)
+// and pads the far side by 1e-6 instead.
 #pragma once
 #include "common.cuh"
 
 namespace lp {
 
-struct RayCtx {
-  f3 o, d, idir;
-  int kx, ky, kz;
+struct LaneRay {
+  f3 o, idir;
   float sx, sy, sz;
+  int kxyz;  // kx | ky << 2 | kz << 4
 };
 
-__device__ __forceinline__ float safe_rcp_dir(float d) {
+template <bool EXACT>
+__device__ __forceinline__ float rcp_dir(float d) {
   const float dd = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
-  return __fdiv_rn(1.0f, dd);
+  if (EXACT) return __frcp_rn(dd);  // correctly rounded, == 1.0f / dd
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd));
+  return r;
 }
 
-__device__ __forceinline__ void ray_setup(RayCtx &r, f3 o, f3 d) {
+template <bool EXACT>
+__device__ __forceinline__ void lane_set_world(LaneRay &r, f3 o, f3 d) {
   r.o = o;
-  r.d = d;
-  r.idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+  r.idir = mk3(rcp_dir<EXACT>(d.x), rcp_dir<EXACT>(d.y), rcp_dir<EXACT>(d.z));
+}
+
+// object-space setup: slab reciprocals + the shear constants of the watertight test
+template <bool EXACT>
+__device__ __forceinline__ void lane_set_object(LaneRay &r, f3 o, f3 d) {
+  r.o = o;
+  r.idir = mk3(rcp_dir<EXACT>(d.x), rcp_dir<EXACT>(d.y), rcp_dir<EXACT>(d.z));
   const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
   int kz = 0;
   if (ay > ax) kz = 1;
@@ -39,12 +56,10 @@ __device__ __forceinline__ void ray_setup(RayCtx &r, f3 o, f3 d) {
     kx = ky;
     ky = t;
   }
-  r.kx = kx;
-  r.ky = ky;
-  r.kz = kz;
-  r.sx = __fdiv_rn(sel(d, kx), dz);
-  r.sy = __fdiv_rn(sel(d, ky), dz);
-  r.sz = __fdiv_rn(1.0f, dz);
+  r.kxyz = kx | (ky << 2) | (kz << 4);
+  r.sz = __frcp_rn(dz);
+  r.sx = __fmul_rn(sel(d, kx), r.sz);
+  r.sy = __fmul_rn(sel(d, ky), r.sz);
 }
 
 // world -> object with the rows of a 3x4 matrix
@@ -59,7 +74,9 @@ __device__ __forceinline__ f3 xform_vector(float4 r0, float4 r1, float4 r2, f3 v
              __fmaf_rn(r2.x, v.x, __fmaf_rn(r2.y, v.y, __fmul_rn(r2.z, v.z))));
 }
 
-__device__ __forceinline__ bool box_test(const RayCtx &r, f3 lo, f3 hi, float tmin, float tmax,
+// slab test against [0, tmax]; returns the entry distance in tnear
+template <bool EXACT>
+__device__ __forceinline__ bool lane_box(const LaneRay &r, f3 lo, f3 hi, float tmax,
                                          float &tnear) {
   const float t0x = __fmul_rn(__fsub_rn(lo.x, r.o.x), r.idir.x);
   const float t1x = __fmul_rn(__fsub_rn(hi.x, r.o.x), r.idir.x);
@@ -67,26 +84,27 @@ __device__ __forceinline__ bool box_test(const RayCtx &r, f3 lo, f3 hi, float tm
   const float t1y = __fmul_rn(__fsub_rn(hi.y, r.o.y), r.idir.y);
   const float t0z = __fmul_rn(__fsub_rn(lo.z, r.o.z), r.idir.z);
   const float t1z = __fmul_rn(__fsub_rn(hi.z, r.o.z), r.idir.z);
-  float tn = fmaxf(tmin, fminf(t0x, t1x));
+  float tn = fmaxf(0.0f, fminf(t0x, t1x));
   float tf = fminf(tmax, fmaxf(t0x, t1x));
   tn = fmaxf(tn, fminf(t0y, t1y));
   tf = fminf(tf, fmaxf(t0y, t1y));
   tn = fmaxf(tn, fminf(t0z, t1z));
   tf = fminf(tf, fmaxf(t0z, t1z));
   tnear = tn;
-  return tn <= __fmul_rn(tf, 1.0000004f);
+  return tn <= __fmul_rn(tf, EXACT ? 1.0000004f : 1.000001f);
 }
 
-__device__ __forceinline__ bool tri_test(const RayCtx &r, float4 p0, float4 p1, float4 p2,
-                                         float tmin, float tmax, float &t_out, float &u_out,
-                                         float &v_out) {
+// watertight test against (0, tmax]; u weights v1, v weights v2
+__device__ __forceinline__ bool lane_tri(const LaneRay &r, float4 p0, float4 p1, float4 p2,
+                                         float tmax, float &t_out, float &u_out, float &v_out) {
+  const int kx = r.kxyz & 3, ky = (r.kxyz >> 2) & 3, kz = r.kxyz >> 4;
   const f3 A = mk3(__fsub_rn(p0.x, r.o.x), __fsub_rn(p0.y, r.o.y), __fsub_rn(p0.z, r.o.z));
   const f3 B = mk3(__fsub_rn(p1.x, r.o.x), __fsub_rn(p1.y, r.o.y), __fsub_rn(p1.z, r.o.z));
   const f3 C = mk3(__fsub_rn(p2.x, r.o.x), __fsub_rn(p2.y, r.o.y), __fsub_rn(p2.z, r.o.z));
-  const float Akz = sel(A, r.kz), Bkz = sel(B, r.kz), Ckz = sel(C, r.kz);
-  const float Ax = __fmaf_rn(-r.sx, Akz, sel(A, r.kx)), Ay = __fmaf_rn(-r.sy, Akz, sel(A, r.ky));
-  const float Bx = __fmaf_rn(-r.sx, Bkz, sel(B, r.kx)), By = __fmaf_rn(-r.sy, Bkz, sel(B, r.ky));
-  const float Cx = __fmaf_rn(-r.sx, Ckz, sel(C, r.kx)), Cy = __fmaf_rn(-r.sy, Ckz, sel(C, r.ky));
+  const float Akz = sel(A, kz), Bkz = sel(B, kz), Ckz = sel(C, kz);
+  const float Ax = __fmaf_rn(-r.sx, Akz, sel(A, kx)), Ay = __fmaf_rn(-r.sy, Akz, sel(A, ky));
+  const float Bx = __fmaf_rn(-r.sx, Bkz, sel(B, kx)), By = __fmaf_rn(-r.sy, Bkz, sel(B, ky));
+  const float Cx = __fmaf_rn(-r.sx, Ckz, sel(C, kx)), Cy = __fmaf_rn(-r.sy, Ckz, sel(C, ky));
   float U = __fmaf_rn(Cx, By, -__fmul_rn(Cy, Bx));
   float V = __fmaf_rn(Ax, Cy, -__fmul_rn(Ay, Cx));
   float W = __fmaf_rn(Bx, Ay, -__fmul_rn(By, Ax));
@@ -100,9 +118,9 @@ __device__ __forceinline__ bool tri_test(const RayCtx &r, float4 p0, float4 p1, 
   if (det == 0.0f) return false;
   const float Az = __fmul_rn(r.sz, Akz), Bz = __fmul_rn(r.sz, Bkz), Cz = __fmul_rn(r.sz, Ckz);
   const float T = __fmaf_rn(U, Az, __fmaf_rn(V, Bz, __fmul_rn(W, Cz)));
-  const float rcp = __fdiv_rn(1.0f, det);
+  const float rcp = __frcp_rn(det);
   const float t = __fmul_rn(T, rcp);
-  if (!(t > tmin && t <= tmax)) return false;
+  if (!(t > 0.0f && t <= tmax)) return false;
   t_out = t;
   u_out = __fmul_rn(V, rcp);
   v_out = __fmul_rn(W, rcp);
@@ -121,10 +139,12 @@ __device__ __forceinline__ bool hit_better(float t, uint32_t inst, uint32_t prim
   return prim < h.prim;
 }
 
+// One ray per thread over the canonical two-level BVH2 (64-byte nodes).
 // cnt[0] += interior nodes tested, cnt[1] += triangles tested, cnt[2] += instances entered
 template <bool ANY, bool STATS>
-__device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float tmin, float tmax,
-                                         Hit &hit, uint32_t *cnt) {
+__device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float tmax, Hit &hit,
+                                         uint32_t *cnt) {
+  constexpr bool EXACT = STATS;
   hit.t = tmax;
   hit.u = hit.v = 0.0f;
   hit.inst = LP_INVALID_INDEX;
@@ -134,8 +154,10 @@ __device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float
 
   uint32_t stack[kStackSize];
   int sp = 0;
-  RayCtx r;
-  ray_setup(r, wo, wd);
+  LaneRay r;
+  r.kxyz = 0;
+  r.sx = r.sy = r.sz = 0.f;
+  lane_set_world<EXACT>(r, wo, wd);
   bool in_blas = false;
   uint32_t inst = 0;
 
@@ -146,8 +168,8 @@ __device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float
       if (STATS) cnt[0]++;
       const float limit = ANY ? tmax : hit.t;
       float t0, t1;
-      const bool h0 = box_test(r, mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), tmin, limit, t0);
-      const bool h1 = box_test(r, mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), tmin, limit, t1);
+      const bool h0 = lane_box<EXACT>(r, mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), limit, t0);
+      const bool h1 = lane_box<EXACT>(r, mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), limit, t1);
       const uint32_t c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
       if (h0 && h1) {
         const bool swap = t1 < t0;
@@ -170,7 +192,7 @@ __device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float
       const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
       const uint32_t root = __float_as_uint(__ldg(ip + 6).x);
       if (STATS) cnt[2]++;
-      ray_setup(r, xform_point(r0, r1, r2, wo), xform_vector(r0, r1, r2, wd));
+      lane_set_object<EXACT>(r, xform_point(r0, r1, r2, wo), xform_vector(r0, r1, r2, wd));
       stack[sp++] = kSentinel;
       in_blas = true;
       cur = root;
@@ -183,7 +205,7 @@ __device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float
         const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
         if (STATS) cnt[1]++;
         float t, u, v;
-        if (tri_test(r, p0, p1, p2, tmin, ANY ? tmax : hit.t, t, u, v)) {
+        if (lane_tri(r, p0, p1, p2, ANY ? tmax : hit.t, t, u, v)) {
           if (ANY) return true;
           const uint32_t prim = __float_as_uint(p0.w);
           if (hit_better(t, inst, prim, hit)) {
@@ -201,7 +223,7 @@ __device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float
     cur = stack[--sp];
     if (cur == kSentinel) {
       in_blas = false;
-      ray_setup(r, wo, wd);
+      lane_set_world<EXACT>(r, wo, wd);
       if (sp == 0) break;
       cur = stack[--sp];
     }

@@ -85,9 +85,9 @@ static void ray_setup(ray_ctx *r, const float o[3], const float d[3]) {
   r->kx = kx;
   r->ky = ky;
   r->kz = kz;
-  r->sx = d[kx] / d[kz];
-  r->sy = d[ky] / d[kz];
   r->sz = 1.0f / d[kz];
+  r->sx = d[kx] * r->sz;
+  r->sy = d[ky] * r->sz;
 }
 
 /* Watertight ray/triangle test (Woop, Benthin, Wald 2013), double-sided.
