@@ -204,17 +204,14 @@ def run_ours(args) -> None:
     sg = lb.SceneGPU.new_from_scene(c["scene"], dev)
     r = lb.Renderer(dev, (w, h), downsample_factor=1.0)
     r.set_resources(sg, None)
+    from loupiote_b200 import multi
     base_cfg = dict(max_bounces=bounces, spp_per_call=args.spp_per_step, jitter=1, seed=0,
-                    env_color=c["env_color"], sample_offset=rank, sample_stride=world)
+                    env_color=c["env_color"], traversal_variant=args.variant,
+                    **multi.sample_partition(rank, world))
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
 
     # the accumulator as a torch tensor (zero copy) for the NCCL reduce
-    ptr, nfloats, _ = r.accum_device_ptr()
-
-    class _Blob:
-        __cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False),
-                                    "version": 3, "strides": None}
-    accum_t = torch.as_tensor(_Blob(), device=torch.device("cuda", local_rank))
+    accum_t = multi.accum_tensor(r, local_rank)
 
     def barrier():
         if world > 1:
@@ -224,18 +221,19 @@ def run_ours(args) -> None:
     def reduce_accum():
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
+                multi.reduce_sum_(accum_t, dst=0)
 
     # ---- canonical traversal statistics (untimed, one step, count_stats on): gives the
     # algorithmic bytes per ray that the roofline is defined on
     r.set_config(**base_cfg, count_stats=1)
-    r.accumulate = True
     r.ray_counters(reset=True)
     r.raytrace(c["view"])
     stats = algorithmic_bytes_flops(r.ray_counters(reset=True))
     r.set_config(**base_cfg, count_stats=0)
+    # every step is an independent batch: `accumulate` stays off, so each raytrace call
+    # overwrites the SUM accumulator with its own spp_per_step samples and the reduce that
+    # follows sums exactly one batch per rank (one reduce per batch)
     r.reset_accumulation()
-    r.accumulate = True
 
     # ---- warm-up
     for _ in range(max(args.warmup, 0)):
@@ -363,6 +361,7 @@ def main() -> None:
     ap.add_argument("--workload", default="spheres-1M-1080p-8b", choices=sorted(WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (tuning)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

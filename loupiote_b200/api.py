@@ -217,7 +217,7 @@ class Scene:
         nrm = None if normals is None else _f32(normals, (n, 3))
         uv = None if uvs is None else _f32(uvs, (n, 2))
         out = C.c_uint32()
-        args = [self._h, pos.ctypes.data, pos.strides[0],
+        args = [self._h, pos.ctypes.data, 4 * pos.shape[1],
                 nrm.ctypes.data if nrm is not None else None, 12,
                 uv.ctypes.data if uv is not None else None, 8, n]
         if indices is None:

@@ -115,9 +115,11 @@ __device__ __forceinline__ void bsdf_eval(const Surface &sf, f3 wo, f3 wi, f3 &f
                     0.04f + (sf.base.z - 0.04f) * sf.metallic);
   const f3 diff = mk3(sf.base.x * inv_m, sf.base.y * inv_m, sf.base.z * inv_m);
   const float spec = D * g1v * g1l / (4.0f * ndl * ndv);
-  f.x = diff.x * LP_INV_PI + (F0.x + (1.0f - F0.x) * fc) * spec;
-  f.y = diff.y * LP_INV_PI + (F0.y + (1.0f - F0.y) * fc) * spec;
-  f.z = diff.z * LP_INV_PI + (F0.z + (1.0f - F0.z) * fc) * spec;
+  // glTF 2.0 material model: dielectric = fresnel_mix(diffuse, specular), F0 = 0.04
+  const float kd = (1.0f - (0.04f + 0.96f * fc)) * LP_INV_PI;
+  f.x = diff.x * kd + (F0.x + (1.0f - F0.x) * fc) * spec;
+  f.y = diff.y * kd + (F0.y + (1.0f - F0.y) * fc) * spec;
+  f.z = diff.z * kd + (F0.z + (1.0f - F0.z) * fc) * spec;
   const float ps = lobe_probability(sf, ndv);
   const float pdf_spec = g1v * D / (4.0f * ndv);
   const float pdf_diff = ndl * LP_INV_PI;

@@ -105,9 +105,11 @@ __device__ __forceinline__ bool lane_tri(const LaneRay &r, float4 p0, float4 p1,
   const float Ax = __fmaf_rn(-r.sx, Akz, sel(A, kx)), Ay = __fmaf_rn(-r.sy, Akz, sel(A, ky));
   const float Bx = __fmaf_rn(-r.sx, Bkz, sel(B, kx)), By = __fmaf_rn(-r.sy, Bkz, sel(B, ky));
   const float Cx = __fmaf_rn(-r.sx, Ckz, sel(C, kx)), Cy = __fmaf_rn(-r.sy, Ckz, sel(C, ky));
-  float U = __fmaf_rn(Cx, By, -__fmul_rn(Cy, Bx));
-  float V = __fmaf_rn(Ax, Cy, -__fmul_rn(Ay, Cx));
-  float W = __fmaf_rn(Bx, Ay, -__fmul_rn(By, Ax));
+  // edge functions UNFUSED: the two products round identically for both triangles sharing
+  // an edge, so their edge values are exact negations (watertightness, Woop et al. 2013)
+  float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+  float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+  float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
   if (U == 0.0f || V == 0.0f || W == 0.0f) {
     U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
     V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));

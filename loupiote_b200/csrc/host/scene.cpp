@@ -50,7 +50,8 @@ Scene::Scene() {
 uint32_t Scene::add_bvh(const void *positions, size_t pstride, const void *normals, size_t nstride,
                         const void *uvs, size_t uvstride, size_t vertex_count,
                         const uint32_t *idx, size_t index_count) {
-  if (!positions || pstride < 12) throw std::invalid_argument("positions missing or stride < 12");
+  if ((!positions && vertex_count) || pstride < 12)
+    throw std::invalid_argument("positions missing or stride < 12");
   if (normals && nstride < 12) throw std::invalid_argument("normal stride < 12");
   if (uvs && uvstride < 8) throw std::invalid_argument("uv stride < 8");
   const size_t tri_count = idx ? index_count / 3 : vertex_count / 3;
@@ -58,6 +59,14 @@ uint32_t Scene::add_bvh(const void *positions, size_t pstride, const void *norma
   if (idx)
     for (size_t i = 0; i < tri_count * 3; ++i)
       if (idx[i] >= vertex_count) throw std::invalid_argument("index out of range");
+
+  // validate everything before mutating the scene: a failed add leaves it untouched
+  for (size_t i = 0; i < vertex_count; ++i) {
+    float p[3];
+    std::memcpy(p, (const uint8_t *)positions + i * pstride, 12);
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2]))
+      throw std::invalid_argument("non-finite vertex position");
+  }
 
   lp_blas_entry e{};
   e.vertex_offset = (uint32_t)vertices.size();

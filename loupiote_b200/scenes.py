@@ -98,7 +98,7 @@ def cornell_box() -> dict:
     scene = Scene()
     loaders.load_gltf(CORNELL_GLB.read_bytes(), scene)
     # 2x2 quad light just under the ceiling, facing -y, radiance 17
-    scene.push_light(center=(0.0, 3.59, 0.4), tangent=(1.0, 0.0, 0.0), bitangent=(0.0, 0.0, -1.0),
+    scene.push_light(center=(0.0, 3.59, 0.4), tangent=(1.0, 0.0, 0.0), bitangent=(0.0, 0.0, 1.0),
                      intensity=17.0, color=(1.0, 1.0, 1.0))
     view = look_at_view((0.0, 0.6, 11.5), (0.0, 0.0, -1.0))
     return {"scene": scene, "view": view, "env_color": (0.0, 0.0, 0.0), "name": "cornell-box"}

