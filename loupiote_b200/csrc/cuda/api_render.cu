@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -159,7 +160,12 @@ lp_status allocate_targets(lp_renderer *r) {
   // samples in flight per wave: enough slots to keep 148 SMs busy in the deep bounces,
   // capped at 8M slots (~1.6 GB of path state)
   const uint32_t spp = std::max(1u, r->cfg.spp_per_call);
-  uint32_t ws = std::max(1u, (8u << 20) / r->slots_per_sample);
+  uint32_t max_slots = 8u << 20;
+  if (const char *env = std::getenv("LP_MAX_SLOTS")) {  // tuning knob (tools/tune_traversal.py)
+    const long v = std::atol(env);
+    if (v >= 1024) max_slots = (uint32_t)std::min<long>(v, 1L << 28);
+  }
+  uint32_t ws = std::max(1u, max_slots / r->slots_per_sample);
   r->wave_samples = std::min(spp, ws);
   r->n_slots = r->slots_per_sample * r->wave_samples;
   const size_t S = r->n_slots;

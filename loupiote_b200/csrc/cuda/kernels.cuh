@@ -181,6 +181,18 @@ __global__ void __launch_bounds__(128) connect_kernel(const __grid_constant__ Fr
   if (STATS) flush_stats(P.counters, 2, cnt);
 }
 
+// Motion vector of a first hit: previous-frame pixel coordinates through
+// prev_model_to_screen = perspective(0.01, 100) * view^-1 [ref renderer.rs:542-546].
+__device__ __forceinline__ float2 reproject(const FrameParams &P, f3 p) {
+  const float *M = P.prev_w2s;
+  const float cx = M[0] * p.x + M[4] * p.y + M[8] * p.z + M[12];
+  const float cy = M[1] * p.x + M[5] * p.y + M[9] * p.z + M[13];
+  const float cw = M[3] * p.x + M[7] * p.y + M[11] * p.z + M[15];
+  if (!(cw > 1e-6f)) return make_float2(-1.f, -1.f);
+  return make_float2((cx / cw * 0.5f + 0.5f) * (float)P.cam.width,
+                     (0.5f - cy / cw * 0.5f) * (float)P.cam.height);
+}
+
 // Shading of bounce `bounce`: emission / environment / light hits with MIS, next-event
 // estimation (one quad light sample + one cosine-weighted environment sample, both as
 // queued shadow rays), BSDF importance sampling of the next ray, queue compaction.
@@ -258,19 +270,17 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Fram
         L.y += T.y * l3.y * l0.w * w;
         L.z += T.z * l3.z * l0.w * w;
         gb = make_uint4(pack_normal(nl), __float_as_uint(hit.t), 0xFFFF0000u | hit.prim, 0xFFFFFFFFu);
+        if (first && P.write_gbuffer) {
+          const float4 o4 = P.ps.ray_o[slot];
+          mv = reproject(P, mk3(o4.x + hit.t * d.x, o4.y + hit.t * d.y, o4.z + hit.t * d.z));
+        }
       } else {
         Surface sf;
         uint32_t mat;
         fetch_surface(sc, hit, d, sf, mat);
         if (first && P.write_gbuffer) {
           gb = make_uint4(pack_normal(sf.ns), __float_as_uint(hit.t), hit.inst, pack_rgba8(sf.base));
-          const float *M = P.prev_w2s;
-          const float cx = M[0] * sf.p.x + M[4] * sf.p.y + M[8] * sf.p.z + M[12];
-          const float cy = M[1] * sf.p.x + M[5] * sf.p.y + M[9] * sf.p.z + M[13];
-          const float cw = M[3] * sf.p.x + M[7] * sf.p.y + M[11] * sf.p.z + M[15];
-          if (cw > 1e-6f)
-            mv = make_float2((cx / cw * 0.5f + 0.5f) * (float)P.cam.width,
-                             (0.5f - cy / cw * 0.5f) * (float)P.cam.height);
+          mv = reproject(P, sf.p);
         }
         L.x += T.x * sf.emission.x;
         L.y += T.y * sf.emission.y;

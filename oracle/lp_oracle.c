@@ -828,6 +828,17 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
         memcpy(&gbuf[1], &hit.t, 4);
         gbuf[2] = 0xFFFF0000u | hit.primitive;
         gbuf[3] = 0xFFFFFFFFu;
+        if (motion && prev_w2s) {
+          const float p[3] = {o[0] + hit.t * d[0], o[1] + hit.t * d[1], o[2] + hit.t * d[2]};
+          const float *M = prev_w2s;
+          const float cx = M[0] * p[0] + M[4] * p[1] + M[8] * p[2] + M[12];
+          const float cy = M[1] * p[0] + M[5] * p[1] + M[9] * p[2] + M[13];
+          const float cw = M[3] * p[0] + M[7] * p[1] + M[11] * p[2] + M[15];
+          if (cw > 1e-6f) {
+            motion[0] = (cx / cw * 0.5f + 0.5f) * (float)cam->width;
+            motion[1] = (0.5f - cy / cw * 0.5f) * (float)cam->height;
+          }
+        }
       }
       break;
     }
