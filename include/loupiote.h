@@ -246,7 +246,8 @@ typedef enum lp_scene_array {
   LP_SCENE_EMISSION = 8,   /* float[4] per material */
   LP_SCENE_TLAS_NODES = 9, /* lp_bvh_node over instances (leaf refs = instance ids) */
   LP_SCENE_GPU_NODES = 10, /* 64-byte re-laid-out traversal nodes (host copy) */
-  LP_SCENE_GPU_INSTANCES = 11 /* 128-byte instance records (host copy) */
+  LP_SCENE_GPU_INSTANCES = 11, /* 128-byte instance records (host copy) */
+  LP_SCENE_GPU_NODES4 = 12 /* 128-byte 4-wide collapse of the same trees (host copy) */
 } lp_scene_array;
 LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const void **out_ptr,
                                     size_t *out_count, size_t *out_elem_size);

@@ -84,7 +84,7 @@ class RayCounters(C.Structure):
 # lp_scene_array
 (SCENE_ENTRIES, SCENE_NODES, SCENE_PRIMITIVES, SCENE_VERTICES, SCENE_INSTANCES, SCENE_MATERIALS,
  SCENE_LIGHTS, SCENE_INDICES, SCENE_EMISSION, SCENE_TLAS_NODES, SCENE_GPU_NODES,
- SCENE_GPU_INSTANCES) = range(12)
+ SCENE_GPU_INSTANCES, SCENE_GPU_NODES4) = range(13)
 
 _vp = C.c_void_p
 _PROTOTYPES = {

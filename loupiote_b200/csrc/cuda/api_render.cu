@@ -16,6 +16,8 @@
 #include "kernels.cuh"
 #include "svgf.cuh"
 #include "trace_persistent.cuh"
+#include "traverse4.cuh"
+#include "trace_pool.cuh"
 
 using namespace lp;
 
@@ -69,7 +71,7 @@ struct lp_device {
 
 struct lp_scene_gpu {
   lp_device *dev = nullptr;
-  DevBuf<float4> nodes, tris, instances, vertices, materials, emission, lights;
+  DevBuf<float4> nodes, nodes4, tris, instances, vertices, materials, emission, lights;
   DevBuf<uint32_t> indices, active_lights;
   SceneDev sc{};
   size_t node_bytes = 0, tri_bytes = 0, total_bytes = 0;
@@ -114,6 +116,7 @@ struct lp_renderer {
   DevBuf<uint32_t> hit_inst, queue0, queue1;
   DevBuf<float4> sl_o, sl_d, sl_c, se_o, se_d, se_c;
   DevBuf<uint32_t> counts;
+  DevBuf<uint32_t> pool_scratch;  // traversal stacks of the ray-pool kernels
   DevBuf<Counters> counters;
   // render targets
   DevBuf<float4> accum;  // main target: RGBA32F sum, alpha = sample count
@@ -157,10 +160,11 @@ lp_status allocate_targets(lp_renderer *r) {
   r->tiles_x = (w + 7) / 8;
   const uint32_t tiles_y = (h + 3) / 4;
   r->slots_per_sample = r->tiles_x * tiles_y * 32u;
-  // samples in flight per wave: enough slots to keep 148 SMs busy in the deep bounces,
-  // capped at 8M slots (~1.6 GB of path state)
+  // samples in flight per wave: the deep bounces keep only a few % of the paths, so a wave
+  // carries many samples of every pixel to keep 148 SMs busy there (measured on config 3:
+  // 16 spp per wave is 15 % faster than 4).  Capped at 64M slots (~12 GB of path state).
   const uint32_t spp = std::max(1u, r->cfg.spp_per_call);
-  uint32_t max_slots = 8u << 20;
+  uint32_t max_slots = 64u << 20;
   if (const char *env = std::getenv("LP_MAX_SLOTS")) {  // tuning knob (tools/tune_traversal.py)
     const long v = std::atol(env);
     if (v >= 1024) max_slots = (uint32_t)std::min<long>(v, 1L << 28);
@@ -344,6 +348,37 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
     case 7: launch_persistent<4, 2, 2, 8>(r, P, b, any, env, stats); break;
     case 8: launch_persistent<20, 8, 4, 10>(r, P, b, any, env, stats); break;
     case 9: launch_persistent<12, 6, 12, 10>(r, P, b, any, env, stats); break;
+    case 11:
+    case 12: {  // ray pool in shared memory (trace_pool.cuh); STATS keeps the canonical walk
+      if (stats) {
+        if (any) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
+        else extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
+        break;
+      }
+      const bool il = r->cfg.traversal_variant == 12;
+      const int g_any = il ? cached_grid(trace_pool_kernel<true, true>, sm)
+                           : cached_grid(trace_pool_kernel<true, false>, sm);
+      const int g_closest = il ? cached_grid(trace_pool_kernel<false, true>, sm)
+                               : cached_grid(trace_pool_kernel<false, false>, sm);
+      const size_t need = (size_t)std::max(g_any, g_closest) * kPoolWarps * kPool * kPoolStack;
+      if (r->pool_scratch.count < need && r->pool_scratch.alloc(need) != cudaSuccess) break;
+      uint32_t *scratch = r->pool_scratch.ptr;
+      if (any && il) trace_pool_kernel<true, true><<<g_any, 128, 0, st>>>(P, b, env, scratch);
+      else if (any) trace_pool_kernel<true, false><<<g_any, 128, 0, st>>>(P, b, env, scratch);
+      else if (il) trace_pool_kernel<false, true><<<g_closest, 128, 0, st>>>(P, b, env, scratch);
+      else trace_pool_kernel<false, false><<<g_closest, 128, 0, st>>>(P, b, env, scratch);
+      break;
+    }
+    case 10:  // 4-wide collapse, one ray per thread (STATS keeps the canonical BVH2 walk)
+      if (stats) {
+        if (any) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
+        else extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
+      } else if (any) {
+        connect4_kernel<<<cached_grid(connect4_kernel, sm), 128, 0, st>>>(P, b, env);
+      } else {
+        extend4_kernel<<<cached_grid(extend4_kernel, sm), 128, 0, st>>>(P, b);
+      }
+      break;
     case 1: launch_persistent<8, 4, 4, 8>(r, P, b, any, env, stats); break;
   }
 }
@@ -487,7 +522,7 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   } catch (const std::exception &e) {
     return fail(LP_ERR_ACCEL_BUILD, e.what());
   }
-  if (s.gpu_max_depth + 2 > (uint32_t)kStackSize)
+  if (s.gpu_max_depth + 2 > (uint32_t)kStackSize || s.gpu_max_stack4 > (uint32_t)kStackSize4)
     return fail(LP_ERR_ACCEL_BUILD, "BVH too deep for the traversal stack");
   CUDA_CHECK(cudaSetDevice(dev->ordinal));
   lp_scene_gpu *g = new (std::nothrow) lp_scene_gpu();
@@ -503,6 +538,7 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
     e = buf.upload(src, bytes / sizeof(*buf.ptr), st);
   };
   up(g->nodes, s.gpu_nodes.data(), s.gpu_nodes.size() * sizeof(GpuNode));
+  up(g->nodes4, s.gpu_nodes4.data(), s.gpu_nodes4.size() * sizeof(GpuNode4));
   up(g->tris, s.primitives.data(), s.primitives.size() * sizeof(lp_bvh_primitive));
   up(g->instances, s.gpu_instances.data(), s.gpu_instances.size() * sizeof(GpuInstance));
   up(g->vertices, s.vertices.data(), s.vertices.size() * sizeof(lp_vertex));
@@ -529,7 +565,9 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   sc.n_active_lights = (uint32_t)active.size();
   sc.n_materials = (uint32_t)s.materials.size();
   sc.tlas_root = s.gpu_tlas_root;
-  g->node_bytes = s.gpu_nodes.size() * sizeof(GpuNode);
+  sc.nodes4 = g->nodes4.ptr;
+  sc.tlas_root4 = s.gpu_tlas_root4;
+  g->node_bytes = s.gpu_nodes.size() * sizeof(GpuNode) + s.gpu_nodes4.size() * sizeof(GpuNode4);
   g->tri_bytes = s.primitives.size() * sizeof(lp_bvh_primitive);
   g->total_bytes = g->node_bytes + g->tri_bytes + s.gpu_instances.size() * sizeof(GpuInstance) +
                    s.vertices.size() * sizeof(lp_vertex) + s.indices.size() * 4 +

@@ -21,6 +21,8 @@ constexpr int kStackSize = 64;
 
 // Scene buffers as the kernels see them (all 16-byte vector loads).
 struct SceneDev {
+  const float4 *nodes4;     // 8 x float4 per 128-byte 4-wide node (production traversal)
+  uint32_t tlas_root4;      // child reference into nodes4
   const float4 *nodes;      // 4 x float4 per 64-byte node
   const float4 *tris;       // 3 x float4 per triangle (leaf order)
   const float4 *instances;  // 8 x float4 per 128-byte instance
@@ -70,6 +72,23 @@ struct Counters {
   unsigned long long rays[3];
   unsigned long long n_int[3], n_tri[3], n_inst[3];
 };
+
+// 256-bit read-only global load (LDG.E.256, sm_100+).  A divergent warp-wide load costs one
+// L1 wavefront per distinct 128-byte line it touches REGARDLESS of its width (ncu: the
+// traversal kernels sit at 65-78 % of the L1 wavefront rate), so fetching a 64-byte node
+// with two 256-bit loads instead of four 128-bit ones halves the L1 work of a node visit.
+// `p` must be 32-byte aligned.
+struct f8 {
+  float4 lo, hi;
+};
+__device__ __forceinline__ f8 ldg256(const void *p) {
+  f8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x),
+                 "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+}
 
 // ------------------------------------------------------------------ float3 helpers
 struct f3 {

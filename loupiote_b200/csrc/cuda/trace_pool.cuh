@@ -1,0 +1,346 @@
+// Ray-pool traversal: the state of 64 rays per warp lives in SHARED MEMORY, lanes are not
+// bound to rays.  Every iteration the warp picks ONE kind of work -- a 4-wide node test, an
+// instance entry or a triangle test -- gathers up to 32 pool rays that need exactly that
+// work, and executes it with a (nearly) full warp; rays that need something else simply wait
+// in the pool without occupying a lane.  Terminated rays are replaced from the global queue.
+//
+// Why (profiles/r01_v1_*): in the one-ray-per-thread kernels the warp executes the triangle
+// test for ~2 lanes, the instance entry for ~3 and even the node test for only 8 of 32 lanes
+// on incoherent rays, so 70-80 % of the issued thread-instructions are idle lanes.  The
+// persistent-lane kernel (trace_persistent.cuh) raises that only to 13/32 because a waiting
+// ray still blocks its lane.  Here waiting costs a pool slot, not a lane (ncu: 19-24 active
+// threads per instruction).  The price is load/store-unit work: ray state moves through
+// shared memory every step, so the state is packed into float4 records (LDS.128).
+//
+// Hit arithmetic is traverse.cuh's (lane_tri, hit_better) and the node test traverse4.cuh's:
+// images are bit-identical to the other kernels and to the CPU restatement.
+#pragma once
+#include "traverse4.cuh"
+
+namespace lp {
+
+constexpr int kPool = 64;                // rays resident per warp
+constexpr int kPoolStack = kStackSize4;  // traversal stack entries per ray (global scratch)
+constexpr int kPoolWarps = 4;            // warps per block
+
+enum : uint32_t { kStEmpty = 0u, kStNode = 1u, kStEntry = 2u, kStTri = 3u };
+constexpr uint32_t kFlagInBlas = 4u;
+
+struct PoolSmem {
+  float4 a[kPool];  // origin.xyz (current space), tmax / best t
+  float4 b[kPool];  // 1/direction.xyz (current space), cur (bits)
+  float4 c[kPool];  // shear sx, sy, sz, kxyz (bits)
+  float4 d[kPool];  // hit u, v, instance (bits), primitive (bits)
+  uint4 e[kPool];   // sp, item, instance being traversed, unused
+  uint32_t state[kPool];  // bits 0..1 = state, bit 2 = inside a BLAS
+  uint32_t list[32];
+};
+
+template <bool ANY, bool IL>
+__global__ void __launch_bounds__(32 * kPoolWarps)
+    trace_pool_kernel(const __grid_constant__ FrameParams P, uint32_t bounce, int env,
+                      uint32_t *__restrict__ stack_scratch) {
+  __shared__ PoolSmem pools[kPoolWarps];
+  PoolSmem &S = pools[threadIdx.x >> 5];
+  const SceneDev &sc = P.sc;
+  uint32_t n;
+  const uint32_t *queue = nullptr;
+  uint32_t *work;
+  const ShadowQueue &sq = env ? P.sq_env : P.sq_light;
+  if (ANY) {
+    n = P.counts[(env ? kCntEnv : kCntLight) + bounce];
+    work = P.counts + (env ? kCntWorkEnv : kCntWorkLight) + bounce;
+  } else {
+    n = bounce == 0 ? P.n_slots : P.counts[kCntNext + bounce - 1];
+    queue = bounce == 0 ? nullptr : P.queue[(bounce - 1) & 1u];
+    work = P.counts + kCntWorkExtend + bounce;
+  }
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t total_warps = (gridDim.x * blockDim.x) >> 5;
+  // stack of pool slot s: IL = false: kPoolStack contiguous words per slot; IL = true:
+  // interleaved by slot (entry d of slot s at d * kPool + s)
+  constexpr uint32_t SBASE = IL ? 1u : (uint32_t)kPoolStack, SSTRIDE = IL ? (uint32_t)kPool : 1u;
+  uint32_t *stack_base = stack_scratch + (size_t)warp_id * (kPool * kPoolStack);
+
+  uint32_t chunk = n / (total_warps * 4u);
+  chunk = chunk < 64u ? 64u : (chunk > 1024u ? 1024u : chunk);
+  uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
+  bool exhausted = false;
+
+  S.state[lane] = kStEmpty;
+  S.state[lane + 32] = kStEmpty;
+
+  auto load_ray = [&](uint32_t item, float4 &o4, float4 &d4) {
+    if (ANY) {
+      o4 = sq.o_tmax[item];
+      d4 = sq.d_slot[item];
+    } else {
+      o4 = P.ps.ray_o[item];
+      d4 = P.ps.ray_d[item];
+    }
+  };
+  // terminate the ray in pool slot s (closest hit: tbest = current best t)
+  auto finish = [&](uint32_t s, uint32_t item, bool occluded, float tbest) {
+    if (ANY) {
+      if (!occluded) {
+        const uint32_t slot = __float_as_uint(sq.d_slot[item].w);
+        const float4 c = sq.contrib[item];
+        float4 acc = P.ps.rad[slot];
+        acc.x += c.x;
+        acc.y += c.y;
+        acc.z += c.z;
+        P.ps.rad[slot] = acc;
+      }
+    } else {
+      const float4 d = S.d[s];
+      Hit hit;
+      hit.t = tbest;
+      hit.u = d.x;
+      hit.v = d.y;
+      hit.inst = __float_as_uint(d.z);
+      hit.prim = __float_as_uint(d.w);
+      if (sc.n_active_lights) {
+        const float4 o4 = P.ps.ray_o[item], d4 = P.ps.ray_d[item];
+        lights_closest(sc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), 0.0f, hit);
+      }
+      P.ps.hit[item] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+      P.ps.hit_inst[item] = hit.inst;
+    }
+    S.state[s] = kStEmpty;
+  };
+  // pop the next reference of slot s (handles leaving an instance); writes cur/sp/state
+  auto pop = [&](uint32_t s, uint32_t *stk, uint32_t sp, uint32_t flags, uint32_t item,
+                 float tbest) {
+    for (;;) {
+      if (sp == 0u) {
+        finish(s, item, false, tbest);
+        return;
+      }
+      const uint32_t c = stk[(--sp) * SSTRIDE];
+      if (c == kSentinel) {
+        flags &= ~kFlagInBlas;
+        float4 o4, d4;
+        load_ray(item, o4, d4);
+        LaneRay r;
+        lane_set_world<false>(r, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
+        S.a[s] = make_float4(r.o.x, r.o.y, r.o.z, tbest);
+        S.b[s] = make_float4(r.idir.x, r.idir.y, r.idir.z, 0.f);
+        continue;
+      }
+      S.b[s].w = __uint_as_float(c);
+      S.e[s].x = sp;
+      const uint32_t st = (c & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode;
+      S.state[s] = st | (flags & kFlagInBlas);
+      return;
+    }
+  };
+
+  for (;;) {
+    __syncwarp();
+    const uint32_t st_lo = S.state[lane] & 3u, st_hi = S.state[lane + 32] & 3u;
+    const unsigned e_lo = __ballot_sync(0xFFFFFFFFu, st_lo == kStEmpty);
+    const unsigned e_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStEmpty);
+    const unsigned n_lo = __ballot_sync(0xFFFFFFFFu, st_lo == kStNode);
+    const unsigned n_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStNode);
+    const unsigned t_lo = __ballot_sync(0xFFFFFFFFu, st_lo == kStTri);
+    const unsigned t_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStTri);
+    const unsigned y_lo = ~(e_lo | n_lo | t_lo), y_hi = ~(e_hi | n_hi | t_hi);  // entry
+    const int c_empty = __popc(e_lo) + __popc(e_hi);
+    const int c_node = __popc(n_lo) + __popc(n_hi);
+    const int c_tri = __popc(t_lo) + __popc(t_hi);
+    const int c_entry = kPool - c_empty - c_node - c_tri;
+
+    // ---------------------------------------------------------------- choose the work
+    unsigned m_lo, m_hi;
+    uint32_t phase;
+    if ((!exhausted && c_empty >= 32) || (c_empty == kPool)) {
+      if (exhausted) break;
+      phase = kStEmpty;
+      m_lo = e_lo;
+      m_hi = e_hi;
+    } else if (c_tri >= 32 || (c_tri >= c_node && c_tri >= c_entry)) {
+      phase = kStTri;
+      m_lo = t_lo;
+      m_hi = t_hi;
+    } else if (c_entry >= 32 || c_entry >= c_node) {
+      phase = kStEntry;
+      m_lo = y_lo;
+      m_hi = y_hi;
+    } else {
+      phase = kStNode;
+      m_lo = n_lo;
+      m_hi = n_hi;
+    }
+    // ---------------------------------------------------------------- gather <= 32 slots
+    {
+      const int base_hi = __popc(m_lo);
+      if (m_lo & (1u << lane)) S.list[__popc(m_lo & lt_mask)] = (uint32_t)lane;
+      if (m_hi & (1u << lane)) {
+        const int k = base_hi + __popc(m_hi & lt_mask);
+        if (k < 32) S.list[k] = (uint32_t)lane + 32u;
+      }
+    }
+    __syncwarp();
+    const int avail = __popc(m_lo) + __popc(m_hi);
+    const int count = avail < 32 ? avail : 32;
+    const bool active = lane < count;
+    const uint32_t s = active ? S.list[lane] : 0u;
+    uint32_t *stk = stack_base + s * SBASE;
+
+    if (phase == kStEmpty) {
+      // -------------------------------------------------------------- refill
+      const uint32_t want = (uint32_t)count;
+      const uint32_t have = chunk_end - chunk_next;
+      uint32_t my = 0xFFFFFFFFu;
+      if (have < want) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, chunk);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (active) my = (uint32_t)lane < have ? chunk_next + lane : base + (lane - have);
+        chunk_next = base + (want - have);
+        chunk_end = base + chunk;
+        if (base >= n) exhausted = true;
+      } else {
+        if (active) my = chunk_next + lane;
+        chunk_next += want;
+      }
+      if (active && my < n) {
+        uint32_t item;
+        float4 o4, d4;
+        bool ok = true;
+        float tmax;
+        if (ANY) {
+          item = my;
+          load_ray(item, o4, d4);
+          tmax = o4.w;
+        } else {
+          item = queue ? queue[my] : my;
+          load_ray(item, o4, d4);
+          ok = d4.w >= 0.0f;  // dead slots (outside the image) are skipped
+          tmax = INFINITY;
+        }
+        if (ok) {
+          LaneRay r;
+          lane_set_world<false>(r, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
+          const uint32_t root = sc.tlas_root4;
+          S.a[s] = make_float4(r.o.x, r.o.y, r.o.z, tmax);
+          S.b[s] = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(root));
+          if (!ANY)
+            S.d[s] = make_float4(0.f, 0.f, __uint_as_float(LP_INVALID_INDEX),
+                                 __uint_as_float(LP_INVALID_INDEX));
+          S.e[s] = make_uint4(0u, item, 0u, 0u);
+          if (root == kNoChildRef) finish(s, item, false, tmax);  // empty scene
+          else S.state[s] = (root & kLeaf) ? kStEntry : kStNode;
+        }
+      }
+      continue;
+    }
+
+    if (!active) continue;
+    const uint4 e = S.e[s];  // sp, item, inst
+    const uint32_t flags = S.state[s] & ~3u;
+
+    if (phase == kStNode) {
+      // -------------------------------------------------------------- 4-wide node test
+      const float4 a = S.a[s], b = S.b[s];
+      LaneRay r;
+      r.o = mk3(a.x, a.y, a.z);
+      r.idir = mk3(b.x, b.y, b.z);
+      uint32_t sp = e.x;
+      uint32_t key[4], ref[4];
+      node4_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
+      uint32_t next = kNoChildRef;
+      if (!ANY) {
+        LP_CSWAP(key[0], key[1], ref[0], ref[1])
+        LP_CSWAP(key[2], key[3], ref[2], ref[3])
+        LP_CSWAP(key[0], key[2], ref[0], ref[2])
+        LP_CSWAP(key[1], key[3], ref[1], ref[3])
+        LP_CSWAP(key[1], key[2], ref[1], ref[2])
+        if (key[0] != 0xFFFFFFFFu) {
+          if (key[3] != 0xFFFFFFFFu) stk[(sp++) * SSTRIDE] = ref[3];
+          if (key[2] != 0xFFFFFFFFu) stk[(sp++) * SSTRIDE] = ref[2];
+          if (key[1] != 0xFFFFFFFFu) stk[(sp++) * SSTRIDE] = ref[1];
+          next = ref[0];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (key[i] != 0xFFFFFFFFu) {
+            if (next != kNoChildRef) stk[(sp++) * SSTRIDE] = next;
+            next = ref[i];
+          }
+      }
+      if (next != kNoChildRef) {
+        S.b[s].w = __uint_as_float(next);
+        if (sp != e.x) S.e[s].x = sp;
+        S.state[s] =
+            ((next & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode) | flags;
+      } else {
+        pop(s, stk, sp, flags, e.y, a.w);
+      }
+    } else if (phase == kStEntry) {
+      // -------------------------------------------------------------- enter an instance
+      const float tbest = S.a[s].w;
+      const uint32_t inst = __float_as_uint(S.b[s].w) & 0x0FFFFFFFu;
+      const float4 *ip = sc.instances + 8u * (size_t)inst;
+      const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+      const uint32_t root = __float_as_uint(__ldg(ip + 7).y);
+      float4 o4, d4;
+      load_ray(e.y, o4, d4);
+      LaneRay r;
+      lane_set_object<false>(r, xform_point(r0, r1, r2, mk3(o4.x, o4.y, o4.z)),
+                             xform_vector(r0, r1, r2, mk3(d4.x, d4.y, d4.z)));
+      S.a[s] = make_float4(r.o.x, r.o.y, r.o.z, tbest);
+      S.b[s] = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(root));
+      S.c[s] = make_float4(r.sx, r.sy, r.sz, __int_as_float(r.kxyz));
+      stk[e.x * SSTRIDE] = kSentinel;
+      S.e[s] = make_uint4(e.x + 1u, e.y, inst, 0u);
+      S.state[s] = ((root & kLeaf) ? kStTri : kStNode) | kFlagInBlas;
+    } else {
+      // -------------------------------------------------------------- one triangle
+      const float4 a = S.a[s], c = S.c[s];
+      LaneRay r;
+      r.o = mk3(a.x, a.y, a.z);
+      r.sx = c.x;
+      r.sy = c.y;
+      r.sz = c.z;
+      r.kxyz = __float_as_int(c.w);
+      float tbest = a.w;
+      const uint32_t cur = __float_as_uint(S.b[s].w);
+      const uint32_t first = cur & 0x0FFFFFFFu;
+      const uint32_t left = (cur >> 28) & 7u;
+      const float4 *tp = sc.tris + 3u * (size_t)first;
+      const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+      float t, u, v;
+      bool occluded = false;
+      if (lane_tri(r, p0, p1, p2, tbest, t, u, v)) {
+        if (ANY) {
+          occluded = true;
+        } else {
+          const uint32_t prim = __float_as_uint(p0.w);
+          const float4 d = S.d[s];
+          Hit best;
+          best.t = tbest;
+          best.inst = __float_as_uint(d.z);
+          best.prim = __float_as_uint(d.w);
+          if (hit_better(t, e.z, prim, best)) {
+            tbest = t;
+            S.a[s].w = t;
+            S.d[s] = make_float4(u, v, __uint_as_float(e.z), __uint_as_float(prim));
+          }
+        }
+      }
+      if (ANY && occluded) {
+        finish(s, e.y, true, tbest);
+      } else if (left) {
+        S.b[s].w = __uint_as_float(kLeaf | ((left - 1u) << 28) | (first + 1u));
+      } else {
+        pop(s, stk, e.x, flags, e.y, tbest);
+      }
+    }
+  }
+}
+
+}  // namespace lp

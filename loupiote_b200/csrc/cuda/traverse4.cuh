@@ -1,0 +1,199 @@
+// Production traversal over the 4-wide collapse of the canonical tree (GpuNode4, 128 B).
+// Same hit arithmetic as traverse.cuh (lane_tri, hit_better), conservative slab test with
+// MUFU reciprocals; four child boxes are tested per node visit and the hit children are
+// visited nearest first (4-element sorting network on the entry distances), so a ray makes
+// about half the dependent node fetches of the BVH2 walk.  Closest hit is the lexicographic
+// minimum of (t, instance, primitive), hence independent of the visiting order: images are
+// bit-identical to the BVH2 kernels and to the CPU restatement.
+#pragma once
+#include "kernels.cuh"
+
+namespace lp {
+
+constexpr int kStackSize4 = 96;
+
+#define LP_CSWAP(ka, kb, ra, rb)          \
+  {                                       \
+    const bool _s = kb < ka;              \
+    const uint32_t _k = _s ? kb : ka;     \
+    const uint32_t _r = _s ? rb : ra;     \
+    kb = _s ? ka : kb;                    \
+    rb = _s ? ra : rb;                    \
+    ka = _k;                              \
+    ra = _r;                              \
+  }
+
+// Tests the four child boxes of node `idx`.  key[i] = entry distance bits (monotonic for
+// t >= 0) or 0xFFFFFFFF when child i is missed / empty; ref[i] = child reference.
+__device__ __forceinline__ void node4_test(const SceneDev &sc, uint32_t idx, const LaneRay &r,
+                                           float tmax, uint32_t key[4], uint32_t ref[4]) {
+  const float4 *np = sc.nodes4 + 8u * (size_t)idx;
+  const f8 n0 = ldg256(np), n1 = ldg256(np + 2), n2 = ldg256(np + 4), n3 = ldg256(np + 6);
+  const float4 lx = n0.lo, ly = n0.hi, lz = n1.lo, hx = n1.hi, hy = n2.lo, hz = n2.hi;
+  const float4 cr = n3.lo;  // 128-byte node = 4 x LDG.256
+  float tn;
+  bool h;
+#define LP_CHILD(i, c)                                                                     \
+  ref[i] = __float_as_uint(cr.c);                                                          \
+  h = lane_box<false>(r, mk3(lx.c, ly.c, lz.c), mk3(hx.c, hy.c, hz.c), tmax, tn) &&        \
+      ref[i] != kNoChildRef;                                                               \
+  key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
+  LP_CHILD(0, x)
+  LP_CHILD(1, y)
+  LP_CHILD(2, z)
+  LP_CHILD(3, w)
+#undef LP_CHILD
+}
+
+// One ray per thread.  Returns true (ANY) as soon as an occluder is found.
+template <bool ANY>
+__device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, float tmax, Hit &hit) {
+  hit.t = tmax;
+  hit.u = hit.v = 0.0f;
+  hit.inst = LP_INVALID_INDEX;
+  hit.prim = LP_INVALID_INDEX;
+  uint32_t cur = sc.tlas_root4;
+  if (cur == kNoChildRef) return false;
+
+  uint32_t stack[kStackSize4];
+  int sp = 0;
+  LaneRay r;
+  r.kxyz = 0;
+  r.sx = r.sy = r.sz = 0.f;
+  lane_set_world<false>(r, wo, wd);
+  bool in_blas = false;
+  uint32_t inst = 0;
+
+  for (;;) {
+    if (!(cur & kLeaf)) {
+      uint32_t key[4], ref[4];
+      node4_test(sc, cur, r, ANY ? tmax : hit.t, key, ref);
+      if (!ANY) {
+        // nearest first: sort (key, ref) ascending; missed children sort last
+        LP_CSWAP(key[0], key[1], ref[0], ref[1])
+        LP_CSWAP(key[2], key[3], ref[2], ref[3])
+        LP_CSWAP(key[0], key[2], ref[0], ref[2])
+        LP_CSWAP(key[1], key[3], ref[1], ref[3])
+        LP_CSWAP(key[1], key[2], ref[1], ref[2])
+        if (key[0] != 0xFFFFFFFFu) {
+          if (key[3] != 0xFFFFFFFFu) stack[sp++] = ref[3];
+          if (key[2] != 0xFFFFFFFFu) stack[sp++] = ref[2];
+          if (key[1] != 0xFFFFFFFFu) stack[sp++] = ref[1];
+          cur = ref[0];
+          continue;
+        }
+      } else {
+        // any hit: order is irrelevant, visit every hit child
+        uint32_t next = kNoChildRef;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (key[i] != 0xFFFFFFFFu) {
+            if (next != kNoChildRef) stack[sp++] = next;
+            next = ref[i];
+          }
+        if (next != kNoChildRef) {
+          cur = next;
+          continue;
+        }
+      }
+    } else if (!in_blas) {
+      inst = cur & 0x0FFFFFFFu;
+      const float4 *ip = sc.instances + 8u * (size_t)inst;
+      const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+      const uint32_t root = __float_as_uint(__ldg(ip + 7).y);
+      lane_set_object<false>(r, xform_point(r0, r1, r2, wo), xform_vector(r0, r1, r2, wd));
+      stack[sp++] = kSentinel;
+      in_blas = true;
+      cur = root;
+      continue;
+    } else {
+      const uint32_t first = cur & 0x0FFFFFFFu;
+      const uint32_t count = ((cur >> 28) & 7u) + 1u;
+      for (uint32_t k = 0; k < count; ++k) {
+        const float4 *tp = sc.tris + 3u * (size_t)(first + k);
+        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+        float t, u, v;
+        if (lane_tri(r, p0, p1, p2, ANY ? tmax : hit.t, t, u, v)) {
+          if (ANY) return true;
+          const uint32_t prim = __float_as_uint(p0.w);
+          if (hit_better(t, inst, prim, hit)) {
+            hit.t = t;
+            hit.u = u;
+            hit.v = v;
+            hit.inst = inst;
+            hit.prim = prim;
+          }
+        }
+      }
+    }
+    if (sp == 0) break;
+    cur = stack[--sp];
+    if (cur == kSentinel) {
+      in_blas = false;
+      lane_set_world<false>(r, wo, wd);
+      if (sp == 0) break;
+      cur = stack[--sp];
+    }
+  }
+  return false;
+}
+
+// extend / connect over the 4-wide layout; same batch scheme as kernels.cuh.
+__global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ FrameParams P,
+                                                      uint32_t bounce) {
+  const uint32_t n = bounce == 0 ? P.n_slots : P.counts[kCntNext + bounce - 1];
+  const uint32_t *queue = bounce == 0 ? nullptr : P.queue[(bounce - 1) & 1u];
+  uint32_t *work = P.counts + kCntWorkExtend + bounce;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(work, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) break;
+    const uint32_t idx = base + lane;
+    if (idx < n) {
+      const uint32_t slot = queue ? queue[idx] : idx;
+      const float4 o = P.ps.ray_o[slot], d = P.ps.ray_d[slot];
+      if (d.w >= 0.0f) {
+        Hit hit;
+        const f3 wo = mk3(o.x, o.y, o.z), wd = mk3(d.x, d.y, d.z);
+        traverse4<false>(P.sc, wo, wd, INFINITY, hit);
+        if (P.sc.n_active_lights) lights_closest(P.sc, wo, wd, 0.0f, hit);
+        P.ps.hit[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+        P.ps.hit_inst[slot] = hit.inst;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) connect4_kernel(const __grid_constant__ FrameParams P,
+                                                       uint32_t bounce, int env) {
+  const uint32_t n = P.counts[(env ? kCntEnv : kCntLight) + bounce];
+  const ShadowQueue &q = env ? P.sq_env : P.sq_light;
+  uint32_t *work = P.counts + (env ? kCntWorkEnv : kCntWorkLight) + bounce;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(work, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) break;
+    const uint32_t idx = base + lane;
+    if (idx < n) {
+      const float4 o = q.o_tmax[idx], d = q.d_slot[idx];
+      Hit hit;
+      const bool occluded =
+          traverse4<true>(P.sc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), o.w, hit);
+      if (!occluded) {
+        const uint32_t slot = __float_as_uint(d.w);
+        const float4 c = q.contrib[idx];
+        float4 r = P.ps.rad[slot];
+        r.x += c.x;
+        r.y += c.y;
+        r.z += c.z;
+        P.ps.rad[slot] = r;
+      }
+    }
+  }
+}
+
+}  // namespace lp

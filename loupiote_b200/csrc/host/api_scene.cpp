@@ -143,6 +143,7 @@ LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const
       case LP_SCENE_TLAS_NODES: s.build_derived(); *out_ptr = s.tlas.data(); *out_count = s.tlas.size(); es = sizeof(lp_bvh_node); break;
       case LP_SCENE_GPU_NODES: s.build_derived(); *out_ptr = s.gpu_nodes.data(); *out_count = s.gpu_nodes.size(); es = sizeof(GpuNode); break;
       case LP_SCENE_GPU_INSTANCES: s.build_derived(); *out_ptr = s.gpu_instances.data(); *out_count = s.gpu_instances.size(); es = sizeof(GpuInstance); break;
+      case LP_SCENE_GPU_NODES4: s.build_derived(); *out_ptr = s.gpu_nodes4.data(); *out_count = s.gpu_nodes4.size(); es = sizeof(GpuNode4); break;
       default: return fail(LP_ERR_INVALID_ARG, "unknown scene array");
     }
   } catch (const std::exception &e) {

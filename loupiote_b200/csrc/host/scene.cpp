@@ -226,6 +226,82 @@ uint32_t relayout(const lp_bvh_node *tree, const LeafEncoder &enc, std::vector<G
   return max_depth;
 }
 
+// Collapse of the SAME canonical tree into 4-wide nodes (128 bytes, SoA child boxes): a
+// node's slots start as its two canonical children; while there is room, the interior slot
+// with the largest surface area is replaced by its own two children.  Halves the dependent
+// node-fetch chain of a traversal; results are unchanged (closest hit is order independent).
+uint32_t relayout4(const lp_bvh_node *tree, const LeafEncoder &enc, std::vector<GpuNode4> &out,
+                   uint32_t &root_index) {
+  if (tree[0].count > 0) {
+    root_index = enc(tree[0]);
+    return 1;
+  }
+  if (tree[0].left_first == 0) {
+    root_index = kNoChild;
+    return 0;
+  }
+  root_index = (uint32_t)out.size();
+  const uint32_t base = root_index;
+  struct Item {
+    uint32_t canon, depth;
+  };
+  std::vector<Item> queue;
+  queue.push_back({0u, 1u});
+  uint32_t max_depth = 1;
+  auto half_area = [&](uint32_t i) {
+    const lp_bvh_node &n = tree[i];
+    const double dx = (double)n.aabb_max[0] - n.aabb_min[0], dy = (double)n.aabb_max[1] - n.aabb_min[1],
+                 dz = (double)n.aabb_max[2] - n.aabb_min[2];
+    return dx * dy + dy * dz + dz * dx;
+  };
+  for (size_t head = 0; head < queue.size(); ++head) {
+    const Item it = queue[head];
+    uint32_t slots[4];
+    int n_slots = 2;
+    slots[0] = tree[it.canon].left_first;
+    slots[1] = tree[it.canon].left_first + 1;
+    while (n_slots < 4) {
+      int best = -1;
+      double best_area = -1.0;
+      for (int s = 0; s < n_slots; ++s)
+        if (tree[slots[s]].count == 0) {
+          const double a = half_area(slots[s]);
+          if (a > best_area) {
+            best_area = a;
+            best = s;
+          }
+        }
+      if (best < 0) break;
+      const uint32_t c = tree[slots[best]].left_first;
+      slots[best] = c;  // keep canonical (near-ish) order: the pair takes the slot's place
+      for (int s = n_slots; s > best + 1; --s) slots[s] = slots[s - 1];
+      slots[best + 1] = c + 1;
+      ++n_slots;
+    }
+    GpuNode4 g;
+    for (int s = 0; s < 4; ++s) {
+      g.lo_x[s] = g.lo_y[s] = g.lo_z[s] = INFINITY;
+      g.hi_x[s] = g.hi_y[s] = g.hi_z[s] = -INFINITY;
+      g.child[s] = kNoChild;
+      g.pad[s] = 0;
+    }
+    for (int s = 0; s < n_slots; ++s) {
+      const lp_bvh_node &ch = tree[slots[s]];
+      g.lo_x[s] = ch.aabb_min[0]; g.lo_y[s] = ch.aabb_min[1]; g.lo_z[s] = ch.aabb_min[2];
+      g.hi_x[s] = ch.aabb_max[0]; g.hi_y[s] = ch.aabb_max[1]; g.hi_z[s] = ch.aabb_max[2];
+      if (ch.count > 0) {
+        g.child[s] = enc(ch);
+      } else {
+        g.child[s] = base + (uint32_t)queue.size();
+        queue.push_back({slots[s], it.depth + 1});
+      }
+      max_depth = std::max(max_depth, it.depth + 1);
+    }
+    out.push_back(g);
+  }
+  return max_depth;
+}
+
 }  // namespace
 
 void Scene::build_derived() {
@@ -285,6 +361,20 @@ void Scene::build_derived() {
   gpu_max_depth = tdepth + bdepth + 1;
   if (primitives.size() >= (1u << 28)) throw std::invalid_argument("too many triangles (>= 2^28)");
 
+  // ---- 4-wide collapse of the same trees (production traversal layout)
+  gpu_nodes4.clear();
+  gpu_nodes4.reserve((tlas.size() + nodes.size()) / 2 + 1);
+  uint32_t tdepth4 = relayout4(tlas.data(), tenc, gpu_nodes4, gpu_tlas_root4);
+  std::vector<uint32_t> blas_root4(entries.size(), 0);
+  uint32_t bdepth4 = 0;
+  for (size_t e = 0; e < entries.size(); ++e) {
+    if (entries[e].primitive_count == 0) continue;
+    LeafEncoder benc{false, entries[e].primitive_offset};
+    uint32_t d = relayout4(nodes.data() + entries[e].node_offset, benc, gpu_nodes4, blas_root4[e]);
+    bdepth4 = std::max(bdepth4, d);
+  }
+  gpu_max_stack4 = 3u * (tdepth4 + bdepth4) + 2u;  // <= 3 pushes per visited node + sentinel
+
   gpu_instances.assign(instances.size(), GpuInstance{});
   for (size_t i = 0; i < instances.size(); ++i) {
     const lp_instance &s = instances[i];
@@ -296,6 +386,7 @@ void Scene::build_derived() {
       }
     const lp_blas_entry &e = entries[s.blas];
     g.root = blas_root[s.blas];
+    g.root4 = blas_root4[s.blas];
     g.material = s.material;
     g.index_offset = e.index_offset;
     g.vertex_offset = e.vertex_offset;

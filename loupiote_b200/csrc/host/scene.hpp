@@ -25,6 +25,16 @@ static_assert(sizeof(GpuNode) == 64, "GpuNode must be 64 bytes");
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kNoChild = 0x7FFFFFFFu;
 
+// 128-byte 4-wide traversal node (collapse of the same tree): child boxes as structure of
+// arrays so each plane of all four children is one LDG.128; empty slots have child = kNoChild.
+struct GpuNode4 {
+  float lo_x[4], lo_y[4], lo_z[4];
+  float hi_x[4], hi_y[4], hi_z[4];
+  uint32_t child[4];
+  uint32_t pad[4];
+};
+static_assert(sizeof(GpuNode4) == 128, "GpuNode4 must be 128 bytes");
+
 // 128-byte instance record: rows of world->object and object->world 3x4 + ids.
 struct GpuInstance {
   float w2o[12];
@@ -34,7 +44,8 @@ struct GpuInstance {
   uint32_t index_offset;  // global offset into indices (3 per triangle)
   uint32_t vertex_offset; // global offset into vertices
   uint32_t blas;
-  uint32_t pad[3];
+  uint32_t root4;         // child reference of the BLAS root in the 4-wide node array
+  uint32_t pad[2];
 };
 static_assert(sizeof(GpuInstance) == 128, "GpuInstance must be 128 bytes");
 
@@ -61,6 +72,9 @@ struct Scene {
   std::vector<GpuInstance> gpu_instances;
   uint32_t gpu_tlas_root = 0;  // child reference (interior index, leaf, or kNoChild)
   uint32_t gpu_max_depth = 0;
+  std::vector<GpuNode4> gpu_nodes4;
+  uint32_t gpu_tlas_root4 = 0;
+  uint32_t gpu_max_stack4 = 0;
   bool derived_dirty = true;
 
   Scene();
