@@ -71,7 +71,7 @@ struct lp_device {
 
 struct lp_scene_gpu {
   lp_device *dev = nullptr;
-  DevBuf<float4> nodes, nodes4, tris, instances, vertices, materials, emission, lights;
+  DevBuf<float4> nodes, nodes4, nodes4h, tris, instances, vertices, materials, emission, lights;
   DevBuf<uint32_t> indices, active_lights;
   SceneDev sc{};
   size_t node_bytes = 0, tri_bytes = 0, total_bytes = 0;
@@ -290,11 +290,15 @@ void query_end(lp_renderer *r) {
 }
 
 // Launch of the traversal kernels.  cfg.traversal_variant selects the implementation:
-//   0 (default) one ray per thread, warps pull 32-ray batches from a global cursor
-//               (kernels.cuh) -- the fastest measured so far
-//   1..         persistent warps with per-lane ray replacement and postponed triangle /
-//               instance-entry phases (trace_persistent.cuh) at several settings; measured
-//               slower on B200 (DESIGN.md "Measured alternatives"), kept for tuning runs
+//   0 / 14 (production) hybrid: coherent primary rays one per thread over the 4-wide fp16
+//               nodes (traverse4.cuh); bounce and shadow rays through the shared-memory ray
+//               pool (trace_pool.cuh), also over the 4-wide fp16 nodes
+//   15          the first version: canonical BVH2, one ray per thread (kernels.cuh)
+//   1..9        persistent lanes with ray replacement + postponed phases (trace_persistent.cuh)
+//   10 / 13     4-wide nodes, one ray per thread (fp32 / fp16 boxes)
+//   11 / 12     ray pool for every ray (fp32 / fp16 boxes)
+// count_stats always runs the canonical BVH2 walk (exact slab test): its counters define the
+// roofline and equal the CPU restatement's.  Measurements: DESIGN.md section 6.
 template <typename K>
 int cached_grid(K kernel, int sm_count) {
   static int grid = 0;  // one per instantiation
@@ -330,7 +334,9 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
                   bool stats) {
   cudaStream_t st = r->dev->stream;
   const int sm = r->dev->sm_count;
-  switch (r->cfg.traversal_variant) {
+  // 0 = production = 14 (hybrid); 15 = the first version (BVH2, one ray per thread)
+  const uint32_t variant = r->cfg.traversal_variant == 0 ? 14u : r->cfg.traversal_variant;
+  switch (variant) {
     default:
       if (any) {
         if (stats) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
@@ -349,13 +355,19 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
     case 8: launch_persistent<20, 8, 4, 10>(r, P, b, any, env, stats); break;
     case 9: launch_persistent<12, 6, 12, 10>(r, P, b, any, env, stats); break;
     case 11:
-    case 12: {  // ray pool in shared memory (trace_pool.cuh); STATS keeps the canonical walk
+    case 12:
+    case 14: {  // ray pool in shared memory (trace_pool.cuh); STATS keeps the canonical walk
       if (stats) {
         if (any) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
         else extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
         break;
       }
-      const bool il = r->cfg.traversal_variant == 12;
+      if (variant == 14 && !any && b == 0) {
+        // coherent primary rays: one ray per thread keeps the 8x4-tile locality in L1
+        extend4_kernel<true><<<cached_grid(extend4_kernel<true>, sm), 128, 0, st>>>(P, b);
+        break;
+      }
+      const bool il = variant != 11;  // 12, 14: fp16 node boxes
       const int g_any = il ? cached_grid(trace_pool_kernel<true, true>, sm)
                            : cached_grid(trace_pool_kernel<true, false>, sm);
       const int g_closest = il ? cached_grid(trace_pool_kernel<false, true>, sm)
@@ -370,13 +382,17 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
       break;
     }
     case 10:  // 4-wide collapse, one ray per thread (STATS keeps the canonical BVH2 walk)
+    case 13:  // ... with fp16 node boxes
       if (stats) {
         if (any) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
         else extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
+      } else if (variant == 13) {
+        if (any) connect4_kernel<true><<<cached_grid(connect4_kernel<true>, sm), 128, 0, st>>>(P, b, env);
+        else extend4_kernel<true><<<cached_grid(extend4_kernel<true>, sm), 128, 0, st>>>(P, b);
       } else if (any) {
-        connect4_kernel<<<cached_grid(connect4_kernel, sm), 128, 0, st>>>(P, b, env);
+        connect4_kernel<false><<<cached_grid(connect4_kernel<false>, sm), 128, 0, st>>>(P, b, env);
       } else {
-        extend4_kernel<<<cached_grid(extend4_kernel, sm), 128, 0, st>>>(P, b);
+        extend4_kernel<false><<<cached_grid(extend4_kernel<false>, sm), 128, 0, st>>>(P, b);
       }
       break;
     case 1: launch_persistent<8, 4, 4, 8>(r, P, b, any, env, stats); break;
@@ -539,7 +555,12 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   };
   up(g->nodes, s.gpu_nodes.data(), s.gpu_nodes.size() * sizeof(GpuNode));
   up(g->nodes4, s.gpu_nodes4.data(), s.gpu_nodes4.size() * sizeof(GpuNode4));
-  up(g->tris, s.primitives.data(), s.primitives.size() * sizeof(lp_bvh_primitive));
+  up(g->nodes4h, s.gpu_nodes4h.data(), s.gpu_nodes4h.size() * sizeof(GpuNode4h));
+  // triangles: canonical 48-byte primitives padded to 64 bytes (two aligned 256-bit loads)
+  std::vector<float> tris64(s.primitives.size() * 16, 0.0f);
+  for (size_t i = 0; i < s.primitives.size(); ++i)
+    std::memcpy(&tris64[16 * i], &s.primitives[i], sizeof(lp_bvh_primitive));
+  up(g->tris, tris64.data(), tris64.size() * sizeof(float));
   up(g->instances, s.gpu_instances.data(), s.gpu_instances.size() * sizeof(GpuInstance));
   up(g->vertices, s.vertices.data(), s.vertices.size() * sizeof(lp_vertex));
   up(g->materials, s.materials.data(), s.materials.size() * sizeof(lp_material));
@@ -566,9 +587,10 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   sc.n_materials = (uint32_t)s.materials.size();
   sc.tlas_root = s.gpu_tlas_root;
   sc.nodes4 = g->nodes4.ptr;
+  sc.nodes4h = g->nodes4h.ptr;
   sc.tlas_root4 = s.gpu_tlas_root4;
   g->node_bytes = s.gpu_nodes.size() * sizeof(GpuNode) + s.gpu_nodes4.size() * sizeof(GpuNode4);
-  g->tri_bytes = s.primitives.size() * sizeof(lp_bvh_primitive);
+  g->tri_bytes = s.primitives.size() * 64;
   g->total_bytes = g->node_bytes + g->tri_bytes + s.gpu_instances.size() * sizeof(GpuInstance) +
                    s.vertices.size() * sizeof(lp_vertex) + s.indices.size() * 4 +
                    s.materials.size() * 48 + s.lights.size() * sizeof(lp_light);

@@ -21,6 +21,7 @@ constexpr int kStackSize = 64;
 
 // Scene buffers as the kernels see them (all 16-byte vector loads).
 struct SceneDev {
+  const float4 *nodes4h;    // 4 x float4 per 64-byte 4-wide node with fp16 boxes
   const float4 *nodes4;     // 8 x float4 per 128-byte 4-wide node (production traversal)
   uint32_t tlas_root4;      // child reference into nodes4
   const float4 *nodes;      // 4 x float4 per 64-byte node

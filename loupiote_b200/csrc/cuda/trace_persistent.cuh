@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS)
       if (__popc(m_tri) >= TRI_MIN || m_node == 0u || aging) {
         const uint32_t first = cur & 0x0FFFFFFFu;
         const uint32_t left = (cur >> 28) & 7u;  // triangles after this one
-        const float4 *tp = sc.tris + 3u * (size_t)first;
-        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+        float4 p0, p1, p2;
+        load_tri(sc, first, p0, p1, p2);
         if (STATS) cnt[1]++;
         float t, u, v;
         if (lane_tri(r, p0, p1, p2, tmax, t, u, v)) {

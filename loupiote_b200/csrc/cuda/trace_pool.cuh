@@ -22,6 +22,7 @@ namespace lp {
 constexpr int kPool = 64;                // rays resident per warp
 constexpr int kPoolStack = kStackSize4;  // traversal stack entries per ray (global scratch)
 constexpr int kPoolWarps = 4;            // warps per block
+constexpr int kRing = 8;                 // newest stack entries of a ray kept in shared memory
 
 enum : uint32_t { kStEmpty = 0u, kStNode = 1u, kStEntry = 2u, kStTri = 3u };
 constexpr uint32_t kFlagInBlas = 4u;
@@ -31,12 +32,13 @@ struct PoolSmem {
   float4 b[kPool];  // 1/direction.xyz (current space), cur (bits)
   float4 c[kPool];  // shear sx, sy, sz, kxyz (bits)
   float4 d[kPool];  // hit u, v, instance (bits), primitive (bits)
-  uint4 e[kPool];   // sp, item, instance being traversed, unused
+  uint4 e[kPool];   // stack (sp | ring base << 16), item, instance being traversed, unused
+  uint32_t ring[kRing * kPool];  // entry i of slot s at ring[(i % kRing) * kPool + s]
   uint32_t state[kPool];  // bits 0..1 = state, bit 2 = inside a BLAS
   uint32_t list[32];
 };
 
-template <bool ANY, bool IL>
+template <bool ANY, bool HALF>
 __global__ void __launch_bounds__(32 * kPoolWarps)
     trace_pool_kernel(const __grid_constant__ FrameParams P, uint32_t bounce, int env,
                       uint32_t *__restrict__ stack_scratch) {
@@ -59,9 +61,9 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
   const unsigned lt_mask = (1u << lane) - 1u;
   const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t total_warps = (gridDim.x * blockDim.x) >> 5;
-  // stack of pool slot s: IL = false: kPoolStack contiguous words per slot; IL = true:
-  // interleaved by slot (entry d of slot s at d * kPool + s)
-  constexpr uint32_t SBASE = IL ? 1u : (uint32_t)kPoolStack, SSTRIDE = IL ? (uint32_t)kPool : 1u;
+  // overflow stack of pool slot s, interleaved by slot: entry d at d * kPool + s (measured
+  // faster than kPoolStack contiguous words per slot)
+  constexpr uint32_t SBASE = 1u, SSTRIDE = (uint32_t)kPool;
   uint32_t *stack_base = stack_scratch + (size_t)warp_id * (kPool * kPoolStack);
 
   uint32_t chunk = n / (total_warps * 4u);
@@ -110,15 +112,36 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
     }
     S.state[s] = kStEmpty;
   };
+  // Traversal stack of a pool slot: entries [base, sp) live in the shared-memory ring, older
+  // entries [0, base) in the global scratch.  The pop a node fetch depends on was the top
+  // long-scoreboard stall when the whole stack was in global memory (ncu).
+  auto push = [&](uint32_t s, uint32_t *stk, uint32_t &spb, uint32_t x) {
+    uint32_t sp = spb & 0xFFFFu, base = spb >> 16;
+    if (sp - base == (uint32_t)kRing) {
+      stk[base * SSTRIDE] = S.ring[(base & (kRing - 1)) * kPool + s];
+      ++base;
+    }
+    S.ring[(sp & (kRing - 1)) * kPool + s] = x;
+    ++sp;
+    spb = sp | (base << 16);
+  };
   // pop the next reference of slot s (handles leaving an instance); writes cur/sp/state
-  auto pop = [&](uint32_t s, uint32_t *stk, uint32_t sp, uint32_t flags, uint32_t item,
+  auto pop = [&](uint32_t s, uint32_t *stk, uint32_t spb, uint32_t flags, uint32_t item,
                  float tbest) {
+    uint32_t sp = spb & 0xFFFFu, base = spb >> 16;
     for (;;) {
       if (sp == 0u) {
         finish(s, item, false, tbest);
         return;
       }
-      const uint32_t c = stk[(--sp) * SSTRIDE];
+      --sp;
+      uint32_t c;
+      if (sp >= base) {
+        c = S.ring[(sp & (kRing - 1)) * kPool + s];
+      } else {
+        c = stk[sp * SSTRIDE];
+        base = sp;
+      }
       if (c == kSentinel) {
         flags &= ~kFlagInBlas;
         float4 o4, d4;
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
         continue;
       }
       S.b[s].w = __uint_as_float(c);
-      S.e[s].x = sp;
+      S.e[s].x = sp | (base << 16);
       const uint32_t st = (c & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode;
       S.state[s] = st | (flags & kFlagInBlas);
       return;
@@ -248,9 +271,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
       LaneRay r;
       r.o = mk3(a.x, a.y, a.z);
       r.idir = mk3(b.x, b.y, b.z);
-      uint32_t sp = e.x;
+      uint32_t spb = e.x;
       uint32_t key[4], ref[4];
-      node4_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
+      if (HALF) node4h_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
+      else node4_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
       uint32_t next = kNoChildRef;
       if (!ANY) {
         LP_CSWAP(key[0], key[1], ref[0], ref[1])
@@ -259,26 +283,26 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
         LP_CSWAP(key[1], key[3], ref[1], ref[3])
         LP_CSWAP(key[1], key[2], ref[1], ref[2])
         if (key[0] != 0xFFFFFFFFu) {
-          if (key[3] != 0xFFFFFFFFu) stk[(sp++) * SSTRIDE] = ref[3];
-          if (key[2] != 0xFFFFFFFFu) stk[(sp++) * SSTRIDE] = ref[2];
-          if (key[1] != 0xFFFFFFFFu) stk[(sp++) * SSTRIDE] = ref[1];
+          if (key[3] != 0xFFFFFFFFu) push(s, stk, spb, ref[3]);
+          if (key[2] != 0xFFFFFFFFu) push(s, stk, spb, ref[2]);
+          if (key[1] != 0xFFFFFFFFu) push(s, stk, spb, ref[1]);
           next = ref[0];
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (key[i] != 0xFFFFFFFFu) {
-            if (next != kNoChildRef) stk[(sp++) * SSTRIDE] = next;
+            if (next != kNoChildRef) push(s, stk, spb, next);
             next = ref[i];
           }
       }
       if (next != kNoChildRef) {
         S.b[s].w = __uint_as_float(next);
-        if (sp != e.x) S.e[s].x = sp;
+        if (spb != e.x) S.e[s].x = spb;
         S.state[s] =
             ((next & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode) | flags;
       } else {
-        pop(s, stk, sp, flags, e.y, a.w);
+        pop(s, stk, spb, flags, e.y, a.w);
       }
     } else if (phase == kStEntry) {
       // -------------------------------------------------------------- enter an instance
@@ -295,8 +319,9 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
       S.a[s] = make_float4(r.o.x, r.o.y, r.o.z, tbest);
       S.b[s] = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(root));
       S.c[s] = make_float4(r.sx, r.sy, r.sz, __int_as_float(r.kxyz));
-      stk[e.x * SSTRIDE] = kSentinel;
-      S.e[s] = make_uint4(e.x + 1u, e.y, inst, 0u);
+      uint32_t spb = e.x;
+      push(s, stk, spb, kSentinel);
+      S.e[s] = make_uint4(spb, e.y, inst, 0u);
       S.state[s] = ((root & kLeaf) ? kStTri : kStNode) | kFlagInBlas;
     } else {
       // -------------------------------------------------------------- one triangle
@@ -311,8 +336,8 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
       const uint32_t cur = __float_as_uint(S.b[s].w);
       const uint32_t first = cur & 0x0FFFFFFFu;
       const uint32_t left = (cur >> 28) & 7u;
-      const float4 *tp = sc.tris + 3u * (size_t)first;
-      const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+      float4 p0, p1, p2;
+      load_tri(sc, first, p0, p1, p2);
       float t, u, v;
       bool occluded = false;
       if (lane_tri(r, p0, p1, p2, tbest, t, u, v)) {

@@ -94,6 +94,17 @@ __device__ __forceinline__ bool lane_box(const LaneRay &r, f3 lo, f3 hi, float t
   return tn <= __fmul_rn(tf, EXACT ? 1.0000004f : 1.000001f);
 }
 
+// Triangle i of the GPU triangle array: the 48-byte canonical primitive padded to 64 bytes so
+// that it is two aligned LDG.256 (two L1 wavefronts per lane instead of three LDG.128).
+__device__ __forceinline__ void load_tri(const SceneDev &sc, uint32_t i, float4 &p0, float4 &p1,
+                                         float4 &p2) {
+  const float4 *tp = sc.tris + 4u * (size_t)i;
+  const f8 a = ldg256(tp), b = ldg256(tp + 2);
+  p0 = a.lo;
+  p1 = a.hi;
+  p2 = b.lo;
+}
+
 // watertight test against (0, tmax]; u weights v1, v weights v2
 __device__ __forceinline__ bool lane_tri(const LaneRay &r, float4 p0, float4 p1, float4 p2,
                                          float tmax, float &t_out, float &u_out, float &v_out) {
@@ -203,8 +214,8 @@ __device__ __forceinline__ bool traverse(const SceneDev &sc, f3 wo, f3 wd, float
       const uint32_t first = cur & 0x0FFFFFFFu;
       const uint32_t count = ((cur >> 28) & 7u) + 1u;
       for (uint32_t k = 0; k < count; ++k) {
-        const float4 *tp = sc.tris + 3u * (size_t)(first + k);
-        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+        float4 p0, p1, p2;
+        load_tri(sc, first + k, p0, p1, p2);
         if (STATS) cnt[1]++;
         float t, u, v;
         if (lane_tri(r, p0, p1, p2, ANY ? tmax : hit.t, t, u, v)) {

@@ -6,6 +6,8 @@
 // minimum of (t, instance, primitive), hence independent of the visiting order: images are
 // bit-identical to the BVH2 kernels and to the CPU restatement.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace lp {
@@ -45,8 +47,41 @@ __device__ __forceinline__ void node4_test(const SceneDev &sc, uint32_t idx, con
 #undef LP_CHILD
 }
 
+__device__ __forceinline__ float2 unpack_half2(float w) {
+  const uint32_t u = __float_as_uint(w);
+  return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+}
+
+// Same test on the 64-byte fp16 node (boxes rounded outwards on the host): 2 x LDG.256, i.e.
+// two L1 wavefronts per lane and visit instead of four.
+__device__ __forceinline__ void node4h_test(const SceneDev &sc, uint32_t idx, const LaneRay &r,
+                                            float tmax, uint32_t key[4], uint32_t ref[4]) {
+  const float4 *np = sc.nodes4h + 4u * (size_t)idx;
+  const f8 n0 = ldg256(np), n1 = ldg256(np + 2);
+  const float2 lx01 = unpack_half2(n0.lo.x), lx23 = unpack_half2(n0.lo.y);
+  const float2 ly01 = unpack_half2(n0.lo.z), ly23 = unpack_half2(n0.lo.w);
+  const float2 lz01 = unpack_half2(n0.hi.x), lz23 = unpack_half2(n0.hi.y);
+  const float2 hx01 = unpack_half2(n0.hi.z), hx23 = unpack_half2(n0.hi.w);
+  const float2 hy01 = unpack_half2(n1.lo.x), hy23 = unpack_half2(n1.lo.y);
+  const float2 hz01 = unpack_half2(n1.lo.z), hz23 = unpack_half2(n1.lo.w);
+  const float4 cr = n1.hi;
+  float tn;
+  bool h;
+#define LP_CHILDH(i, c, L, H, m)                                                             \
+  ref[i] = __float_as_uint(cr.c);                                                            \
+  h = lane_box<false>(r, mk3(lx##L.m, ly##L.m, lz##L.m), mk3(hx##L.m, hy##L.m, hz##L.m),     \
+                      tmax, tn) &&                                                           \
+      ref[i] != kNoChildRef;                                                                 \
+  key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
+  LP_CHILDH(0, x, 01, 01, x)
+  LP_CHILDH(1, y, 01, 01, y)
+  LP_CHILDH(2, z, 23, 23, x)
+  LP_CHILDH(3, w, 23, 23, y)
+#undef LP_CHILDH
+}
+
 // One ray per thread.  Returns true (ANY) as soon as an occluder is found.
-template <bool ANY>
+template <bool ANY, bool HALF>
 __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, float tmax, Hit &hit) {
   hit.t = tmax;
   hit.u = hit.v = 0.0f;
@@ -67,7 +102,8 @@ __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, floa
   for (;;) {
     if (!(cur & kLeaf)) {
       uint32_t key[4], ref[4];
-      node4_test(sc, cur, r, ANY ? tmax : hit.t, key, ref);
+      if (HALF) node4h_test(sc, cur, r, ANY ? tmax : hit.t, key, ref);
+      else node4_test(sc, cur, r, ANY ? tmax : hit.t, key, ref);
       if (!ANY) {
         // nearest first: sort (key, ref) ascending; missed children sort last
         LP_CSWAP(key[0], key[1], ref[0], ref[1])
@@ -110,8 +146,8 @@ __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, floa
       const uint32_t first = cur & 0x0FFFFFFFu;
       const uint32_t count = ((cur >> 28) & 7u) + 1u;
       for (uint32_t k = 0; k < count; ++k) {
-        const float4 *tp = sc.tris + 3u * (size_t)(first + k);
-        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+        float4 p0, p1, p2;
+        load_tri(sc, first + k, p0, p1, p2);
         float t, u, v;
         if (lane_tri(r, p0, p1, p2, ANY ? tmax : hit.t, t, u, v)) {
           if (ANY) return true;
@@ -139,6 +175,7 @@ __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, floa
 }
 
 // extend / connect over the 4-wide layout; same batch scheme as kernels.cuh.
+template <bool HALF>
 __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ FrameParams P,
                                                       uint32_t bounce) {
   const uint32_t n = bounce == 0 ? P.n_slots : P.counts[kCntNext + bounce - 1];
@@ -157,7 +194,7 @@ __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ Fr
       if (d.w >= 0.0f) {
         Hit hit;
         const f3 wo = mk3(o.x, o.y, o.z), wd = mk3(d.x, d.y, d.z);
-        traverse4<false>(P.sc, wo, wd, INFINITY, hit);
+        traverse4<false, HALF>(P.sc, wo, wd, INFINITY, hit);
         if (P.sc.n_active_lights) lights_closest(P.sc, wo, wd, 0.0f, hit);
         P.ps.hit[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
         P.ps.hit_inst[slot] = hit.inst;
@@ -166,6 +203,7 @@ __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ Fr
   }
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(128) connect4_kernel(const __grid_constant__ FrameParams P,
                                                        uint32_t bounce, int env) {
   const uint32_t n = P.counts[(env ? kCntEnv : kCntLight) + bounce];
@@ -182,7 +220,7 @@ __global__ void __launch_bounds__(128) connect4_kernel(const __grid_constant__ F
       const float4 o = q.o_tmax[idx], d = q.d_slot[idx];
       Hit hit;
       const bool occluded =
-          traverse4<true>(P.sc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), o.w, hit);
+          traverse4<true, HALF>(P.sc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), o.w, hit);
       if (!occluded) {
         const uint32_t slot = __float_as_uint(d.w);
         const float4 c = q.contrib[idx];

@@ -226,6 +226,70 @@ uint32_t relayout(const lp_bvh_node *tree, const LeafEncoder &enc, std::vector<G
   return max_depth;
 }
 
+// ---- IEEE binary16 conversion with directed rounding (for the fp16 node boxes)
+float half_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const uint32_t exp = (h >> 10) & 0x1Fu, mant = h & 0x3FFu;
+  uint32_t bits;
+  if (exp == 0) {
+    if (mant == 0) {
+      bits = sign;
+    } else {
+      const float v = (float)mant * (1.0f / 16777216.0f);  // subnormal: mant * 2^-24
+      std::memcpy(&bits, &v, 4);
+      bits |= sign;
+    }
+  } else if (exp == 31) {
+    bits = sign | 0x7F800000u | (mant << 13);
+  } else {
+    bits = sign | ((exp + 112u) << 23) | (mant << 13);
+  }
+  float out;
+  std::memcpy(&out, &bits, 4);
+  return out;
+}
+
+uint16_t float_to_half_rn(float f) {
+  uint32_t x;
+  std::memcpy(&x, &f, 4);
+  const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+  x &= 0x7FFFFFFFu;
+  if (x >= 0x7F800000u) return sign | (x > 0x7F800000u ? 0x7E00u : 0x7C00u);
+  if (x >= 0x477FF000u) return sign | 0x7C00u;  // >= 65520 rounds to infinity
+  if (x < 0x33000001u) return sign;             // <= 2^-25 rounds to zero
+  if (x < 0x38800000u) {                        // half subnormal
+    float v;
+    std::memcpy(&v, &x, 4);
+    return sign | (uint16_t)std::lrintf(v * 16777216.0f);
+  }
+  const uint32_t mant = x & 0x7FFFFFu, exp = (x >> 23) - 112u;
+  uint32_t h = (exp << 10) | (mant >> 13);
+  const uint32_t rem = mant & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return sign | (uint16_t)h;
+}
+
+uint16_t half_next_up(uint16_t h) {
+  if (h & 0x8000u) return (h & 0x7FFFu) == 0 ? 0x0001u : (uint16_t)(h - 1);
+  return h == 0x7C00u ? h : (uint16_t)(h + 1);
+}
+uint16_t half_next_down(uint16_t h) {
+  if (!(h & 0x8000u)) return h == 0 ? 0x8001u : (uint16_t)(h - 1);
+  return h == 0xFC00u ? h : (uint16_t)(h + 1);
+}
+uint16_t float_to_half_up(float f) {  // smallest half >= f
+  if (std::isnan(f)) return 0x7E00u;
+  uint16_t h = float_to_half_rn(f);
+  if (half_to_float(h) < f) h = half_next_up(h);
+  return h;
+}
+uint16_t float_to_half_down(float f) {  // largest half <= f
+  if (std::isnan(f)) return 0x7E00u;
+  uint16_t h = float_to_half_rn(f);
+  if (half_to_float(h) > f) h = half_next_down(h);
+  return h;
+}
+
 // Collapse of the SAME canonical tree into 4-wide nodes (128 bytes, SoA child boxes): a
 // node's slots start as its two canonical children; while there is room, the interior slot
 // with the largest surface area is replaced by its own two children.  Halves the dependent
@@ -374,6 +438,23 @@ void Scene::build_derived() {
     bdepth4 = std::max(bdepth4, d);
   }
   gpu_max_stack4 = 3u * (tdepth4 + bdepth4) + 2u;  // <= 3 pushes per visited node + sentinel
+
+  // ---- 64-byte variant of the 4-wide nodes: child boxes in fp16, rounded OUTWARDS (lo
+  // towards -inf, hi towards +inf) so the slab test stays conservative
+  gpu_nodes4h.resize(gpu_nodes4.size());
+  for (size_t i = 0; i < gpu_nodes4.size(); ++i) {
+    const GpuNode4 &n = gpu_nodes4[i];
+    GpuNode4h &h = gpu_nodes4h[i];
+    for (int s = 0; s < 4; ++s) {
+      h.lo_x[s] = float_to_half_down(n.lo_x[s]);
+      h.lo_y[s] = float_to_half_down(n.lo_y[s]);
+      h.lo_z[s] = float_to_half_down(n.lo_z[s]);
+      h.hi_x[s] = float_to_half_up(n.hi_x[s]);
+      h.hi_y[s] = float_to_half_up(n.hi_y[s]);
+      h.hi_z[s] = float_to_half_up(n.hi_z[s]);
+      h.child[s] = n.child[s];
+    }
+  }
 
   gpu_instances.assign(instances.size(), GpuInstance{});
   for (size_t i = 0; i < instances.size(); ++i) {

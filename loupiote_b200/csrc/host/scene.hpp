@@ -35,6 +35,14 @@ struct GpuNode4 {
 };
 static_assert(sizeof(GpuNode4) == 128, "GpuNode4 must be 128 bytes");
 
+// 64-byte 4-wide node: the same child boxes in fp16, rounded outwards (2 x LDG.256).
+struct GpuNode4h {
+  uint16_t lo_x[4], lo_y[4], lo_z[4], hi_x[4];  // first 32 bytes
+  uint16_t hi_y[4], hi_z[4];                    // second 32 bytes ...
+  uint32_t child[4];
+};
+static_assert(sizeof(GpuNode4h) == 64, "GpuNode4h must be 64 bytes");
+
 // 128-byte instance record: rows of world->object and object->world 3x4 + ids.
 struct GpuInstance {
   float w2o[12];
@@ -73,6 +81,7 @@ struct Scene {
   uint32_t gpu_tlas_root = 0;  // child reference (interior index, leaf, or kNoChild)
   uint32_t gpu_max_depth = 0;
   std::vector<GpuNode4> gpu_nodes4;
+  std::vector<GpuNode4h> gpu_nodes4h;
   uint32_t gpu_tlas_root4 = 0;
   uint32_t gpu_max_stack4 = 0;
   bool derived_dirty = true;

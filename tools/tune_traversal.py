@@ -22,7 +22,7 @@ import loupiote_b200 as lb  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="spheres-1M-1080p-8b")
-    ap.add_argument("--variants", default="1,0,2,3,4,5,6,7")
+    ap.add_argument("--variants", default="15,0,1,10,13,11,12")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--spp", type=int, default=4)
     args = ap.parse_args()
