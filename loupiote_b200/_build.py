@@ -25,15 +25,19 @@ SOURCES = [
     CSRC / "host" / "api_scene.cpp",
     CSRC / "cuda" / "api_render.cu",
 ]
+# translation units whose arithmetic never decides a hit: FMA contraction on
+SOURCES_FMAD = [
+    CSRC / "cuda" / "shade_kernel.cu",
+]
 
-NVCC_FLAGS = [
+COMMON_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    # FMA contraction is explicit in the kernels (arithmetic contract)
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3,-ffp-contract=off",
-    "-shared",
 ]
+# FMA contraction is explicit in the kernels (arithmetic contract)
+NVCC_FLAGS = COMMON_FLAGS + ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]
+NVCC_FLAGS_FMAD = COMMON_FLAGS + ["-fmad=true", "-prec-div=true", "-prec-sqrt=true"]
 
 
 def _nvcc() -> str:
@@ -50,30 +54,56 @@ def _fingerprint() -> str:
     for f in files:
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + NVCC_FLAGS_FMAD).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the library if sources changed since the last build; returns its path."""
+def build(force: bool = False, verbose: bool = False, variant: str = "",
+          defines: tuple = ()) -> Path:
+    """Compile the library if sources changed since the last build; returns its path.
+
+    `variant` / `defines` build a tuning copy libloupiote_b200.<variant>.so with extra -D
+    flags (A/B measurements on the GPU box: LP_LIB_VARIANT=<variant> selects it at load)."""
     LIB_DIR.mkdir(exist_ok=True)
-    stamp = LIB_DIR / "build.stamp"
-    fp = _fingerprint()
-    if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == fp:
-        return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, f"-I{ROOT / 'include'}", "-o", str(LIB_PATH)]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    lib_path = LIB_DIR / (f"libloupiote_b200.{variant}.so" if variant else LIB_PATH.name)
+    stamp = LIB_DIR / (f"build.{variant}.stamp" if variant else "build.stamp")
+    fp = _fingerprint() + " " + " ".join(defines)
+    if not force and lib_path.exists() and stamp.exists() and stamp.read_text() == fp:
+        return lib_path
+    obj_dir = LIB_DIR / (f"obj.{variant}" if variant else "obj")
+    obj_dir.mkdir(exist_ok=True)
+    jobs = [(src, NVCC_FLAGS) for src in SOURCES] + [(src, NVCC_FLAGS_FMAD) for src in SOURCES_FMAD]
+    procs, objs = [], []
+    for src, flags in jobs:  # one nvcc per translation unit, all in parallel
+        obj = obj_dir / (src.stem + ".o")
+        objs.append(obj)
+        cmd = [_nvcc(), *flags, *[f"-D{d}" for d in defines], f"-I{ROOT / 'include'}", "-c",
+               str(src), "-o", str(obj)]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                      text=True))
+    failed = False
+    for proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0 or verbose:
+            sys.stderr.write(out)
+        failed |= proc.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libloupiote_b200.so")
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(lib_path),
+            *[str(o) for o in objs]]
+    proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
-        raise RuntimeError("nvcc failed building libloupiote_b200.so")
-    if verbose:
-        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed linking libloupiote_b200.so")
     stamp.write_text(fp)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m loupiote_b200._build [--force] [-v] [--variant NAME -DX=1 -DY ...]
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    _defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=_variant,
+                defines=_defs))

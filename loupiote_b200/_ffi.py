@@ -3,6 +3,7 @@ reference would write as an `extern "C"` block)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import _build
@@ -163,11 +164,17 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         path: Path = _build.LIB_PATH
-        try:
-            path = _build.build()
-        except Exception:
+        variant = os.environ.get("LP_LIB_VARIANT", "")  # tuning copies, see _build.build
+        if variant:
+            path = _build.LIB_DIR / f"libloupiote_b200.{variant}.so"
             if not path.exists():
-                raise
+                raise FileNotFoundError(path)
+        else:
+            try:
+                path = _build.build()
+            except Exception:
+                if not path.exists():
+                    raise
         cdll = C.CDLL(str(path))
         for name, (res, args) in _PROTOTYPES.items():
             fn = getattr(cdll, name)

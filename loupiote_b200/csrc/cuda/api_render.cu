@@ -147,7 +147,6 @@ struct lp_renderer {
   double kt_ms[4] = {0, 0, 0, 0};
   uint64_t kt_launches[4] = {0, 0, 0, 0};
 
-  int grid_shade = 0;
 };
 
 namespace {
@@ -363,15 +362,39 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
         break;
       }
       if (variant == 14 && !any && b == 0) {
-        // coherent primary rays: one ray per thread keeps the 8x4-tile locality in L1
-        extend4_kernel<true><<<cached_grid(extend4_kernel<true>, sm), 128, 0, st>>>(P, b);
+        // coherent primary rays: one ray per thread keeps the 8x4-tile locality in L1; the
+        // camera rays are generated in the kernel (no generate_kernel, see fused_raygen)
+        extend4_kernel<true, true><<<cached_grid(extend4_kernel<true, true>, sm), 128, 0, st>>>(P, b);
         break;
       }
       const bool il = variant != 11;  // 12, 14: fp16 node boxes
-      const int g_any = il ? cached_grid(trace_pool_kernel<true, true>, sm)
-                           : cached_grid(trace_pool_kernel<true, false>, sm);
-      const int g_closest = il ? cached_grid(trace_pool_kernel<false, true>, sm)
-                               : cached_grid(trace_pool_kernel<false, false>, sm);
+      // LP_POOL_BLOCKS (tuning knob): resident pool blocks per SM.  Fewer blocks than the
+      // shared-memory limit leave more of the SM's 256 KB to the L1 cache (the carve-out is
+      // set to what the chosen number of blocks needs).
+      static int pool_grid = 0;  // the four instantiations share one launch shape
+      if (!pool_grid) {
+        const char *e = std::getenv("LP_POOL_BLOCKS");
+        const int want = e ? std::atoi(e) : 0;
+        int per_sm = 64;
+        for (auto kernel : {trace_pool_kernel<true, true>, trace_pool_kernel<true, false>,
+                            trace_pool_kernel<false, true>, trace_pool_kernel<false, false>}) {
+          int k_sm = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_sm, kernel, 128, 0) != cudaSuccess ||
+              k_sm < 1)
+            k_sm = 1;
+          per_sm = std::min(per_sm, k_sm);
+        }
+        if (want > 0 && want < per_sm) {
+          per_sm = want;
+          const int pct = std::min(100, (int)((per_sm * (sizeof(PoolSmem) * kPoolWarps + 1024) * 100 +
+                                               (228 * 1024 - 1)) / (228 * 1024)));
+          for (auto kernel : {trace_pool_kernel<true, true>, trace_pool_kernel<true, false>,
+                              trace_pool_kernel<false, true>, trace_pool_kernel<false, false>})
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+        pool_grid = per_sm * sm;
+      }
+      const int g_any = pool_grid, g_closest = pool_grid;
       const size_t need = (size_t)std::max(g_any, g_closest) * kPoolWarps * kPool * kPoolStack;
       if (r->pool_scratch.count < need && r->pool_scratch.alloc(need) != cudaSuccess) break;
       uint32_t *scratch = r->pool_scratch.ptr;
@@ -673,7 +696,6 @@ LP_API lp_status lp_renderer_new(lp_device *dev, uint32_t width, uint32_t height
         delete r;
         return fail(LP_ERR_CUDA, "cudaEventCreate failed");
       }
-  r->grid_shade = persistent_grid(shade_kernel, 128, dev->sm_count);
   lp_status st = allocate_targets(r);
   if (st != LP_OK) {
     lp_renderer_destroy(r);
@@ -798,6 +820,9 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
   r->q_labels.clear();
   const bool stats = cfg.count_stats != 0;
   const int sm = r->dev->sm_count;
+  // production traversal (variant 0 = 14): RayPass is fused into the primary extend kernel
+  // and the primary shade kernel; every other variant reads the rays generate_kernel wrote
+  const bool fused_raygen = !stats && (cfg.traversal_variant == 0 || cfg.traversal_variant == 14);
   uint32_t remaining = cfg.spp_per_call;
   bool first_wave = true;
   while (remaining > 0) {
@@ -809,7 +834,7 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
     CUDA_CHECK(cudaMemsetAsync(r->counts.ptr, 0, kCntTotal * sizeof(uint32_t), st));
 
     if (first_wave) query_start(r, "ray generation");  // [ref renderer.rs:444]
-    { KtScope k(r, 3); generate_kernel<<<sm * 8, 256, 0, st>>>(P); }
+    if (!fused_raygen) { KtScope k(r, 3); generate_kernel<<<sm * 8, 256, 0, st>>>(P); }
     if (first_wave) query_end(r);
     for (uint32_t b = 0; b < cfg.max_bounces; ++b) {
       if (first_wave && b == 0) query_start(r, "primary intersection");  // [ref :457]
@@ -822,7 +847,7 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
         query_end(r);
         query_start(r, "shading 0");  // [ref :471]
       }
-      { KtScope k(r, 1); shade_kernel<<<r->grid_shade, 128, 0, st>>>(P, b); }
+      { KtScope k(r, 1); launch_shade(P, b, sm, st); }
       if (P.sc.n_active_lights) {
         KtScope k(r, 2);
         launch_trace(r, P, b, true, 0, stats);

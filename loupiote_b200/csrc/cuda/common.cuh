@@ -90,6 +90,64 @@ __device__ __forceinline__ f8 ldg256(const void *p) {
                : "l"(p));
   return r;
 }
+// Cache-policy experiments (all OFF by default, compile with -DLP_HINT_TRI_NA / _KEEP /
+// _STREAM): the ray-pool kernels leave ~30 KB of L1 per SM next to their shared-memory pools
+// (ncu: 8 % L1 hit rate), so keeping triangles (no-allocate) and the streamed ray state
+// (evict-first) out of it and pinning the instance table (evict-last) looked promising.
+// Measured on config 3 with all three on: 5 % SLOWER (profiles/r01_v3_ab.txt).
+__device__ __forceinline__ f8 ldg256_na(const void *p) {
+#ifndef LP_HINT_TRI_NA
+  return ldg256(p);
+#else
+  f8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x),
+                 "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+#endif
+}
+// 128-bit read-only load that stays in L1 as long as possible (instance records)
+__device__ __forceinline__ float4 ldg_keep(const float4 *p) {
+#ifndef LP_HINT_KEEP
+  return __ldg(p);
+#else
+  float4 r;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+#endif
+}
+// streamed path state: read once / written once per kernel (evict-first)
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+#ifndef LP_HINT_STREAM
+  return *p;
+#else
+  return __ldcs(p);
+#endif
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
+#ifndef LP_HINT_STREAM
+  return *p;
+#else
+  return __ldcs(p);
+#endif
+}
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) {
+#ifndef LP_HINT_STREAM
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
+__device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v) {
+#ifndef LP_HINT_STREAM
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
 
 // ------------------------------------------------------------------ float3 helpers
 struct f3 {

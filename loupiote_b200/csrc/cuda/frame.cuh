@@ -1,0 +1,100 @@
+// Frame-level data model of the wavefront pipeline shared by every translation unit: the
+// per-wave counter block, FrameParams, the slot <-> pixel mapping, the warp-aggregated queue
+// append and the camera ray (RayPass [ref crates/lib/src/renderer.rs:444-448]).
+#pragma once
+#include "common.cuh"
+#include "shade.cuh"
+#include "traverse.cuh"
+
+namespace lp {
+
+constexpr uint32_t kMaxBounces = 32;
+// layout of the per-wave counter block (uint32_t each)
+constexpr uint32_t kCntNext = 0;                    // [b] paths continuing after bounce b
+constexpr uint32_t kCntLight = kMaxBounces;         // [b] light shadow rays made at bounce b
+constexpr uint32_t kCntEnv = 2 * kMaxBounces;       // [b] env shadow rays made at bounce b
+constexpr uint32_t kCntWorkExtend = 3 * kMaxBounces;   // [b] dynamic work cursors
+constexpr uint32_t kCntWorkLight = 4 * kMaxBounces;
+constexpr uint32_t kCntWorkEnv = 5 * kMaxBounces;
+constexpr uint32_t kCntTotal = 6 * kMaxBounces;
+
+struct FrameParams {
+  SceneDev sc;
+  CameraDev cam;
+  PathState ps;
+  uint32_t *queue[2];
+  ShadowQueue sq_light, sq_env;
+  uint32_t *counts;
+  Counters *counters;
+  uint32_t n_pixels, slots_per_sample, n_slots, tiles_x, samples_in_wave;
+  uint32_t sample_base, sample_stride, seed, jitter, max_bounces, rr_start;
+  float4 *accum;
+  uint32_t *fh_inst, *fh_prim;
+  float *fh_t;
+  uint4 *gbuffer;
+  float2 *motion;
+  float prev_w2s[16];
+  int write_gbuffer;
+  int overwrite_accum;
+};
+
+// slot-local index <-> pixel through 8x4 tiles (one warp = one tile: coherent primary rays)
+__device__ __forceinline__ bool slot_to_pixel(uint32_t sl, uint32_t tiles_x, uint32_t w,
+                                              uint32_t h, uint32_t &px, uint32_t &py) {
+  const uint32_t tile = sl >> 5, l = sl & 31u;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  px = tx * 8u + (l & 7u);
+  py = ty * 4u + (l >> 3);
+  return px < w && py < h;
+}
+__device__ __forceinline__ uint32_t pixel_to_slot(uint32_t px, uint32_t py, uint32_t tiles_x) {
+  return (((py >> 2) * tiles_x + (px >> 3)) << 5) + ((py & 3u) << 3) + (px & 7u);
+}
+
+// warp-aggregated queue append: one atomic per warp, order inside the warp preserved
+__device__ __forceinline__ uint32_t warp_push(bool pred, uint32_t *counter) {
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+  if (m == 0u) return 0u;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+// Camera ray of path slot `slot` (RayPass).  Every operation is an explicitly rounded
+// intrinsic, so the three places that need the ray -- generate_kernel, the fused primary
+// extend kernel and the primary shade kernel -- compute bit-identical rays whatever the
+// contraction flags of their translation unit; the CPU restatement does the same in C.
+// Returns false for the dead slots of a ragged image edge.
+__device__ __forceinline__ bool primary_ray(const FrameParams &P, uint32_t slot, f3 &o, f3 &d,
+                                            uint32_t &pixel, uint32_t &sample, uint32_t &ls) {
+  ls = slot / P.slots_per_sample;
+  const uint32_t sl = slot - ls * P.slots_per_sample;
+  uint32_t px, py;
+  if (!slot_to_pixel(sl, P.tiles_x, P.cam.width, P.cam.height, px, py)) return false;
+  pixel = py * P.cam.width + px;
+  sample = P.sample_base + ls * P.sample_stride;
+  float jx = 0.5f, jy = 0.5f;
+  if (P.jitter) {
+    const uint4 r = rng4(pixel, sample, 0u, P.seed);
+    jx = u01(r.x);
+    jy = u01(r.y);
+  }
+  const float sx = __fmul_rn(
+      __fsub_rn(__fmul_rn(__fadd_rn((float)px, jx), P.cam.inv_w2), 1.0f), P.cam.tan_x);
+  const float sy = __fmul_rn(
+      __fsub_rn(1.0f, __fmul_rn(__fadd_rn((float)py, jy), P.cam.inv_h2)), P.cam.tan_y);
+  const float dx = __fmaf_rn(sx, P.cam.right[0], __fmaf_rn(sy, P.cam.up[0], P.cam.forward[0]));
+  const float dy = __fmaf_rn(sx, P.cam.right[1], __fmaf_rn(sy, P.cam.up[1], P.cam.forward[1]));
+  const float dz = __fmaf_rn(sx, P.cam.right[2], __fmaf_rn(sy, P.cam.up[2], P.cam.forward[2]));
+  const float l = __fsqrt_rn(
+      __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const float rl = __fdiv_rn(1.0f, l);
+  d = mk3(__fmul_rn(dx, rl), __fmul_rn(dy, rl), __fmul_rn(dz, rl));
+  o = mk3(P.cam.origin[0], P.cam.origin[1], P.cam.origin[2]);
+  return true;
+}
+
+}  // namespace lp

@@ -13,6 +13,39 @@ struct Surface {
   float metallic, alpha;
 };
 
+// Shading arithmetic is compared with the CPU restatement under a tolerance (DESIGN.md
+// section 2), never bit for bit, so it uses the MUFU units directly: division = x * rcp(y),
+// sqrt / rsqrt / sin / cos approximations (<= 2 ulp; sin/cos <= 4e-7 absolute on [-pi, pi]).
+// The IEEE sequences nvcc emits for `/` and sqrtf were 40 % of the shade kernel's
+// instructions (profiles/r01_v2_ncu_shade_*).  Nothing here decides a hit: ray generation and
+// the traversal keep the exactly rounded operations.
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float frcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fsqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float frsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ f3 normalize_fast(f3 v) {
+  const float r = frsqrt(dot(v, v));
+  return f3{v.x * r, v.y * r, v.z * r};
+}
+// sin / cos of 2*pi*u, u in [0, 1): MUFU on the argument shifted into [-pi, pi)
+__device__ __forceinline__ void sincos_2pi(float u, float &s, float &c) {
+  const float x = 2.0f * LP_PI * u - LP_PI;
+  s = -__sinf(x);
+  c = -__cosf(x);
+}
+
 __device__ __forceinline__ void fetch_surface(const SceneDev &sc, const Hit &hit, f3 d,
                                               Surface &sf, uint32_t &material_out) {
   const float4 *ip = sc.instances + 8u * (size_t)hit.inst;
@@ -40,11 +73,11 @@ __device__ __forceinline__ void fetch_surface(const SceneDev &sc, const Hit &hit
   const f3 go = cross(e1, e2);
   sf.p = xform_point(m0, m1, m2, po);
   // normals: inverse transpose = columns of world->object
-  sf.ng = normalize(mk3(__fmaf_rn(w0.x, go.x, __fmaf_rn(w1.x, go.y, w2.x * go.z)),
+  sf.ng = normalize_fast(mk3(__fmaf_rn(w0.x, go.x, __fmaf_rn(w1.x, go.y, w2.x * go.z)),
                         __fmaf_rn(w0.y, go.x, __fmaf_rn(w1.y, go.y, w2.y * go.z)),
                         __fmaf_rn(w0.z, go.x, __fmaf_rn(w1.z, go.y, w2.z * go.z))));
   if (dot(no, no) > 0.0f) {
-    sf.ns = normalize(mk3(__fmaf_rn(w0.x, no.x, __fmaf_rn(w1.x, no.y, w2.x * no.z)),
+    sf.ns = normalize_fast(mk3(__fmaf_rn(w0.x, no.x, __fmaf_rn(w1.x, no.y, w2.x * no.z)),
                           __fmaf_rn(w0.y, no.x, __fmaf_rn(w1.y, no.y, w2.y * no.z)),
                           __fmaf_rn(w0.z, no.x, __fmaf_rn(w1.z, no.y, w2.z * no.z))));
   } else {
@@ -65,7 +98,7 @@ __device__ __forceinline__ void fetch_surface(const SceneDev &sc, const Hit &hit
 
 __device__ __forceinline__ void onb(f3 n, f3 &t, f3 &b) {
   const float sign = copysignf(1.0f, n.z);
-  const float a = -1.0f / (sign + n.z);
+  const float a = -frcp(sign + n.z);
   const float bb = n.x * n.y * a;
   t = mk3(1.0f + sign * n.x * n.x * a, sign * bb, -sign * n.x);
   b = mk3(bb, sign + n.y * n.y * a, -n.y);
@@ -79,92 +112,96 @@ __device__ __forceinline__ float pow5(float x) {
   return x2 * x2 * x;
 }
 __device__ __forceinline__ float ggx_g1(float ndx, float a2) {
-  return 2.0f * ndx / (ndx + sqrtf(a2 + (1.0f - a2) * ndx * ndx));
+  return fdiv(2.0f * ndx, ndx + fsqrt(a2 + (1.0f - a2) * ndx * ndx));
 }
 
-__device__ __forceinline__ float lobe_probability(const Surface &sf, float ndv) {
-  const float k = pow5(1.0f - ndv);
+// View-dependent terms shared by every BSDF evaluation at one surface point (the shade kernel
+// evaluates up to three directions per hit: light NEE, environment NEE, the BSDF sample).
+struct BsdfCtx {
+  f3 F0, diff;
+  float a2, ndv, g1v, ps;  // ps = probability of sampling the specular lobe
+};
+
+__device__ __forceinline__ BsdfCtx bsdf_ctx(const Surface &sf, f3 wo) {
+  BsdfCtx cx;
+  cx.ndv = fmaxf(dot(sf.ns, wo), 1e-4f);
+  cx.a2 = sf.alpha * sf.alpha;
   const float inv_m = 1.0f - sf.metallic;
-  const f3 F0 = mk3(0.04f + (sf.base.x - 0.04f) * sf.metallic,
-                    0.04f + (sf.base.y - 0.04f) * sf.metallic,
-                    0.04f + (sf.base.z - 0.04f) * sf.metallic);
-  const f3 diff = mk3(sf.base.x * inv_m, sf.base.y * inv_m, sf.base.z * inv_m);
-  const f3 Fv = mk3(F0.x + (1.0f - F0.x) * k, F0.y + (1.0f - F0.y) * k, F0.z + (1.0f - F0.z) * k);
-  const float ws = luminance(Fv), wd = luminance(diff);
-  return wd > 0.0f ? clampf(ws / (ws + wd), 0.1f, 0.9f) : 1.0f;
+  cx.F0 = mk3(0.04f + (sf.base.x - 0.04f) * sf.metallic, 0.04f + (sf.base.y - 0.04f) * sf.metallic,
+              0.04f + (sf.base.z - 0.04f) * sf.metallic);
+  cx.diff = mk3(sf.base.x * inv_m, sf.base.y * inv_m, sf.base.z * inv_m);
+  cx.g1v = ggx_g1(cx.ndv, cx.a2);
+  const float k = pow5(1.0f - cx.ndv);
+  const f3 Fv = mk3(cx.F0.x + (1.0f - cx.F0.x) * k, cx.F0.y + (1.0f - cx.F0.y) * k,
+                    cx.F0.z + (1.0f - cx.F0.z) * k);
+  const float ws = luminance(Fv), wd = luminance(cx.diff);
+  cx.ps = wd > 0.0f ? clampf(fdiv(ws, ws + wd), 0.1f, 0.9f) : 1.0f;
+  return cx;
 }
 
 // f (without the cosine) and the combined sampling pdf of the lobe mixture
-__device__ __forceinline__ void bsdf_eval(const Surface &sf, f3 wo, f3 wi, f3 &f, float &pdf) {
+__device__ __forceinline__ void bsdf_eval(const Surface &sf, const BsdfCtx &cx, f3 wo, f3 wi, f3 &f,
+                                          float &pdf) {
   const float ndl = dot(sf.ns, wi);
-  const float ndv = fmaxf(dot(sf.ns, wo), 1e-4f);
   f = mk3(0.0f, 0.0f, 0.0f);
   pdf = 0.0f;
   if (!(ndl > 0.0f)) return;
-  const f3 h = normalize(wo + wi);
+  const f3 h = normalize_fast(wo + wi);
   const float ndh = fmaxf(dot(sf.ns, h), 0.0f);
   const float vdh = fmaxf(dot(wo, h), 0.0f);
-  const float a2 = sf.alpha * sf.alpha;
-  const float dd = ndh * ndh * (a2 - 1.0f) + 1.0f;
-  const float D = a2 / (LP_PI * dd * dd);
-  const float g1v = ggx_g1(ndv, a2), g1l = ggx_g1(ndl, a2);
+  const float dd = ndh * ndh * (cx.a2 - 1.0f) + 1.0f;
+  const float D = fdiv(cx.a2, LP_PI * dd * dd);
+  const float g1l = ggx_g1(ndl, cx.a2);
   const float fc = pow5(1.0f - vdh);
-  const float inv_m = 1.0f - sf.metallic;
-  const f3 F0 = mk3(0.04f + (sf.base.x - 0.04f) * sf.metallic,
-                    0.04f + (sf.base.y - 0.04f) * sf.metallic,
-                    0.04f + (sf.base.z - 0.04f) * sf.metallic);
-  const f3 diff = mk3(sf.base.x * inv_m, sf.base.y * inv_m, sf.base.z * inv_m);
-  const float spec = D * g1v * g1l / (4.0f * ndl * ndv);
+  const float inv_4ndv = frcp(4.0f * cx.ndv);
+  const float pdf_spec = cx.g1v * D * inv_4ndv;
+  const float spec = fdiv(pdf_spec * g1l, ndl);  // D G1(v) G1(l) / (4 n.l n.v)
   // glTF 2.0 material model: dielectric = fresnel_mix(diffuse, specular), F0 = 0.04
   const float kd = (1.0f - (0.04f + 0.96f * fc)) * LP_INV_PI;
-  f.x = diff.x * kd + (F0.x + (1.0f - F0.x) * fc) * spec;
-  f.y = diff.y * kd + (F0.y + (1.0f - F0.y) * fc) * spec;
-  f.z = diff.z * kd + (F0.z + (1.0f - F0.z) * fc) * spec;
-  const float ps = lobe_probability(sf, ndv);
-  const float pdf_spec = g1v * D / (4.0f * ndv);
+  f.x = cx.diff.x * kd + (cx.F0.x + (1.0f - cx.F0.x) * fc) * spec;
+  f.y = cx.diff.y * kd + (cx.F0.y + (1.0f - cx.F0.y) * fc) * spec;
+  f.z = cx.diff.z * kd + (cx.F0.z + (1.0f - cx.F0.z) * fc) * spec;
   const float pdf_diff = ndl * LP_INV_PI;
-  pdf = ps * pdf_spec + (1.0f - ps) * pdf_diff;
+  pdf = cx.ps * pdf_spec + (1.0f - cx.ps) * pdf_diff;
 }
 
 __device__ __forceinline__ f3 cosine_sample(f3 n, float u1, float u2) {
   f3 t, b;
   onb(n, t, b);
-  const float r = sqrtf(u1), phi = 2.0f * LP_PI * u2;
+  const float r = fsqrt(u1);
   float s, c;
-  sincosf(phi, &s, &c);
-  const float x = r * c, y = r * s, z = sqrtf(fmaxf(0.0f, 1.0f - u1));
+  sincos_2pi(u2, s, c);
+  const float x = r * c, y = r * s, z = fsqrt(fmaxf(0.0f, 1.0f - u1));
   return mk3(x * t.x + y * b.x + z * n.x, x * t.y + y * b.y + z * n.y,
              x * t.z + y * b.z + z * n.z);
 }
 
-__device__ __forceinline__ bool bsdf_sample(const Surface &sf, f3 wo, float ul, float u1, float u2,
-                                            f3 &wi) {
-  const float ndv = fmaxf(dot(sf.ns, wo), 1e-4f);
-  const float ps = lobe_probability(sf, ndv);
-  if (ul < ps) {
+__device__ __forceinline__ bool bsdf_sample(const Surface &sf, const BsdfCtx &cx, f3 wo, float ul,
+                                            float u1, float u2, f3 &wi) {
+  if (ul < cx.ps) {
     f3 t, b;
     onb(sf.ns, t, b);
     const float a = sf.alpha;
-    const f3 v = mk3(dot(wo, t), dot(wo, b), fmaxf(dot(wo, sf.ns), 1e-4f));
-    const f3 vh = normalize(mk3(a * v.x, a * v.y, v.z));
+    const f3 v = mk3(dot(wo, t), dot(wo, b), cx.ndv);
+    const f3 vh = normalize_fast(mk3(a * v.x, a * v.y, v.z));
     const float lensq = vh.x * vh.x + vh.y * vh.y;
     f3 T1 = mk3(1.0f, 0.0f, 0.0f);
     if (lensq > 0.0f) {
-      const float il = 1.0f / sqrtf(lensq);
+      const float il = frsqrt(lensq);
       T1 = mk3(-vh.y * il, vh.x * il, 0.0f);
     }
     const f3 T2 = cross(vh, T1);
-    const float r = sqrtf(u1), phi = 2.0f * LP_PI * u2;
+    const float r = fsqrt(u1);
     float sn, cs;
-    sincosf(phi, &sn, &cs);
+    sincos_2pi(u2, sn, cs);
     const float p1 = r * cs;
     float p2 = r * sn;
     const float sv = 0.5f * (1.0f + vh.z);
-    p2 = (1.0f - sv) * sqrtf(fmaxf(0.0f, 1.0f - p1 * p1)) + sv * p2;
-    const float pz = sqrtf(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2));
+    p2 = (1.0f - sv) * fsqrt(fmaxf(0.0f, 1.0f - p1 * p1)) + sv * p2;
+    const float pz = fsqrt(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2));
     const f3 nh = mk3(p1 * T1.x + p2 * T2.x + pz * vh.x, p1 * T1.y + p2 * T2.y + pz * vh.y,
                       p1 * T1.z + p2 * T2.z + pz * vh.z);
-    const f3 hl = normalize(mk3(a * nh.x, a * nh.y, fmaxf(0.0f, nh.z)));
+    const f3 hl = normalize_fast(mk3(a * nh.x, a * nh.y, fmaxf(0.0f, nh.z)));
     const f3 h = mk3(hl.x * t.x + hl.y * b.x + hl.z * sf.ns.x, hl.x * t.y + hl.y * b.y + hl.z * sf.ns.y,
                      hl.x * t.z + hl.y * b.z + hl.z * sf.ns.z);
     const float vdh = dot(wo, h);
@@ -194,7 +231,7 @@ __device__ __forceinline__ f3 env_radiance(const SceneDev &sc, f3 d) {
 
 __device__ __forceinline__ float power_heuristic(float a, float b) {
   const float a2 = a * a, b2 = b * b;
-  return a2 / (a2 + b2);
+  return fdiv(a2, a2 + b2);
 }
 
 __device__ __forceinline__ uint32_t pack_normal(f3 n) {

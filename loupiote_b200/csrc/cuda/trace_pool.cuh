@@ -22,7 +22,13 @@ namespace lp {
 constexpr int kPool = 64;                // rays resident per warp
 constexpr int kPoolStack = kStackSize4;  // traversal stack entries per ray (global scratch)
 constexpr int kPoolWarps = 4;            // warps per block
-constexpr int kRing = 8;                 // newest stack entries of a ray kept in shared memory
+#ifndef LP_POOL_RING
+#define LP_POOL_RING 8
+#endif
+#ifndef LP_POOL_MIN_BLOCKS
+#define LP_POOL_MIN_BLOCKS 8
+#endif
+constexpr int kRing = LP_POOL_RING;      // newest stack entries of a ray kept in shared memory
 
 enum : uint32_t { kStEmpty = 0u, kStNode = 1u, kStEntry = 2u, kStTri = 3u };
 constexpr uint32_t kFlagInBlas = 4u;
@@ -30,16 +36,22 @@ constexpr uint32_t kFlagInBlas = 4u;
 struct PoolSmem {
   float4 a[kPool];  // origin.xyz (current space), tmax / best t
   float4 b[kPool];  // 1/direction.xyz (current space), cur (bits)
-  float4 c[kPool];  // shear sx, sy, sz, kxyz (bits)
-  float4 d[kPool];  // hit u, v, instance (bits), primitive (bits)
-  uint4 e[kPool];   // stack (sp | ring base << 16), item, instance being traversed, unused
+  float4 c[kPool];  // shear sx, sy, sz, (kxyz | instance being traversed << 6) (bits)
+  float4 d[kPool];  // closest: hit u, v, instance (bits), primitive (bits)
+                    // any hit: contribution r, g, b, path slot (bits)
+  uint2 e[kPool];   // stack (sp | ring base << 16), item
   uint32_t ring[kRing * kPool];  // entry i of slot s at ring[(i % kRing) * kPool + s]
-  uint32_t state[kPool];  // bits 0..1 = state, bit 2 = inside a BLAS
-  uint32_t list[32];
+  uint8_t state[kPool];  // bits 0..1 = state, bit 2 = inside a BLAS
+  uint8_t list[32];
 };
+// 7040 bytes per warp: eight 4-warp blocks (the register limit) fit the 228 KB of an SM.
+// Occupancy is what this kernel is short of (ncu: 41 % with seven blocks, long-scoreboard
+// stalls on top; LP_POOL_BLOCKS=6/5/4 cost 5 / 15 / 29 %).
+static_assert(sizeof(PoolSmem) * kPoolWarps + 1024 <= 228 * 1024 / LP_POOL_MIN_BLOCKS,
+              "pool blocks per SM");
 
 template <bool ANY, bool HALF>
-__global__ void __launch_bounds__(32 * kPoolWarps)
+__global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
     trace_pool_kernel(const __grid_constant__ FrameParams P, uint32_t bounce, int env,
                       uint32_t *__restrict__ stack_scratch) {
   __shared__ PoolSmem pools[kPoolWarps];
@@ -76,24 +88,22 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
 
   auto load_ray = [&](uint32_t item, float4 &o4, float4 &d4) {
     if (ANY) {
-      o4 = sq.o_tmax[item];
-      d4 = sq.d_slot[item];
+      o4 = ld_stream(sq.o_tmax + item);
+      d4 = ld_stream(sq.d_slot + item);
     } else {
-      o4 = P.ps.ray_o[item];
-      d4 = P.ps.ray_d[item];
+      o4 = ld_stream(P.ps.ray_o + item);
+      d4 = ld_stream(P.ps.ray_d + item);
     }
   };
   // terminate the ray in pool slot s (closest hit: tbest = current best t)
   auto finish = [&](uint32_t s, uint32_t item, bool occluded, float tbest) {
     if (ANY) {
+      // Unoccluded: add the contribution parked in the pool at refill time.  One shadow ray
+      // per path and launch, so the reduction (RED.ADD.F32x4, fire and forget) is
+      // deterministic; the first version's load-add-store stalled 4 lanes on two round trips.
       if (!occluded) {
-        const uint32_t slot = __float_as_uint(sq.d_slot[item].w);
-        const float4 c = sq.contrib[item];
-        float4 acc = P.ps.rad[slot];
-        acc.x += c.x;
-        acc.y += c.y;
-        acc.z += c.z;
-        P.ps.rad[slot] = acc;
+        const float4 c = S.d[s];
+        atomicAdd(P.ps.rad + __float_as_uint(c.w), make_float4(c.x, c.y, c.z, 0.0f));
       }
     } else {
       const float4 d = S.d[s];
@@ -107,8 +117,8 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
         const float4 o4 = P.ps.ray_o[item], d4 = P.ps.ray_d[item];
         lights_closest(sc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), 0.0f, hit);
       }
-      P.ps.hit[item] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
-      P.ps.hit_inst[item] = hit.inst;
+      st_stream(P.ps.hit + item, make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim)));
+      st_stream(P.ps.hit_inst + item, hit.inst);
     }
     S.state[s] = kStEmpty;
   };
@@ -199,10 +209,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
     // ---------------------------------------------------------------- gather <= 32 slots
     {
       const int base_hi = __popc(m_lo);
-      if (m_lo & (1u << lane)) S.list[__popc(m_lo & lt_mask)] = (uint32_t)lane;
+      if (m_lo & (1u << lane)) S.list[__popc(m_lo & lt_mask)] = (uint8_t)lane;
       if (m_hi & (1u << lane)) {
         const int k = base_hi + __popc(m_hi & lt_mask);
-        if (k < 32) S.list[k] = (uint32_t)lane + 32u;
+        if (k < 32) S.list[k] = (uint8_t)(lane + 32);
       }
     }
     __syncwarp();
@@ -238,8 +248,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
           item = my;
           load_ray(item, o4, d4);
           tmax = o4.w;
+          const float4 c = ld_stream(sq.contrib + item);
+          S.d[s] = make_float4(c.x, c.y, c.z, d4.w);
         } else {
-          item = queue ? queue[my] : my;
+          item = queue ? ld_stream(queue + my) : my;
           load_ray(item, o4, d4);
           ok = d4.w >= 0.0f;  // dead slots (outside the image) are skipped
           tmax = INFINITY;
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
           if (!ANY)
             S.d[s] = make_float4(0.f, 0.f, __uint_as_float(LP_INVALID_INDEX),
                                  __uint_as_float(LP_INVALID_INDEX));
-          S.e[s] = make_uint4(0u, item, 0u, 0u);
+          S.e[s] = make_uint2(0u, item);
           if (root == kNoChildRef) finish(s, item, false, tmax);  // empty scene
           else S.state[s] = (root & kLeaf) ? kStEntry : kStNode;
         }
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
     }
 
     if (!active) continue;
-    const uint4 e = S.e[s];  // sp, item, inst
+    const uint2 e = S.e[s];  // sp, item
     const uint32_t flags = S.state[s] & ~3u;
 
     if (phase == kStNode) {
@@ -309,8 +321,8 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
       const float tbest = S.a[s].w;
       const uint32_t inst = __float_as_uint(S.b[s].w) & 0x0FFFFFFFu;
       const float4 *ip = sc.instances + 8u * (size_t)inst;
-      const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
-      const uint32_t root = __float_as_uint(__ldg(ip + 7).y);
+      const float4 r0 = ldg_keep(ip), r1 = ldg_keep(ip + 1), r2 = ldg_keep(ip + 2);
+      const uint32_t root = __float_as_uint(ldg_keep(ip + 7).y);
       float4 o4, d4;
       load_ray(e.y, o4, d4);
       LaneRay r;
@@ -318,10 +330,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
                              xform_vector(r0, r1, r2, mk3(d4.x, d4.y, d4.z)));
       S.a[s] = make_float4(r.o.x, r.o.y, r.o.z, tbest);
       S.b[s] = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(root));
-      S.c[s] = make_float4(r.sx, r.sy, r.sz, __int_as_float(r.kxyz));
+      S.c[s] = make_float4(r.sx, r.sy, r.sz, __uint_as_float((uint32_t)r.kxyz | (inst << 6)));
       uint32_t spb = e.x;
       push(s, stk, spb, kSentinel);
-      S.e[s] = make_uint4(spb, e.y, inst, 0u);
+      S.e[s].x = spb;
       S.state[s] = ((root & kLeaf) ? kStTri : kStNode) | kFlagInBlas;
     } else {
       // -------------------------------------------------------------- one triangle
@@ -331,13 +343,14 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
       r.sx = c.x;
       r.sy = c.y;
       r.sz = c.z;
-      r.kxyz = __float_as_int(c.w);
+      r.kxyz = __float_as_int(c.w) & 63;
+      const uint32_t inst = __float_as_uint(c.w) >> 6;
       float tbest = a.w;
       const uint32_t cur = __float_as_uint(S.b[s].w);
       const uint32_t first = cur & 0x0FFFFFFFu;
       const uint32_t left = (cur >> 28) & 7u;
       float4 p0, p1, p2;
-      load_tri(sc, first, p0, p1, p2);
+      load_tri<true>(sc, first, p0, p1, p2);
       float t, u, v;
       bool occluded = false;
       if (lane_tri(r, p0, p1, p2, tbest, t, u, v)) {
@@ -350,10 +363,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps)
           best.t = tbest;
           best.inst = __float_as_uint(d.z);
           best.prim = __float_as_uint(d.w);
-          if (hit_better(t, e.z, prim, best)) {
+          if (hit_better(t, inst, prim, best)) {
             tbest = t;
             S.a[s].w = t;
-            S.d[s] = make_float4(u, v, __uint_as_float(e.z), __uint_as_float(prim));
+            S.d[s] = make_float4(u, v, __uint_as_float(inst), __uint_as_float(prim));
           }
         }
       }

@@ -96,10 +96,11 @@ __device__ __forceinline__ bool lane_box(const LaneRay &r, f3 lo, f3 hi, float t
 
 // Triangle i of the GPU triangle array: the 48-byte canonical primitive padded to 64 bytes so
 // that it is two aligned LDG.256 (two L1 wavefronts per lane instead of three LDG.128).
+template <bool NA = false>
 __device__ __forceinline__ void load_tri(const SceneDev &sc, uint32_t i, float4 &p0, float4 &p1,
                                          float4 &p2) {
   const float4 *tp = sc.tris + 4u * (size_t)i;
-  const f8 a = ldg256(tp), b = ldg256(tp + 2);
+  const f8 a = NA ? ldg256_na(tp) : ldg256(tp), b = NA ? ldg256_na(tp + 2) : ldg256(tp + 2);
   p0 = a.lo;
   p1 = a.hi;
   p2 = b.lo;

@@ -174,8 +174,10 @@ __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, floa
   return false;
 }
 
-// extend / connect over the 4-wide layout; same batch scheme as kernels.cuh.
-template <bool HALF>
+// extend / connect over the 4-wide layout; same batch scheme as kernels.cuh.  GEN = the
+// production primary pass: RayPass is fused in, the camera ray is computed here
+// (primary_ray) instead of being written by generate_kernel and read back (64 B per path).
+template <bool HALF, bool GEN = false>
 __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ FrameParams P,
                                                       uint32_t bounce) {
   const uint32_t n = bounce == 0 ? P.n_slots : P.counts[kCntNext + bounce - 1];
@@ -190,10 +192,19 @@ __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ Fr
     const uint32_t idx = base + lane;
     if (idx < n) {
       const uint32_t slot = queue ? queue[idx] : idx;
-      const float4 o = P.ps.ray_o[slot], d = P.ps.ray_d[slot];
-      if (d.w >= 0.0f) {
+      f3 wo, wd;
+      bool alive;
+      if (GEN) {
+        uint32_t pixel, sample, ls;
+        alive = primary_ray(P, slot, wo, wd, pixel, sample, ls);
+      } else {
+        const float4 o = P.ps.ray_o[slot], d = P.ps.ray_d[slot];
+        wo = mk3(o.x, o.y, o.z);
+        wd = mk3(d.x, d.y, d.z);
+        alive = d.w >= 0.0f;
+      }
+      if (alive) {
         Hit hit;
-        const f3 wo = mk3(o.x, o.y, o.z), wd = mk3(d.x, d.y, d.z);
         traverse4<false, HALF>(P.sc, wo, wd, INFINITY, hit);
         if (P.sc.n_active_lights) lights_closest(P.sc, wo, wd, 0.0f, hit);
         P.ps.hit[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));

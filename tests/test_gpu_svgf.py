@@ -41,11 +41,17 @@ def test_gbuffer_and_motion_match_oracle(device):
     cfg.sample_offset = 1  # second frame = sample index 1
     acc, st, ogb, omv = O.render(osc, cam, cfg, 1, want_gbuffer=True,
                                  prev_world_to_screen=prev_w2s)
-    # ids and depth bits are exact; packed normal / albedo may differ by one quantum on a
-    # handful of pixels (normalize -> 16-bit snorm rounding of a value on a .5 boundary)
+    # ids and depth bits are exact.  The packed normal is the 16-bit snorm quantisation of a
+    # vector the shade kernel normalises with MUFU rsqrt (<= 2 ulp): a component within 2 ulp
+    # of a .5 rounding boundary lands on the neighbouring code (probability ~ 2 ulp * 32767 =
+    # 4e-3 per component), never further than one code (3e-5) from the oracle's
     assert np.array_equal(gb[..., 2], ogb[..., 2])
     assert np.array_equal(gb[..., 1], ogb[..., 1])
-    assert (gb[..., 0] != ogb[..., 0]).mean() < 1e-3
+    for shift in (0, 16):
+        a = ((gb[..., 0] >> shift) & 0xFFFF).astype(np.int16).astype(np.int32)
+        b = ((ogb[..., 0] >> shift) & 0xFFFF).astype(np.int16).astype(np.int32)
+        assert np.abs(a - b).max() <= 1
+    assert (gb[..., 0] != ogb[..., 0]).mean() < 3e-2
     assert np.array_equal(gb[..., 3], ogb[..., 3])
     hit = ogb[..., 2] != 0xFFFFFFFF
     assert np.abs(mv - omv)[hit].max() < 2e-3  # pixels; world_to_screen inverse is float
