@@ -242,7 +242,6 @@ def run_ours(args) -> None:
     barrier()
     r.ray_counters(reset=True)
     r.kernel_times(reset=True)
-    r.set_kernel_timing(True)
 
     # ---- timed region: K steps, CUDA events on the stream the kernels are launched on
     sampler = ClockSampler(local_rank)
@@ -257,12 +256,30 @@ def run_ours(args) -> None:
             reduce_accum()
         e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    kt = r.kernel_times(reset=True)
-    r.set_kernel_timing(False)
+    launches = sum(v[1] for v in r.kernel_times(reset=True).values())
     counters = r.ray_counters(reset=True)
     rays = counters["primary"] + counters["bounce"] + counters["shadow"]
+
+    # ---- per-kernel durations: the same K steps again with an event pair around every launch.
+    # Per-launch timing serialises the frame (the production frame overlaps the shadow-ray
+    # kernels of bounce b with the extend kernel of bounce b+1 on a second stream, where a
+    # bracketed duration would be the duration of the pair), so this pass is a little slower
+    # than the timed region; `kernel_ms` and `roofline` come from it, `value` does not.
+    r.set_kernel_timing(True)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        k0.record(stream)
+        for _ in range(args.steps):
+            r.raytrace(c["view"])
+            reduce_accum()
+        k1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    serial_ms = k0.elapsed_time(k1)
+    kt = r.kernel_times(reset=True)
+    r.set_kernel_timing(False)
+    r.ray_counters(reset=True)
 
     # ---- e2e: same steps through the public API with HOST buffers: per step the view
     # matrix + uniforms go host->device and the tone-mapped frame comes back (read_pixels)
@@ -302,7 +319,6 @@ def run_ours(args) -> None:
         roof_mrays = min(peaks["hbm_gbs"] * 1e9 / (total_bytes / total_rays),
                          fp32 * 1e12 / (total_flops / total_rays)) / 1e6
         value = rays / (ms * 1e-3) / 1e6
-        launches = sum(v[1] for v in kt.values())
         line = {
             "metric": "path-tracing throughput (primary+bounce+shadow rays)",
             "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -328,6 +344,9 @@ def run_ours(args) -> None:
                                                 for k in range(3)],
                          "path_roofline_mrays": roof_mrays},
             "kernel_ms": {k: v[0] for k, v in kt.items()},
+            "kernel_timing_pass": {"ms_per_step": serial_ms / args.steps,
+                                   "note": "separate pass of the same K steps, one stream, an "
+                                           "event pair around every launch"},
             "gpu_launches": launches,
             "clocks": clocks,
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",

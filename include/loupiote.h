@@ -351,8 +351,10 @@ LP_API lp_status lp_renderer_read_aux(lp_renderer *r, int which, void *out, size
 
 /* Measurement hooks.  Kernel classes: 0 = extend (closest hit), 1 = shade, 2 = connect
  * (any hit), 3 = everything else (generate, accumulate, SVGF, tone-map).  Launch counts are
- * always kept; per-launch CUDA-event timing (on the device stream) is opt-in.
- * lp_renderer_kernel_times synchronises. */
+ * always kept; per-launch CUDA-event timing (on the device stream) is opt-in and serialises the
+ * frame: while it is on, the shadow-ray kernels of bounce b are not overlapped with the extend
+ * kernel of bounce b+1 on the second stream, so every event pair brackets one kernel running
+ * alone.  lp_renderer_kernel_times synchronises. */
 LP_API lp_status lp_renderer_set_kernel_timing(lp_renderer *r, int flag);
 LP_API lp_status lp_renderer_kernel_times(lp_renderer *r, double ms[4], uint64_t launches[4],
                                           int reset);

@@ -28,6 +28,7 @@ SOURCES = [
 # translation units whose arithmetic never decides a hit: FMA contraction on
 SOURCES_FMAD = [
     CSRC / "cuda" / "shade_kernel.cu",
+    CSRC / "cuda" / "svgf_kernels.cu",
 ]
 
 COMMON_FLAGS = [

@@ -65,6 +65,7 @@ struct DevBuf {
 struct lp_device {
   int ordinal = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // shadow rays of bounce b overlap the extend of bounce b+1
   int sm_count = 0;
   cudaDeviceProp prop{};
 };
@@ -134,6 +135,7 @@ struct lp_renderer {
   // Queries [ref renderer.rs:321,444-517]
   static constexpr int kMaxQueries = 10;
   cudaEvent_t ev[kMaxQueries][2] = {};
+  cudaEvent_t ev_shaded = nullptr, ev_connected = nullptr;  // cross-stream ordering
   std::vector<std::string> q_labels;
   std::vector<const char *> q_label_ptrs;
   std::vector<double> q_ms;
@@ -330,8 +332,7 @@ void launch_persistent(lp_renderer *r, const FrameParams &P, uint32_t b, bool an
 }
 
 void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, int env,
-                  bool stats) {
-  cudaStream_t st = r->dev->stream;
+                  bool stats, cudaStream_t st) {
   const int sm = r->dev->sm_count;
   // 0 = production = 14 (hybrid); 15 = the first version (BVH2, one ray per thread)
   const uint32_t variant = r->cfg.traversal_variant == 0 ? 14u : r->cfg.traversal_variant;
@@ -395,13 +396,18 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
         pool_grid = per_sm * sm;
       }
       const int g_any = pool_grid, g_closest = pool_grid;
+      // overflow stacks: one region per concurrently running launch (extend | connect)
       const size_t need = (size_t)std::max(g_any, g_closest) * kPoolWarps * kPool * kPoolStack;
-      if (r->pool_scratch.count < need && r->pool_scratch.alloc(need) != cudaSuccess) break;
-      uint32_t *scratch = r->pool_scratch.ptr;
-      if (any && il) trace_pool_kernel<true, true><<<g_any, 128, 0, st>>>(P, b, env, scratch);
-      else if (any) trace_pool_kernel<true, false><<<g_any, 128, 0, st>>>(P, b, env, scratch);
-      else if (il) trace_pool_kernel<false, true><<<g_closest, 128, 0, st>>>(P, b, env, scratch);
-      else trace_pool_kernel<false, false><<<g_closest, 128, 0, st>>>(P, b, env, scratch);
+      if (r->pool_scratch.count < 2 * need && r->pool_scratch.alloc(2 * need) != cudaSuccess) break;
+      uint32_t *scratch = r->pool_scratch.ptr + (any ? need : 0);
+      static const uint32_t chunk_max = [] {  // LP_POOL_CHUNK: tuning knob
+        const char *e = std::getenv("LP_POOL_CHUNK");
+        return e ? (uint32_t)std::max(32L, std::atol(e)) : 64u;
+      }();
+      if (any && il) trace_pool_kernel<true, true><<<g_any, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+      else if (any) trace_pool_kernel<true, false><<<g_any, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+      else if (il) trace_pool_kernel<false, true><<<g_closest, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+      else trace_pool_kernel<false, false><<<g_closest, 128, 0, st>>>(P, b, env, scratch, chunk_max);
       break;
     }
     case 10:  // 4-wide collapse, one ray per thread (STATS keeps the canonical BVH2 walk)
@@ -427,6 +433,7 @@ constexpr size_t kKtPool = 2048;
 void kt_drain(lp_renderer *r) {
   if (!r->kt_used) return;
   cudaStreamSynchronize(r->dev->stream);
+  cudaStreamSynchronize(r->dev->stream2);
   for (size_t i = 0; i < r->kt_used; ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r->kt_events[2 * i], r->kt_events[2 * i + 1]) == cudaSuccess)
@@ -439,7 +446,9 @@ void kt_drain(lp_renderer *r) {
 struct KtScope {
   lp_renderer *r;
   bool timed;
-  KtScope(lp_renderer *rr, int kind) : r(rr), timed(false) {
+  cudaStream_t st;
+  KtScope(lp_renderer *rr, int kind, cudaStream_t stream = nullptr)
+      : r(rr), timed(false), st(stream ? stream : rr->dev->stream) {
     r->kt_launches[kind]++;
     if (!r->kt_enabled) return;
     if (r->kt_events.empty()) {
@@ -449,12 +458,12 @@ struct KtScope {
     }
     if (r->kt_used == kKtPool) kt_drain(r);
     r->kt_kind[r->kt_used] = kind;
-    cudaEventRecord(r->kt_events[2 * r->kt_used], r->dev->stream);
+    cudaEventRecord(r->kt_events[2 * r->kt_used], st);
     timed = true;
   }
   ~KtScope() {
     if (!timed) return;
-    cudaEventRecord(r->kt_events[2 * r->kt_used + 1], r->dev->stream);
+    cudaEventRecord(r->kt_events[2 * r->kt_used + 1], st);
     r->kt_used++;
   }
 };
@@ -506,7 +515,9 @@ LP_API lp_status lp_device_create(int cuda_ordinal, lp_device **out) {
     return fail(LP_ERR_CUDA, "device '" + name + "' is not sm_100 class; kernels are built for sm_100a only");
   }
   d->sm_count = d->prop.multiProcessorCount;
-  if ((e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+  if ((e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking)) != cudaSuccess) {
+    if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
     return fail(LP_ERR_CUDA, cudaGetErrorString(e));
   }
@@ -517,6 +528,10 @@ LP_API lp_status lp_device_create(int cuda_ordinal, lp_device **out) {
 LP_API lp_status lp_device_destroy(lp_device *dev) {
   if (!dev) return LP_OK;
   cudaSetDevice(dev->ordinal);
+  if (dev->stream2) {
+    cudaStreamSynchronize(dev->stream2);
+    cudaStreamDestroy(dev->stream2);
+  }
   if (dev->stream) {
     cudaStreamSynchronize(dev->stream);
     cudaStreamDestroy(dev->stream);
@@ -696,6 +711,11 @@ LP_API lp_status lp_renderer_new(lp_device *dev, uint32_t width, uint32_t height
         delete r;
         return fail(LP_ERR_CUDA, "cudaEventCreate failed");
       }
+  if (cudaEventCreateWithFlags(&r->ev_shaded, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&r->ev_connected, cudaEventDisableTiming) != cudaSuccess) {
+    lp_renderer_destroy(r);
+    return fail(LP_ERR_CUDA, "cudaEventCreate failed");
+  }
   lp_status st = allocate_targets(r);
   if (st != LP_OK) {
     lp_renderer_destroy(r);
@@ -714,6 +734,8 @@ LP_API lp_status lp_renderer_destroy(lp_renderer *r) {
       if (r->ev[i][k]) cudaEventDestroy(r->ev[i][k]);
   for (auto &e : r->kt_events)
     if (e) cudaEventDestroy(e);
+  if (r->ev_shaded) cudaEventDestroy(r->ev_shaded);
+  if (r->ev_connected) cudaEventDestroy(r->ev_connected);
   delete r;
   return LP_OK;
 }
@@ -823,6 +845,14 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
   // production traversal (variant 0 = 14): RayPass is fused into the primary extend kernel
   // and the primary shade kernel; every other variant reads the rays generate_kernel wrote
   const bool fused_raygen = !stats && (cfg.traversal_variant == 0 || cfg.traversal_variant == 14);
+  // LP_OVERLAP=0 keeps every kernel on one stream (tuning / debugging)
+  static const bool overlap_env = [] {
+    const char *e = std::getenv("LP_OVERLAP");
+    return e ? std::atoi(e) != 0 : true;
+  }();
+  // per-launch timing brackets each kernel with an event pair: keep them un-contended
+  const bool overlap = overlap_env && !stats && !r->kt_enabled;
+  bool connect_pending = false;
   uint32_t remaining = cfg.spp_per_call;
   bool first_wave = true;
   while (remaining > 0) {
@@ -841,23 +871,41 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
       if (first_wave && b == 1) query_start(r, "bounces");
       {
         KtScope k(r, 0);
-        launch_trace(r, P, b, false, 0, stats);
+        launch_trace(r, P, b, false, 0, stats, st);
       }
       if (first_wave && b == 0) {
         query_end(r);
         query_start(r, "shading 0");  // [ref :471]
       }
+      // shade(b) reads and rewrites the radiance the shadow rays of bounce b-1 add to
+      if (connect_pending) CUDA_CHECK(cudaStreamWaitEvent(st, r->ev_connected, 0));
+      connect_pending = false;
       { KtScope k(r, 1); launch_shade(P, b, sm, st); }
+      const bool shadows = P.sc.n_active_lights || P.sc.env_on;
+      cudaStream_t sc_st = st;
+      if (overlap && shadows) {
+        // the shadow rays of this bounce run beside the next bounce's extend: each kernel is
+        // a persistent grid, so the second one fills the SMs the first one's tail frees
+        sc_st = r->dev->stream2;
+        CUDA_CHECK(cudaEventRecord(r->ev_shaded, st));
+        CUDA_CHECK(cudaStreamWaitEvent(sc_st, r->ev_shaded, 0));
+      }
       if (P.sc.n_active_lights) {
-        KtScope k(r, 2);
-        launch_trace(r, P, b, true, 0, stats);
+        KtScope k(r, 2, sc_st);
+        launch_trace(r, P, b, true, 0, stats, sc_st);
       }
       if (P.sc.env_on) {
-        KtScope k(r, 2);
-        launch_trace(r, P, b, true, 1, stats);
+        KtScope k(r, 2, sc_st);
+        launch_trace(r, P, b, true, 1, stats, sc_st);
+      }
+      if (overlap && shadows) {
+        CUDA_CHECK(cudaEventRecord(r->ev_connected, sc_st));
+        connect_pending = true;
       }
       if (first_wave && b == 0) query_end(r);
     }
+    if (connect_pending) CUDA_CHECK(cudaStreamWaitEvent(st, r->ev_connected, 0));
+    connect_pending = false;
     if (first_wave && cfg.max_bounces > 1) query_end(r);
     { KtScope k(r, 3); finalize_counts_kernel<<<1, 32, 0, st>>>(P); }
 
@@ -889,7 +937,7 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
     T.out_rad = r->pp[cur].radiance.ptr;
     T.out_mom = r->pp[cur].moments.ptr;
     T.out_hist = r->pp[cur].history.ptr;
-    { KtScope k(r, 3); svgf_temporal_kernel<<<sm * 8, 256, 0, st>>>(T); }
+    { KtScope k(r, 3); launch_svgf_temporal(T, sm, st); }
     if (r->mode == LP_BLIT_DENOISED_PATHRACE) {
       // a-trous ping-pong between `temp` and the main target [ref asvgf.rs:277-290]
       const float4 *src = r->pp[cur].radiance.ptr;
@@ -897,12 +945,11 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
         float4 *dst = (it & 1u) ? r->accum.ptr : r->temp.ptr;
         {
           KtScope k(r, 3);
-          svgf_atrous_kernel<<<sm * 8, 256, 0, st>>>(r->width, r->height, src,
-                                                     r->pp[cur].gbuffer.ptr, it, dst);
+          launch_svgf_atrous(r->width, r->height, src, r->pp[cur].gbuffer.ptr, it, dst, sm, st);
         }
         src = dst;
       }
-      { KtScope k(r, 3); svgf_composite_kernel<<<sm * 8, 256, 0, st>>>(n, src, r->pp[cur].gbuffer.ptr, r->accum.ptr); }
+      { KtScope k(r, 3); launch_svgf_composite(n, src, r->pp[cur].gbuffer.ptr, r->accum.ptr, sm, st); }
     }
     query_end(r);
   }

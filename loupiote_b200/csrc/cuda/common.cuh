@@ -90,13 +90,15 @@ __device__ __forceinline__ f8 ldg256(const void *p) {
                : "l"(p));
   return r;
 }
-// Cache-policy experiments (all OFF by default, compile with -DLP_HINT_TRI_NA / _KEEP /
-// _STREAM): the ray-pool kernels leave ~30 KB of L1 per SM next to their shared-memory pools
-// (ncu: 8 % L1 hit rate), so keeping triangles (no-allocate) and the streamed ray state
-// (evict-first) out of it and pinning the instance table (evict-last) looked promising.
-// Measured on config 3 with all three on: 5 % SLOWER (profiles/r01_v3_ab.txt).
+// Cache policies.  The ray-pool kernels leave ~30 KB of L1 per SM next to their
+// shared-memory pools (ncu: 8 % L1 hit rate).  Measured one at a time on config 3
+// (profiles/r01_v3_ab.txt): triangles without L1 allocation in the pool kernels +1 % (ON);
+// instance records evict-last +-0 (off, -DLP_HINT_KEEP); ray state evict-first -3.5 % (off,
+// -DLP_HINT_STREAM: the world ray is re-read when a ray leaves an instance); triangles
+// without allocation in the coherent primary kernel: slower (its 65 % L1 hit rate is reuse
+// between the rays of a tile), so load_tri<NA> is per kernel.
 __device__ __forceinline__ f8 ldg256_na(const void *p) {
-#ifndef LP_HINT_TRI_NA
+#ifdef LP_NO_HINT_TRI_NA
   return ldg256(p);
 #else
   f8 r;

@@ -19,7 +19,13 @@
 
 namespace lp {
 
-constexpr int kPool = 64;                // rays resident per warp
+#ifndef LP_POOL_RAYS
+#define LP_POOL_RAYS 64
+#endif
+constexpr int kPool = LP_POOL_RAYS;      // rays resident per warp (33..64)
+static_assert(kPool > 32 && kPool <= 64, "the pool is scanned as two 32-slot halves");
+// slots of the upper half that exist
+constexpr unsigned kHiMask = kPool == 64 ? 0xFFFFFFFFu : ((1u << (kPool - 32)) - 1u);
 constexpr int kPoolStack = kStackSize4;  // traversal stack entries per ray (global scratch)
 constexpr int kPoolWarps = 4;            // warps per block
 #ifndef LP_POOL_RING
@@ -53,7 +59,7 @@ static_assert(sizeof(PoolSmem) * kPoolWarps + 1024 <= 228 * 1024 / LP_POOL_MIN_B
 template <bool ANY, bool HALF>
 __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
     trace_pool_kernel(const __grid_constant__ FrameParams P, uint32_t bounce, int env,
-                      uint32_t *__restrict__ stack_scratch) {
+                      uint32_t *__restrict__ stack_scratch, uint32_t chunk_max) {
   __shared__ PoolSmem pools[kPoolWarps];
   PoolSmem &S = pools[threadIdx.x >> 5];
   const SceneDev &sc = P.sc;
@@ -79,12 +85,14 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
   uint32_t *stack_base = stack_scratch + (size_t)warp_id * (kPool * kPoolStack);
 
   uint32_t chunk = n / (total_warps * 4u);
-  chunk = chunk < 64u ? 64u : (chunk > 1024u ? 1024u : chunk);
+  // rays a warp reserves per atomic.  Large reservations leave single warps working long
+  // after the queue is empty: 1024 -> 64 rays was worth 4 % of the frame (r01_v3_ab.txt)
+  chunk = chunk < 32u ? 32u : (chunk > chunk_max ? chunk_max : chunk);
   uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
   bool exhausted = false;
 
   S.state[lane] = kStEmpty;
-  S.state[lane + 32] = kStEmpty;
+  if (lane + 32 < kPool) S.state[lane + 32] = kStEmpty;
 
   auto load_ray = [&](uint32_t item, float4 &o4, float4 &d4) {
     if (ANY) {
@@ -172,14 +180,15 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
 
   for (;;) {
     __syncwarp();
-    const uint32_t st_lo = S.state[lane] & 3u, st_hi = S.state[lane + 32] & 3u;
+    const uint32_t st_lo = S.state[lane] & 3u;
+    const uint32_t st_hi = S.state[kPool == 64 ? lane + 32 : (lane + 32 < kPool ? lane + 32 : 32)] & 3u;
     const unsigned e_lo = __ballot_sync(0xFFFFFFFFu, st_lo == kStEmpty);
-    const unsigned e_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStEmpty);
+    const unsigned e_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStEmpty) & kHiMask;
     const unsigned n_lo = __ballot_sync(0xFFFFFFFFu, st_lo == kStNode);
-    const unsigned n_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStNode);
+    const unsigned n_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStNode) & kHiMask;
     const unsigned t_lo = __ballot_sync(0xFFFFFFFFu, st_lo == kStTri);
-    const unsigned t_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStTri);
-    const unsigned y_lo = ~(e_lo | n_lo | t_lo), y_hi = ~(e_hi | n_hi | t_hi);  // entry
+    const unsigned t_hi = __ballot_sync(0xFFFFFFFFu, st_hi == kStTri) & kHiMask;
+    const unsigned y_lo = ~(e_lo | n_lo | t_lo), y_hi = ~(e_hi | n_hi | t_hi) & kHiMask;  // entry
     const int c_empty = __popc(e_lo) + __popc(e_hi);
     const int c_node = __popc(n_lo) + __popc(n_hi);
     const int c_tri = __popc(t_lo) + __popc(t_hi);

@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B measurements on the GPU box: one bench.py line per library variant / tuning knob.
-#   tools/ab_bench.sh TAG "variant1 variant2 ..." "POOL_BLOCKS values ..."
+#   tools/ab_bench.sh TAG "variant1 variant2 ..." "ENV1=VAL ENV2=VAL ..."
 # Library variants are built beforehand with `python -m loupiote_b200._build --variant NAME -D...`.
 TAG=${1:-ab}
 VARIANTS=${2:-base}
@@ -15,8 +15,8 @@ for v in $VARIANTS; do
 done
 unset LP_LIB_VARIANT
 for b in $BLOCKS; do
-  echo "{\"pool_blocks\": $b}" >> $OUT
-  LP_POOL_BLOCKS=$b timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline >> $OUT 2>> gpurun_out/${TAG}_ab.err
+  echo "{\"env\": \"$b\"}" >> $OUT
+  env $b timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline >> $OUT 2>> gpurun_out/${TAG}_ab.err
 done
 python - <<PY
 import json
