@@ -15,6 +15,7 @@
 #include "../host/scene.hpp"
 #include "kernels.cuh"
 #include "svgf.cuh"
+#include "svgf_temporal.cuh"
 #include "trace_persistent.cuh"
 #include "traverse4.cuh"
 #include "trace_pool.cuh"

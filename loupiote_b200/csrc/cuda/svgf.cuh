@@ -26,7 +26,7 @@ struct SvgfTemporalParams {
   float *out_hist;
 };
 
-void launch_svgf_temporal(const SvgfTemporalParams &T, int sm_count, cudaStream_t stream);
+// launch_svgf_temporal: svgf_temporal.cuh (uncontracted translation unit)
 // One a-trous iteration (5x5 taps at stride 2^iteration) from `in` to `out`.
 void launch_svgf_atrous(uint32_t w, uint32_t h, const float4 *in, const uint4 *gbuffer,
                         uint32_t iteration, float4 *out, int sm_count, cudaStream_t stream);

@@ -1,0 +1,80 @@
+// SVGF temporal accumulation [ref crates/lib/src/render/asvgf.rs:192-205,250-256]: demodulate
+// by the first-hit albedo, 2x2 bilinear reprojection through the motion vectors validated by
+// mesh id / normal / depth, exponential moving average with alpha = 1/N, luminance moments.
+// Compiled in the uncontracted translation unit: the history length it produces is compared
+// EXACTLY with the CPU restatement (tests/test_gpu_svgf.py).  HBM-bound: 112 B per pixel.
+#pragma once
+#include "frame.cuh"
+#include "svgf.cuh"
+
+namespace lp {
+
+__global__ void __launch_bounds__(256) svgf_temporal_kernel(const SvgfTemporalParams P) {
+  const uint32_t n = P.w * P.h;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t x = i % P.w, y = i / P.w;
+    const uint4 g = P.gb_cur[i];
+    const f3 albedo = unpack_albedo(g.w);
+    const float4 s = P.sample_rad[pixel_to_slot(x, y, P.tiles_x)];
+    const f3 cur = mk3(s.x / albedo.x, s.y / albedo.y, s.z / albedo.z);
+    const float lum = luminance(cur);
+    f3 prev_c = mk3(0.f, 0.f, 0.f);
+    float pm0 = 0.f, pm1 = 0.f, prev_h = 0.f, wsum = 0.f;
+    const float2 mv = P.motion[i];
+    if (g.z != LP_INVALID_INDEX && mv.x >= 0.0f && mv.y >= 0.0f) {
+      const f3 ncur = unpack_normal(g.x);
+      const float zc = __uint_as_float(g.y);
+      const float fx = mv.x - 0.5f, fy = mv.y - 0.5f;
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const float tx = fx - x0f, ty = fy - y0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long xx = (long)x0f + (k & 1), yy = (long)y0f + (k >> 1);
+        if (xx < 0 || yy < 0 || xx >= (long)P.w || yy >= (long)P.h) continue;
+        const uint32_t j = (uint32_t)yy * P.w + (uint32_t)xx;
+        const uint4 gp = P.gb_prev[j];
+        if (gp.z != g.z) continue;
+        if (dot(unpack_normal(gp.x), ncur) < 0.9f) continue;
+        const float zp = __uint_as_float(gp.y);
+        if (fabsf(zp - zc) > 0.1f * fmaxf(zc, 1e-6f)) continue;
+        const float wk = ((k & 1) ? tx : 1.0f - tx) * ((k >> 1) ? ty : 1.0f - ty);
+        const float4 pr = P.prev_rad[j];
+        const float2 pm = P.prev_mom[j];
+        prev_c.x += wk * pr.x;
+        prev_c.y += wk * pr.y;
+        prev_c.z += wk * pr.z;
+        pm0 += wk * pm.x;
+        pm1 += wk * pm.y;
+        prev_h += wk * P.prev_hist[j];
+        wsum += wk;
+      }
+    }
+    float hist = 1.0f, alpha = 1.0f;
+    if (wsum > 0.01f) {
+      const float inv = 1.0f / wsum;
+      prev_c = prev_c * inv;
+      pm0 *= inv;
+      pm1 *= inv;
+      prev_h *= inv;
+      hist = fminf(prev_h + 1.0f, kSvgfMaxHistory);
+      alpha = 1.0f / hist;
+    }
+    const f3 out_c = mk3(prev_c.x + (cur.x - prev_c.x) * alpha, prev_c.y + (cur.y - prev_c.y) * alpha,
+                         prev_c.z + (cur.z - prev_c.z) * alpha);
+    const float m0 = pm0 + (lum - pm0) * alpha;
+    const float m1 = pm1 + (lum * lum - pm1) * alpha;
+    float var = fmaxf(0.0f, m1 - m0 * m0);
+    if (hist < 4.0f) var *= 4.0f / hist;
+    P.out_rad[i] = make_float4(out_c.x, out_c.y, out_c.z, var);
+    P.out_mom[i] = make_float2(m0, m1);
+    P.out_hist[i] = hist;
+  }
+}
+
+
+inline void launch_svgf_temporal(const SvgfTemporalParams &T, int sm_count, cudaStream_t stream) {
+  svgf_temporal_kernel<<<sm_count * 8, 256, 0, stream>>>(T);
+}
+
+}  // namespace lp

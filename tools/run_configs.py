@@ -115,7 +115,7 @@ def config4(dev):
     stats = bench.algorithmic_bytes_flops(r.ray_counters(reset=True))
     spp = int(__import__("os").environ.get("LP_CONFIG4_SPP", "7"))  # samples per wave
     r.set_config(max_bounces=bounces, spp_per_call=spp, jitter=1, seed=0,
-                 env_color=c["env_color"])
+                 env_color=c["env_color"], count_stats=0)
     for _ in range(2):
         r.raytrace(c["view"])
     dev.synchronize()
