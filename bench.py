@@ -129,6 +129,8 @@ def cpu_reference_sample(c, w, h, bounces, spp, pixel_step, sample_offset=0):
     """Times the CPU restatement (oracle) on a bounded sample of the workload."""
     from loupiote_b200 import _ffi
     from oracle import oracle as O
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all host threads
+    O.set_threads(os.cpu_count() or 1)
     osc = O.OracleScene(c["scene"], env_color=c["env_color"])
     cam = O.camera_from_view(c["view"], w, h, V_FOV)
     cfg = _ffi.RenderConfig()
@@ -333,7 +335,7 @@ def run_ours(args) -> None:
                        "scene_bytes": sg.stats()["total_bytes"]},
             "spp_per_s": world * args.spp_per_step * args.steps / (ms * 1e-3),
             "rays_per_step": rays / args.steps,
-            "roofline_fraction_of_path": value / roof_mrays,
+            "roofline_fraction_of_path": value / (world * roof_mrays),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
                          "kernel": "extend_kernel", "launch_ms": ext_ms / max(ext_launches, 1),

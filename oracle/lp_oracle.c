@@ -16,6 +16,26 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Number of OpenMP threads of the render / image loops (harness knob: torchrun exports
+ * OMP_NUM_THREADS=1 to its ranks, the CPU baseline arm wants every host thread). */
+void lpo_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+int lpo_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 
 #define LPO_PI 3.14159265358979323846f
 #define LPO_INV_PI 0.31830988618379067154f

@@ -115,6 +115,10 @@ void lpo_render(const lpo_scene *s, const lp_camera *cam, const lp_render_config
                 uint32_t *gbuffer, float *motion, const float prev_world_to_screen[16]);
 
 /* linear RGBA32F (already normalised) -> sRGB8 (clamp, IEC 61966-2-1 OETF, round) */
+/* OpenMP thread count of the loops below (harness knob) */
+void lpo_set_threads(int n);
+int lpo_max_threads(void);
+
 void lpo_tonemap_srgb8(const float *rgba, size_t n_pixels, uint8_t *out);
 void lpo_rgbe_decode(const uint8_t rgbe[4], float rgb[3]);
 

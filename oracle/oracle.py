@@ -90,8 +90,11 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def set_threads(n: int) -> None:
+def set_threads(n: int) -> int:
+    """Sets the OpenMP thread count of the oracle's loops; returns what is in effect."""
     os.environ["OMP_NUM_THREADS"] = str(n)
+    lib().lpo_set_threads(C.c_int(n))
+    return int(lib().lpo_max_threads())
 
 
 class OracleScene:
