@@ -247,11 +247,23 @@ typedef enum lp_scene_array {
   LP_SCENE_TLAS_NODES = 9, /* lp_bvh_node over instances (leaf refs = instance ids) */
   LP_SCENE_GPU_NODES = 10, /* 64-byte re-laid-out traversal nodes (host copy) */
   LP_SCENE_GPU_INSTANCES = 11, /* 128-byte instance records (host copy) */
-  LP_SCENE_GPU_NODES4 = 12 /* 128-byte 4-wide collapse of the same trees (host copy) */
+  LP_SCENE_GPU_NODES4 = 12, /* 128-byte 4-wide collapse of the same trees (host copy) */
+  LP_SCENE_ATLAS_BLOCKS = 13, /* uint32_t[4] per image: x | y << 16, w | h << 16, layer, 0 */
+  LP_SCENE_ATLAS_TEXELS = 14  /* uint8_t[4] per texel, layers * size * size texels */
 } lp_scene_array;
 LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const void **out_ptr,
                                     size_t *out_count, size_t *out_elem_size);
 LP_API lp_status lp_scene_image_count(const lp_scene *scene, size_t *out_count);
+/* ImageData::{data, width, height} of scene.images[index] [ref scene.rs:5-28]. */
+LP_API lp_status lp_scene_get_image(const lp_scene *scene, size_t index, const uint8_t **rgba8,
+                                    uint32_t *width, uint32_t *height);
+/* Decodes a PNG or baseline JPEG file image the way gltf::import_slice + rgba8_image do
+ * [ref gltf.rs:12-44,150-153] and pushes it.  Undecodable data -> LP_ERR_FILE_NOT_FOUND. */
+LP_API lp_status lp_scene_push_encoded_image(lp_scene *scene, const uint8_t *file_bytes,
+                                             size_t size, uint32_t *out_index);
+/* Atlas geometry of the texture atlas SceneGPU::new_from_scene builds from scene.images
+ * [ref scene.rs:172-184]: every layer is size x size RGBA8 texels. */
+LP_API lp_status lp_scene_atlas_info(lp_scene *scene, uint32_t *layer_size, uint32_t *layers);
 
 /* loaders::load_gltf(&[u8], &mut Scene) -> Result<(), Error> [ref gltf.rs:46-156]. */
 LP_API lp_status lp_load_gltf(const uint8_t *data, size_t size, lp_scene *scene);
@@ -274,6 +286,11 @@ LP_API lp_status lp_scene_gpu_stats(const lp_scene_gpu *sg, size_t *node_bytes, 
 LP_API lp_status lp_probe_new(lp_device *dev, const uint8_t *rgbe8, uint32_t width,
                               uint32_t height, lp_probe **out);
 LP_API lp_status lp_probe_destroy(lp_probe *probe);
+/* Host-side copy of the sampling tables lp_probe_new uploads next to the texels (the probe
+ * is importance sampled by luminance x sin(theta)): pmf[w*h],
+ * cdf_row[h], cdf_col[w*h].  No device needed; used by the CPU tests. */
+LP_API lp_status lp_probe_tables(const uint8_t *rgbe8, uint32_t width, uint32_t height, float *pmf,
+                                 float *cdf_row, float *cdf_col);
 
 /* ------------------------------------------------------------------ Renderer */
 

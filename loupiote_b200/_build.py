@@ -22,6 +22,8 @@ SOURCES = [
     CSRC / "host" / "bvh_build.cpp",
     CSRC / "host" / "scene.cpp",
     CSRC / "host" / "gltf.cpp",
+    CSRC / "host" / "image_decode.cpp",
+    CSRC / "host" / "textures.cpp",
     CSRC / "host" / "api_scene.cpp",
     CSRC / "cuda" / "api_render.cu",
 ]

@@ -85,7 +85,7 @@ class RayCounters(C.Structure):
 # lp_scene_array
 (SCENE_ENTRIES, SCENE_NODES, SCENE_PRIMITIVES, SCENE_VERTICES, SCENE_INSTANCES, SCENE_MATERIALS,
  SCENE_LIGHTS, SCENE_INDICES, SCENE_EMISSION, SCENE_TLAS_NODES, SCENE_GPU_NODES,
- SCENE_GPU_INSTANCES, SCENE_GPU_NODES4) = range(13)
+ SCENE_GPU_INSTANCES, SCENE_GPU_NODES4, SCENE_ATLAS_BLOCKS, SCENE_ATLAS_TEXELS) = range(15)
 
 _vp = C.c_void_p
 _PROTOTYPES = {
@@ -112,6 +112,10 @@ _PROTOTYPES = {
     "lp_scene_get_array": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_size_t)]),
     "lp_scene_image_count": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+    "lp_scene_get_image": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp), c_u32_p, c_u32_p]),
+    "lp_scene_push_encoded_image": (C.c_int, [_vp, _vp, C.c_size_t, c_u32_p]),
+    "lp_scene_atlas_info": (C.c_int, [_vp, c_u32_p, c_u32_p]),
+    "lp_probe_tables": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "lp_load_gltf": (C.c_int, [_vp, C.c_size_t, _vp]),
     "lp_load_gltf_path": (C.c_int, [C.c_char_p, _vp]),
     "lp_load_binary_from_path": (C.c_int, [C.c_char_p, _vp]),

@@ -141,6 +141,8 @@ _ARRAY_DTYPES = {
                                         ("root4", "<u4"), ("pad", "<u4", 2)]),
     _ffi.SCENE_GPU_NODES4: np.dtype([("lo", "<f4", (3, 4)), ("hi", "<f4", (3, 4)),
                                      ("child", "<u4", 4), ("pad", "<u4", 4)]),
+    _ffi.SCENE_ATLAS_BLOCKS: np.dtype(("<u4", 4)),
+    _ffi.SCENE_ATLAS_TEXELS: np.dtype(("u1", 4)),
 }
 
 
@@ -211,6 +213,34 @@ class Scene:
         _check(_ffi.lib().lp_scene_image_count(self._h, C.byref(n)))
         return n.value
 
+    def image(self, index: int) -> np.ndarray:
+        """(h, w, 4) uint8 copy of scene.images[index] (ImageData, scene.rs:5-28)."""
+        ptr, w, h = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        _check(_ffi.lib().lp_scene_get_image(self._h, index, C.byref(ptr), C.byref(w), C.byref(h)))
+        buf = C.string_at(ptr.value, w.value * h.value * 4)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(h.value, w.value, 4).copy()
+
+    def push_encoded_image(self, file_bytes: bytes) -> int:
+        """Decodes a PNG / baseline JPEG like gltf::import + rgba8_image (gltf.rs:12-44)."""
+        buf = (C.c_uint8 * len(file_bytes)).from_buffer_copy(file_bytes)
+        out = C.c_uint32()
+        _check(_ffi.lib().lp_scene_push_encoded_image(self._h, C.cast(buf, C.c_void_p),
+                                                      len(file_bytes), C.byref(out)))
+        return out.value
+
+    def atlas(self):
+        """Texture atlas SceneGPU::new_from_scene builds (scene.rs:172-184): returns
+        (texels (layers, size, size, 4) uint8, blocks (n_images, 5) = x, y, w, h, layer)."""
+        size, layers = C.c_uint32(), C.c_uint32()
+        _check(_ffi.lib().lp_scene_atlas_info(self._h, C.byref(size), C.byref(layers)))
+        raw = self.array(_ffi.SCENE_ATLAS_BLOCKS).reshape(-1, 4)
+        blocks = np.stack([raw[:, 0] & 0xFFFF, raw[:, 0] >> 16, raw[:, 1] & 0xFFFF,
+                           raw[:, 1] >> 16, raw[:, 2]], axis=1) if raw.size else \
+            np.zeros((0, 5), dtype=np.uint32)
+        texels = self.array(_ffi.SCENE_ATLAS_TEXELS).reshape(layers.value, size.value,
+                                                             size.value, 4)
+        return texels, blocks
+
     def _add_bvh(self, positions, normals, uvs, indices) -> int:
         pos = np.ascontiguousarray(positions, dtype=np.float32)
         if pos.ndim != 2 or pos.shape[1] not in (3, 4):
@@ -271,6 +301,17 @@ class Scene:
         m = _mat4(model_to_world)
         _check(_ffi.lib().lp_scene_set_instance_transform(self._h, instance_index,
                                                           m.ctypes.data_as(_ffi.c_float_p)))
+
+
+def probe_tables(rgbe8: np.ndarray, width: int, height: int):
+    """Host copy of the sampling tables ProbeGPU uploads: pmf (h, w), cdf_row (h,), cdf_col (h, w)."""
+    data = np.ascontiguousarray(rgbe8, dtype=np.uint8)
+    pmf = np.empty((height, width), dtype=np.float32)
+    cdf_row = np.empty(height, dtype=np.float32)
+    cdf_col = np.empty((height, width), dtype=np.float32)
+    _check(_ffi.lib().lp_probe_tables(data.ctypes.data, width, height, pmf.ctypes.data,
+                                      cdf_row.ctypes.data, cdf_col.ctypes.data))
+    return pmf, cdf_row, cdf_col
 
 
 class loaders:

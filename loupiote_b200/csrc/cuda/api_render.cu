@@ -75,6 +75,9 @@ struct lp_scene_gpu {
   lp_device *dev = nullptr;
   DevBuf<float4> nodes, nodes4, nodes4h, tris, instances, vertices, materials, emission, lights;
   DevBuf<uint32_t> indices, active_lights;
+  DevBuf<uchar4> atlas;
+  DevBuf<uint4> tex_blocks;
+  DevBuf<float> srgb_lut;
   SceneDev sc{};
   size_t node_bytes = 0, tri_bytes = 0, total_bytes = 0;
   uint32_t max_depth = 0;
@@ -83,6 +86,7 @@ struct lp_scene_gpu {
 struct lp_probe {
   lp_device *dev = nullptr;
   DevBuf<uchar4> texels;
+  DevBuf<float> pmf, cdf_row, cdf_col;
   uint32_t w = 0, h = 0;
 };
 
@@ -607,6 +611,16 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   up(g->lights, s.lights.data(), s.lights.size() * sizeof(lp_light));
   up(g->indices, s.indices.data(), s.indices.size() * sizeof(uint32_t));
   up(g->active_lights, active.data(), active.size() * sizeof(uint32_t));
+  // texture atlas + block table [ref scene.rs:172-184]; sRGB8 -> linear table (IEC 61966-2-1
+  // EOTF evaluated in double, rounded once: the same 256 floats the CPU restatement uses)
+  up(g->atlas, s.atlas.texels.data(), s.atlas.texels.size());
+  up(g->tex_blocks, s.atlas.gpu_blocks.data(), s.atlas.gpu_blocks.size() * sizeof(uint32_t));
+  float lut[256];
+  for (int i = 0; i < 256; ++i) {
+    const double c = i / 255.0;
+    lut[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+  }
+  up(g->srgb_lut, lut, sizeof(lut));
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     delete g;
@@ -628,11 +642,17 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   sc.nodes4 = g->nodes4.ptr;
   sc.nodes4h = g->nodes4h.ptr;
   sc.tlas_root4 = s.gpu_tlas_root4;
+  sc.atlas = g->atlas.ptr;
+  sc.tex_blocks = g->tex_blocks.ptr;
+  sc.srgb_lut = g->srgb_lut.ptr;
+  sc.atlas_size = s.atlas.size;
+  sc.n_textures = (uint32_t)s.atlas.blocks.size();
   g->node_bytes = s.gpu_nodes.size() * sizeof(GpuNode) + s.gpu_nodes4.size() * sizeof(GpuNode4);
   g->tri_bytes = s.primitives.size() * 64;
   g->total_bytes = g->node_bytes + g->tri_bytes + s.gpu_instances.size() * sizeof(GpuInstance) +
                    s.vertices.size() * sizeof(lp_vertex) + s.indices.size() * 4 +
-                   s.materials.size() * 48 + s.lights.size() * sizeof(lp_light);
+                   s.materials.size() * 48 + s.lights.size() * sizeof(lp_light) +
+                   s.atlas.texels.size() + s.atlas.gpu_blocks.size() * 4;
   g->max_depth = s.gpu_max_depth;
   *out = g;
   return LP_OK;
@@ -663,7 +683,17 @@ LP_API lp_status lp_probe_new(lp_device *dev, const uint8_t *rgbe8, uint32_t wid
   p->dev = dev;
   p->w = width;
   p->h = height;
+  ProbeTables tables;
+  try {
+    build_probe_tables(rgbe8, width, height, tables);
+  } catch (const std::exception &ex) {
+    delete p;
+    return fail(LP_ERR_OOM, ex.what());
+  }
   cudaError_t e = p->texels.upload(rgbe8, (size_t)width * height, dev->stream);
+  if (e == cudaSuccess) e = p->pmf.upload(tables.pmf.data(), tables.pmf.size(), dev->stream);
+  if (e == cudaSuccess) e = p->cdf_row.upload(tables.cdf_row.data(), tables.cdf_row.size(), dev->stream);
+  if (e == cudaSuccess) e = p->cdf_col.upload(tables.cdf_col.data(), tables.cdf_col.size(), dev->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
   if (e != cudaSuccess) {
     delete p;
@@ -803,6 +833,9 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
     P.sc.probe = r->probe->texels.ptr;
     P.sc.probe_w = r->probe->w;
     P.sc.probe_h = r->probe->h;
+    P.sc.probe_pmf = r->probe->pmf.ptr;
+    P.sc.probe_cdf_row = r->probe->cdf_row.ptr;
+    P.sc.probe_cdf_col = r->probe->cdf_col.ptr;
   }
   P.sc.env_on = (r->probe != nullptr) || cfg.env_color[0] > 0.0f || cfg.env_color[1] > 0.0f ||
                 cfg.env_color[2] > 0.0f;

@@ -40,6 +40,13 @@ struct SceneDev {
   float env_color[3];
   const uchar4 *probe;
   uint32_t probe_w, probe_h;
+  // sampling tables of the probe (importance sampling by luminance x sin theta)
+  const float *probe_pmf, *probe_cdf_row, *probe_cdf_col;
+  // texture atlas [ref scene.rs:172-184]: layers of atlas_size^2 RGBA8 texels + block table
+  const uchar4 *atlas;
+  const uint4 *tex_blocks;  // x | y << 16, w | h << 16, layer, 0
+  const float *srgb_lut;    // 256 entries: sRGB8 -> linear
+  uint32_t atlas_size, n_textures;
 };
 
 struct CameraDev {

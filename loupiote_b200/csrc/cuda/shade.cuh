@@ -46,6 +46,43 @@ __device__ __forceinline__ void sincos_2pi(float u, float &s, float &c) {
   c = -__cosf(x);
 }
 
+// Bilinear, repeat-wrapped lookup of atlas block `tex` at glTF texture coordinates (u, v)
+// (origin top-left, texel centres at +0.5).  SRGB: the three colour channels go through the
+// sRGB8 -> linear table BEFORE filtering (albedo); otherwise bytes / 255 (metal-rough).
+template <bool SRGB>
+__device__ __forceinline__ f3 sample_atlas(const SceneDev &sc, uint32_t tex, float u, float v) {
+  const uint4 blk = __ldg(sc.tex_blocks + tex);
+  const int bx = (int)(blk.x & 0xFFFFu), by = (int)(blk.x >> 16);
+  const int bw = (int)(blk.y & 0xFFFFu), bh = (int)(blk.y >> 16);
+  if (!(fabsf(u) <= 3.0e38f)) u = 0.0f;
+  if (!(fabsf(v) <= 3.0e38f)) v = 0.0f;
+  const float x = (u - floorf(u)) * (float)bw - 0.5f, y = (v - floorf(v)) * (float)bh - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float tx = x - fx, ty = y - fy;
+  int x0 = (int)fx, y0 = (int)fy;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  if (x0 < 0) x0 += bw;
+  if (y0 < 0) y0 += bh;
+  if (x1 >= bw) x1 -= bw;
+  if (y1 >= bh) y1 -= bh;
+  const uchar4 *layer = sc.atlas + (size_t)blk.z * sc.atlas_size * sc.atlas_size;
+  const uchar4 *r0 = layer + (size_t)(by + y0) * sc.atlas_size + bx;
+  const uchar4 *r1 = layer + (size_t)(by + y1) * sc.atlas_size + bx;
+  const uchar4 t00 = __ldg(r0 + x0), t10 = __ldg(r0 + x1), t01 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
+  const float w00 = (1.0f - tx) * (1.0f - ty), w10 = tx * (1.0f - ty), w01 = (1.0f - tx) * ty,
+              w11 = tx * ty;
+  if (SRGB) {
+    const float *lut = sc.srgb_lut;
+    return mk3(__ldg(lut + t00.x) * w00 + __ldg(lut + t10.x) * w10 + __ldg(lut + t01.x) * w01 + __ldg(lut + t11.x) * w11,
+               __ldg(lut + t00.y) * w00 + __ldg(lut + t10.y) * w10 + __ldg(lut + t01.y) * w01 + __ldg(lut + t11.y) * w11,
+               __ldg(lut + t00.z) * w00 + __ldg(lut + t10.z) * w10 + __ldg(lut + t01.z) * w01 + __ldg(lut + t11.z) * w11);
+  }
+  const float k = 1.0f / 255.0f;
+  return mk3(((float)t00.x * w00 + (float)t10.x * w10 + (float)t01.x * w01 + (float)t11.x * w11) * k,
+             ((float)t00.y * w00 + (float)t10.y * w10 + (float)t01.y * w01 + (float)t11.y * w11) * k,
+             ((float)t00.z * w00 + (float)t10.z * w10 + (float)t01.z * w01 + (float)t11.z * w11) * k);
+}
+
 __device__ __forceinline__ void fetch_surface(const SceneDev &sc, const Hit &hit, f3 d,
                                               Surface &sf, uint32_t &material_out) {
   const float4 *ip = sc.instances + 8u * (size_t)hit.inst;
@@ -90,8 +127,25 @@ __device__ __forceinline__ void fetch_surface(const SceneDev &sc, const Hit &hit
   const float4 em = __ldg(sc.emission + mi);
   sf.base = mk3(c.x, c.y, c.z);
   sf.emission = mk3(em.x, em.y, em.z);
-  sf.metallic = clampf(pr.y, 0.0f, 1.0f);
-  const float rough = clampf(pr.x, 0.0f, 1.0f);
+  float metal = pr.y, rough = pr.x;
+  // textured materials [ref gltf.rs:117-124]: base colour = factor x sRGB texture, roughness =
+  // factor x G, metallic = factor x B of the metallic-roughness texture (glTF 2.0 3.9.2)
+  const uint32_t tex_a = __float_as_uint(pr.z), tex_m = __float_as_uint(pr.w);
+  if (tex_a < sc.n_textures || tex_m < sc.n_textures) {
+    const float tu = __fmaf_rn(bw, a0.w, __fmaf_rn(bu, b0.w, bv * c0.w));
+    const float tv = __fmaf_rn(bw, a1.w, __fmaf_rn(bu, b1.w, bv * c1.w));
+    if (tex_a < sc.n_textures) {
+      const f3 t = sample_atlas<true>(sc, tex_a, tu, tv);
+      sf.base = mk3(sf.base.x * t.x, sf.base.y * t.y, sf.base.z * t.z);
+    }
+    if (tex_m < sc.n_textures) {
+      const f3 t = sample_atlas<false>(sc, tex_m, tu, tv);
+      rough *= t.y;
+      metal *= t.z;
+    }
+  }
+  sf.metallic = clampf(metal, 0.0f, 1.0f);
+  rough = clampf(rough, 0.0f, 1.0f);
   sf.alpha = fmaxf(rough * rough, 1e-3f);
   material_out = mi;
 }
@@ -218,15 +272,56 @@ __device__ __forceinline__ f3 rgbe_decode(uchar4 p) {
   return mk3((float)p.x * f, (float)p.y * f, (float)p.z * f);
 }
 
-__device__ __forceinline__ f3 env_radiance(const SceneDev &sc, f3 d) {
+// solid-angle pdf of the probe's sampling distribution for a direction inside texel `i`
+__device__ __forceinline__ float probe_pdf(const SceneDev &sc, size_t i, float sin_theta) {
+  return fdiv(__ldg(sc.probe_pmf + i) * (float)sc.probe_w * (float)sc.probe_h,
+              2.0f * LP_PI * LP_PI * fmaxf(sin_theta, 1e-6f));
+}
+
+// Environment radiance in direction d (nearest texel of the equirect probe, +y up) and, when
+// a probe is bound, the pdf with which probe_sample would have produced d.
+__device__ __forceinline__ f3 env_radiance(const SceneDev &sc, f3 d, float &pdf) {
   if (sc.probe) {
     const float u = atan2f(d.z, d.x) * (0.5f * LP_INV_PI) + 0.5f;
     const float v = acosf(clampf(d.y, -1.0f, 1.0f)) * LP_INV_PI;
     const uint32_t x = (uint32_t)fminf(u * (float)sc.probe_w, (float)(sc.probe_w - 1));
     const uint32_t y = (uint32_t)fminf(v * (float)sc.probe_h, (float)(sc.probe_h - 1));
-    return rgbe_decode(__ldg(sc.probe + (size_t)y * sc.probe_w + x));
+    const size_t i = (size_t)y * sc.probe_w + x;
+    pdf = probe_pdf(sc, i, fsqrt(fmaxf(0.0f, 1.0f - d.y * d.y)));
+    return rgbe_decode(__ldg(sc.probe + i));
   }
   return mk3(sc.env_color[0], sc.env_color[1], sc.env_color[2]);
+}
+
+// first index whose CDF entry exceeds u (the last entry of every CDF is exactly 1)
+__device__ __forceinline__ uint32_t cdf_upper_bound(const float *cdf, uint32_t n, float u) {
+  uint32_t lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(cdf + mid) > u) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// Importance-samples the probe: row from cdf_row with u1, column from that row's cdf_col with
+// u2, uniform inside the texel with the rescaled random numbers.
+__device__ __forceinline__ void probe_sample(const SceneDev &sc, float u1, float u2, f3 &wi, f3 &Le,
+                                             float &pdf) {
+  const uint32_t w = sc.probe_w, h = sc.probe_h;
+  const uint32_t y = cdf_upper_bound(sc.probe_cdf_row, h, u1);
+  const float rlo = y ? __ldg(sc.probe_cdf_row + y - 1) : 0.0f, rhi = __ldg(sc.probe_cdf_row + y);
+  const float *cc = sc.probe_cdf_col + (size_t)y * w;
+  const uint32_t x = cdf_upper_bound(cc, w, u2);
+  const float clo = x ? __ldg(cc + x - 1) : 0.0f, chi = __ldg(cc + x);
+  const float dv = clampf(fdiv(u1 - rlo, rhi - rlo), 0.0f, 0.99999f);
+  const float du = clampf(fdiv(u2 - clo, chi - clo), 0.0f, 0.99999f);
+  const float phi = (fdiv((float)x + du, (float)w) - 0.5f) * (2.0f * LP_PI);
+  const float theta = fdiv((float)y + dv, (float)h) * LP_PI;
+  const float st = __sinf(theta), ct = __cosf(theta);
+  wi = mk3(st * __cosf(phi), ct, st * __sinf(phi));
+  const size_t i = (size_t)y * w + x;
+  pdf = probe_pdf(sc, i, st);
+  Le = rgbe_decode(__ldg(sc.probe + i));
 }
 
 __device__ __forceinline__ float power_heuristic(float a, float b) {

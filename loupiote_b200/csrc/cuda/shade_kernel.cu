@@ -69,8 +69,9 @@ __device__ __forceinline__ void load_path(const FrameParams &P, uint32_t slot, P
 // A path that left the scene: environment radiance with the MIS weight of the BSDF sample.
 __device__ __forceinline__ void shade_miss(const FrameParams &P, PathIn &in) {
   if (P.sc.env_on) {
-    const f3 Le = env_radiance(P.sc, in.d);
-    const float w = in.pdf_bsdf < 0.0f ? 1.0f : power_heuristic(in.pdf_bsdf, in.pdf_env_dir);
+    float pdf_e = in.pdf_env_dir;  // cosine pdf (constant environment) unless a probe is bound
+    const f3 Le = env_radiance(P.sc, in.d, pdf_e);
+    const float w = in.pdf_bsdf < 0.0f ? 1.0f : power_heuristic(in.pdf_bsdf, pdf_e);
     in.L.x += in.T.x * Le.x * w;
     in.L.y += in.T.y * Le.y * w;
     in.L.z += in.T.z * Le.z * w;
@@ -163,16 +164,23 @@ __device__ __forceinline__ void shade_hit(const FrameParams &P, uint32_t bounce,
     }
   }
   if (sc.env_on) {
-    const f3 wi = cosine_sample(sf.ns, u01(r0.w), u01(r1.x));
+    // environment NEE: the probe's luminance distribution when one is bound, else cosine
+    f3 wi, Le;
+    float pdf_e;
+    if (sc.probe) {
+      probe_sample(sc, u01(r0.w), u01(r1.x), wi, Le, pdf_e);
+    } else {
+      wi = cosine_sample(sf.ns, u01(r0.w), u01(r1.x));
+      pdf_e = dot(sf.ns, wi) * LP_INV_PI;
+      Le = mk3(sc.env_color[0], sc.env_color[1], sc.env_color[2]);
+    }
     const float ndl = dot(sf.ns, wi);
-    if (ndl > 0.0f && dot(sf.ng, wi) > 0.0f) {
+    if (ndl > 0.0f && dot(sf.ng, wi) > 0.0f && pdf_e > 0.0f) {
       f3 f;
       float pdf_b;
       bsdf_eval(sf, cx, wo, wi, f, pdf_b);
-      const f3 Le = env_radiance(sc, wi);
-      const float pdf_e = ndl * LP_INV_PI;
       const float w = power_heuristic(pdf_e, pdf_b);
-      const float k = w * LP_PI;  // ndl * w / pdf_e
+      const float k = fdiv(ndl * w, pdf_e);
       out.se_c = mk3(T.x * f.x * Le.x * k, T.y * f.y * Le.y * k, T.z * f.z * Le.z * k);
       if (out.se_c.x > 0.0f || out.se_c.y > 0.0f || out.se_c.z > 0.0f) {
         out.want_e = true;

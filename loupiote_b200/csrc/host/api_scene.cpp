@@ -120,7 +120,7 @@ LP_API lp_status lp_scene_push_image(lp_scene *scene, const uint8_t *rgba8, uint
   if (!scene || !rgba8) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   LP_TRY(Image img; img.width = width; img.height = height;
          img.data.assign(rgba8, rgba8 + (size_t)width * height * 4);
-         scene->s.images.push_back(std::move(img));
+         scene->s.images.push_back(std::move(img)); scene->s.derived_dirty = true;
          if (out_index) *out_index = (uint32_t)scene->s.images.size() - 1; return LP_OK;)
 }
 
@@ -144,6 +144,8 @@ LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const
       case LP_SCENE_GPU_NODES: s.build_derived(); *out_ptr = s.gpu_nodes.data(); *out_count = s.gpu_nodes.size(); es = sizeof(GpuNode); break;
       case LP_SCENE_GPU_INSTANCES: s.build_derived(); *out_ptr = s.gpu_instances.data(); *out_count = s.gpu_instances.size(); es = sizeof(GpuInstance); break;
       case LP_SCENE_GPU_NODES4: s.build_derived(); *out_ptr = s.gpu_nodes4.data(); *out_count = s.gpu_nodes4.size(); es = sizeof(GpuNode4); break;
+      case LP_SCENE_ATLAS_BLOCKS: s.build_derived(); *out_ptr = s.atlas.gpu_blocks.data(); *out_count = s.atlas.blocks.size(); es = 16; break;
+      case LP_SCENE_ATLAS_TEXELS: s.build_derived(); *out_ptr = s.atlas.texels.data(); *out_count = s.atlas.texels.size() / 4; es = 4; break;
       default: return fail(LP_ERR_INVALID_ARG, "unknown scene array");
     }
   } catch (const std::exception &e) {
@@ -157,6 +159,41 @@ LP_API lp_status lp_scene_image_count(const lp_scene *scene, size_t *out_count) 
   if (!scene || !out_count) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   *out_count = scene->s.images.size();
   return LP_OK;
+}
+
+LP_API lp_status lp_scene_get_image(const lp_scene *scene, size_t index, const uint8_t **rgba8,
+                                    uint32_t *width, uint32_t *height) {
+  if (!scene) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (index >= scene->s.images.size()) return fail(LP_ERR_INVALID_ARG, "unknown image index");
+  const Image &im = scene->s.images[index];
+  if (rgba8) *rgba8 = im.data.data();
+  if (width) *width = im.width;
+  if (height) *height = im.height;
+  return LP_OK;
+}
+
+LP_API lp_status lp_scene_push_encoded_image(lp_scene *scene, const uint8_t *file_bytes,
+                                             size_t size, uint32_t *out_index) {
+  if (!scene || !file_bytes) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  LP_TRY(Image img; std::string err;
+         if (!decode_image(file_bytes, size, img, err)) return fail(LP_ERR_FILE_NOT_FOUND, err);
+         scene->s.images.push_back(std::move(img)); scene->s.derived_dirty = true;
+         if (out_index) *out_index = (uint32_t)scene->s.images.size() - 1; return LP_OK;)
+}
+
+LP_API lp_status lp_scene_atlas_info(lp_scene *scene, uint32_t *layer_size, uint32_t *layers) {
+  if (!scene) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  LP_TRY(scene->s.build_derived(); if (layer_size) *layer_size = scene->s.atlas.size;
+         if (layers) *layers = scene->s.atlas.layers; return LP_OK;)
+}
+
+LP_API lp_status lp_probe_tables(const uint8_t *rgbe8, uint32_t width, uint32_t height, float *pmf,
+                                 float *cdf_row, float *cdf_col) {
+  if (!rgbe8 || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
+  LP_TRY(ProbeTables t; build_probe_tables(rgbe8, width, height, t);
+         if (pmf) std::memcpy(pmf, t.pmf.data(), t.pmf.size() * 4);
+         if (cdf_row) std::memcpy(cdf_row, t.cdf_row.data(), t.cdf_row.size() * 4);
+         if (cdf_col) std::memcpy(cdf_col, t.cdf_col.data(), t.cdf_col.size() * 4); return LP_OK;)
 }
 
 LP_API lp_status lp_load_gltf(const uint8_t *data, size_t size, lp_scene *scene) {

@@ -3,8 +3,8 @@
 // The reference delegates parsing to the `gltf` 1.4.1 crate; this is a self-contained
 // GLB / .gltf(JSON with embedded base64 buffers) reader covering what load_gltf consumes:
 // POSITION / NORMAL / TEXCOORD_0 / indices accessors, pbrMetallicRoughness factors,
-// node-local transforms (matrix or TRS).  Image decoding (PNG/JPEG) is not available in
-// this build: textures referenced by materials are recorded as LP_INVALID_INDEX.
+// node-local transforms (matrix or TRS), baseColorTexture / metallicRoughnessTexture, and the
+// images (bufferView or data-URI PNG / JPEG, decoded by image_decode.cpp).
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -441,6 +441,57 @@ lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string 
       }
     }
 
+    // ---- images [ref gltf.rs:150-153]: every glTF image becomes one Scene image, in order,
+    // so image i of this file is scene image texture_offset + i.  An image that cannot be
+    // decoded (external uri, progressive JPEG, ...) keeps its slot as a 1x1 white texel so
+    // the indices of the others stay valid (gltf::import_slice would fail the whole load).
+    const uint32_t texture_offset = (uint32_t)scene.images.size();
+    const JValue *imgs = doc.root.get("images");
+    for (size_t i = 0; imgs && i < imgs->size(); ++i) {
+      const JValue &im = imgs->arr[i];
+      Image decoded;
+      std::string ierr;
+      bool ok = false;
+      const long bv_index = im.integer("bufferView", -1);
+      const std::string uri = im.string("uri");
+      if (bv_index >= 0) {
+        const JValue *bvs = doc.root.get("bufferViews");
+        if (bvs && (size_t)bv_index < bvs->size()) {
+          const JValue &bv = bvs->arr[bv_index];
+          const long buf = bv.integer("buffer", 0);
+          const size_t boff = (size_t)bv.integer("byteOffset", 0);
+          const size_t blen = (size_t)bv.integer("byteLength", 0);
+          if (buf >= 0 && (size_t)buf < doc.buffers.size() && boff + blen <= doc.buffers[buf].size())
+            ok = decode_image(doc.buffers[buf].data() + boff, blen, decoded, ierr);
+        }
+      } else if (uri.rfind("data:", 0) == 0) {
+        const size_t comma = uri.find(',');
+        if (comma != std::string::npos) {
+          const std::vector<uint8_t> bytes =
+              base64_decode(uri.c_str() + comma + 1, uri.size() - comma - 1);
+          ok = decode_image(bytes.data(), bytes.size(), decoded, ierr);
+        }
+      }
+      if (!ok) {
+        decoded.width = decoded.height = 1;
+        decoded.data.assign(4, 255);
+      }
+      scene.images.push_back(std::move(decoded));
+    }
+    // texture -> image: the reference stores `texture_offset + texture().index()` and then
+    // pushes one Scene image per glTF IMAGE [ref gltf.rs:117-124,150-153], which only
+    // addresses the right pixels when texture i uses image i; this loader resolves
+    // textures[i].source (documented deviation).
+    const JValue *texs = doc.root.get("textures");
+    auto texture_image = [&](const JValue *info) -> uint32_t {
+      if (!info) return LP_INVALID_INDEX;
+      const long ti = info->integer("index", -1);
+      if (!texs || ti < 0 || (size_t)ti >= texs->size()) return LP_INVALID_INDEX;
+      const long src = texs->arr[ti].integer("source", -1);
+      if (!imgs || src < 0 || (size_t)src >= imgs->size()) return LP_INVALID_INDEX;
+      return texture_offset + (uint32_t)src;
+    };
+
     // ---- materials [ref gltf.rs:109-127]
     const uint32_t mat_offset = (uint32_t)scene.materials.size();
     const JValue *mats = doc.root.get("materials");
@@ -456,6 +507,8 @@ lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string 
           for (size_t k = 0; k < 4 && k < c->size(); ++k) m.color[k] = (float)c->arr[k].num;
         m.roughness = (float)pbr->number("roughnessFactor", 1.0);
         m.reflectivity = (float)pbr->number("metallicFactor", 1.0);
+        m.albedo_texture = texture_image(pbr->get("baseColorTexture"));
+        m.mra_texture = texture_image(pbr->get("metallicRoughnessTexture"));
       }
       scene.materials.push_back(m);
       scene.emission.push_back({0.f, 0.f, 0.f, 0.f});

@@ -473,6 +473,7 @@ void Scene::build_derived() {
     g.vertex_offset = e.vertex_offset;
     g.blas = s.blas;
   }
+  build_atlas(images, 16384u, atlas);
   derived_dirty = false;
 }
 

@@ -62,6 +62,29 @@ struct Image {
   uint32_t width = 0, height = 0;
 };
 
+// Texture atlas [ref crates/lib/src/scene.rs:172-184]: every Scene image gets a block of a
+// layered RGBA8 atlas (`Atlas2D::reserve` per image, `TextureAtlas::from_atlas2d`, `upload`);
+// a material's albedo_texture / mra_texture indexes `blocks` (the texture_blocks lookup).
+struct AtlasBlock {
+  uint32_t x, y, w, h, layer;
+};
+struct Atlas {
+  uint32_t size = 0, layers = 0;    // every layer is size x size texels
+  std::vector<AtlasBlock> blocks;   // one per image, in image order
+  std::vector<uint8_t> texels;      // layers * size * size * 4 bytes
+  std::vector<uint32_t> gpu_blocks; // 4 x u32 per block: x | y << 16, w | h << 16, layer, 0
+};
+void build_atlas(const std::vector<Image> &images, uint32_t max_layer_size, Atlas &out);
+
+// Piecewise-constant sampling distribution of an RGBE8 equirect probe (luminance x sin theta):
+// pmf per texel, CDF over rows, per-row CDF over columns.
+struct ProbeTables {
+  std::vector<float> pmf, cdf_row, cdf_col;
+};
+void build_probe_tables(const uint8_t *rgbe8, uint32_t w, uint32_t h, ProbeTables &out);
+
+bool decode_image(const uint8_t *data, size_t size, Image &out, std::string &err);
+
 struct Scene {
   std::vector<lp_material> materials;
   std::vector<std::array<float, 4>> emission;
@@ -84,6 +107,7 @@ struct Scene {
   std::vector<GpuNode4h> gpu_nodes4h;
   uint32_t gpu_tlas_root4 = 0;
   uint32_t gpu_max_stack4 = 0;
+  Atlas atlas;
   bool derived_dirty = true;
 
   Scene();

@@ -175,3 +175,113 @@ def orbit_view(view: np.ndarray, degrees: float) -> np.ndarray:
     R = np.array([[math.cos(a), 0, math.sin(a), 0], [0, 1, 0, 0],
                   [-math.sin(a), 0, math.cos(a), 0], [0, 0, 0, 1]], dtype=np.float32)
     return (R @ view).astype(np.float32)
+
+
+def rgbe_encode(rgb: np.ndarray) -> np.ndarray:
+    """Float RGB (h, w, 3) -> RGBE8 (h, w, 4) (Ward's shared-exponent format, what the
+    reference's .hdr loader hands to ProbeGPU::new, standalone/src/app.rs:139-155)."""
+    rgb = np.asarray(rgb, dtype=np.float64)
+    m = rgb.max(axis=-1)
+    out = np.zeros(rgb.shape[:-1] + (4,), dtype=np.uint8)
+    ok = m > 1e-32
+    mant, exp = np.frexp(np.where(ok, m, 1.0))
+    scale = np.where(ok, mant * 256.0 / np.where(ok, m, 1.0), 0.0)
+    out[..., :3] = np.clip(rgb * scale[..., None], 0, 255).astype(np.uint8)
+    out[..., 3] = np.where(ok, exp + 128, 0).astype(np.uint8)
+    return out
+
+
+def procedural_probe(width: int = 256, height: int = 128):
+    """Deterministic RGBE8 equirect sky: horizon-to-zenith gradient, dim ground, a small very
+    bright sun (what importance sampling is for) and a secondary soft light.
+    Returns (rgbe8 (h, w, 4) uint8, width, height)."""
+    v, u = np.mgrid[0:height, 0:width].astype(np.float64)
+    theta = (v + 0.5) / height * math.pi
+    phi = ((u + 0.5) / width - 0.5) * 2.0 * math.pi
+    d = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta), np.sin(theta) * np.sin(phi)], -1)
+    up = np.clip(d[..., 1], 0.0, 1.0)[..., None]
+    sky = (1 - up) * np.array([0.9, 0.85, 0.8]) + up * np.array([0.25, 0.45, 0.95])
+    rgb = np.where(d[..., 1:2] >= 0.0, sky, np.array([0.12, 0.1, 0.08]))
+    sun = np.array([0.45, 0.75, 0.35])
+    sun /= np.linalg.norm(sun)
+    c = d @ sun
+    rgb = rgb + (c > math.cos(math.radians(3.0)))[..., None] * np.array([900.0, 820.0, 700.0])
+    lamp = np.array([-0.7, 0.3, -0.5])
+    lamp /= np.linalg.norm(lamp)
+    rgb = rgb + np.clip((d @ lamp - 0.9) / 0.1, 0, 1)[..., None] ** 2 * np.array([3.0, 6.0, 9.0])
+    return rgbe_encode(rgb), width, height
+
+
+def _uv_sphere(stacks: int, slices: int):
+    """Unit sphere with equirect texture coordinates (seam duplicated)."""
+    vi, ui = np.mgrid[0:stacks + 1, 0:slices + 1]
+    th = vi / stacks * math.pi
+    ph = ui / slices * 2.0 * math.pi
+    p = np.stack([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)], -1).reshape(-1, 3)
+    uv = np.stack([ui / slices, vi / stacks], -1).reshape(-1, 2)
+    a = (vi[:-1, :-1] * (slices + 1) + ui[:-1, :-1]).reshape(-1)
+    b, c, d = a + 1, a + slices + 1, a + slices + 2
+    f = np.concatenate([np.stack([a, c, b], 1), np.stack([b, c, d], 1)], 0)
+    return p, uv, f.astype(np.uint32)
+
+
+def procedural_textures(size: int = 64):
+    """Three deterministic RGBA8 images of different sizes: an sRGB albedo checker with
+    coloured cells, a metal-rough map (G = roughness stripes, B = metallic dots) and a small
+    non-square noise albedo (exercises the atlas packer and the wrap)."""
+    y, x = np.mgrid[0:size, 0:size]
+    cell = ((x // (size // 8)) + (y // (size // 8))) % 2
+    albedo = np.zeros((size, size, 4), dtype=np.uint8)
+    albedo[..., 0] = np.where(cell, 230, 40 + (x * 3) % 100)
+    albedo[..., 1] = np.where(cell, 220 - (y * 2) % 120, 60)
+    albedo[..., 2] = np.where(cell, 60 + (x + y) % 150, 200)
+    albedo[..., 3] = 255
+    mra = np.zeros((size * 2, size, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[0:size * 2, 0:size]
+    mra[..., 1] = (40 + 200 * ((yy // 8) % 2)).astype(np.uint8)
+    mra[..., 2] = (255 * ((((xx % 16) - 8) ** 2 + ((yy % 16) - 8) ** 2) < 25)).astype(np.uint8)
+    mra[..., 3] = 255
+    h = _hash_u32(np.arange(24 * 40, dtype=np.uint64))
+    noise = np.zeros((24, 40, 4), dtype=np.uint8)
+    noise[..., 0] = (h & np.uint32(0xFF)).reshape(24, 40)
+    noise[..., 1] = ((h >> np.uint32(8)) & np.uint32(0xFF)).reshape(24, 40)
+    noise[..., 2] = ((h >> np.uint32(16)) & np.uint32(0xFF)).reshape(24, 40)
+    noise[..., 3] = 255
+    return albedo, mra, noise
+
+
+def textured_scene(with_light: bool = True) -> dict:
+    """textured ground (uv repeated 4x, beyond [0,1] and negative), three
+    uv-mapped spheres (albedo only, albedo + metal-rough, metal-rough only) under a quad light
+    and the procedural probe."""
+    scene = Scene()
+    albedo, mra, noise = procedural_textures()
+    ia, im, inz = scene.push_image(albedo), scene.push_image(mra), scene.push_image(noise)
+    half = 6.0
+    pos = np.array([[-half, 0, -half], [half, 0, -half], [half, 0, half], [-half, 0, half]],
+                   dtype=np.float32)
+    nrm = np.tile(np.array([[0.0, 1.0, 0.0]], dtype=np.float32), (4, 1))
+    uv = np.array([[-2.0, -2.0], [2.0, -2.0], [2.0, 2.0], [-2.0, 2.0]], dtype=np.float32)
+    ground = scene.blas.add_bvh_indexed(pos, np.array([0, 2, 1, 0, 3, 2], dtype=np.uint32), nrm, uv)
+    mg = scene.push_material(color=[0.9, 0.9, 0.9, 1.0], roughness=0.9, reflectivity=0.0,
+                             albedo_texture=ia)
+    scene.blas.add_instance(ground, np.eye(4, dtype=np.float32), mg)
+    p, suv, f = _uv_sphere(24, 48)
+    sphere = scene.blas.add_bvh_indexed(p.astype(np.float32), f.reshape(-1), p.astype(np.float32),
+                                        (suv * np.array([3.0, 2.0])).astype(np.float32))
+    mats = [scene.push_material(color=[1, 1, 1, 1], roughness=0.7, reflectivity=0.0, albedo_texture=inz),
+            scene.push_material(color=[1.0, 0.9, 0.8, 1], roughness=1.0, reflectivity=1.0,
+                                albedo_texture=ia, mra_texture=im),
+            scene.push_material(color=[0.8, 0.8, 0.85, 1], roughness=0.8, reflectivity=1.0,
+                                mra_texture=im)]
+    for k, mat in enumerate(mats):
+        m = np.eye(4, dtype=np.float32)
+        m[0, 3], m[1, 3], m[2, 3] = (k - 1) * 2.4, 1.0, 0.0
+        scene.blas.add_instance(sphere, m, mat)
+    if with_light:
+        scene.push_light(center=(0.0, 5.0, 1.0), tangent=(1.0, 0.0, 0.0), bitangent=(0.0, 0.0, 1.0),
+                         intensity=8.0, color=(1.0, 0.95, 0.9))
+    d = np.array([0.0, -0.35, -1.0])
+    view = look_at_view((0.0, 3.2, 7.5), d / np.linalg.norm(d))
+    return {"scene": scene, "view": view, "env_color": (0.0, 0.0, 0.0), "name": "textured",
+            "probe": procedural_probe()}

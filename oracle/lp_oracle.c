@@ -553,6 +553,49 @@ static void xform_normal(const lp_instance *inst, const float n[3], float out[3]
     out[r] = fmaf(m[4 * r], n[0], fmaf(m[4 * r + 1], n[1], m[4 * r + 2] * n[2]));
 }
 
+/* sRGB8 -> linear (IEC 61966-2-1 EOTF in double, rounded once to float) */
+static float srgb_lut[256];
+static int srgb_lut_ready = 0;
+static void srgb_lut_init(void) {
+#pragma omp critical(lpo_srgb_lut)
+  if (!srgb_lut_ready) {
+    for (int i = 0; i < 256; ++i) {
+      const double c = i / 255.0;
+      srgb_lut[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+    }
+    srgb_lut_ready = 1;
+  }
+}
+
+void lpo_sample_image(const lpo_scene *s, uint32_t image, float u, float v, int srgb, float rgb[3]) {
+  if (!srgb_lut_ready) srgb_lut_init();
+  const int w = (int)s->image_w[image], h = (int)s->image_h[image];
+  const uint8_t *px = s->images[image];
+  if (!(fabsf(u) <= 3.0e38f)) u = 0.0f;
+  if (!(fabsf(v) <= 3.0e38f)) v = 0.0f;
+  /* repeat wrap, texel centres at +0.5, origin top-left (glTF 2.0 3.8.4) */
+  const float x = (u - floorf(u)) * (float)w - 0.5f, y = (v - floorf(v)) * (float)h - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float tx = x - fx, ty = y - fy;
+  int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  if (x0 < 0) x0 += w;
+  if (y0 < 0) y0 += h;
+  if (x1 >= w) x1 -= w;
+  if (y1 >= h) y1 -= h;
+  const uint8_t *t00 = px + 4 * ((size_t)y0 * w + x0), *t10 = px + 4 * ((size_t)y0 * w + x1);
+  const uint8_t *t01 = px + 4 * ((size_t)y1 * w + x0), *t11 = px + 4 * ((size_t)y1 * w + x1);
+  const float w00 = (1.0f - tx) * (1.0f - ty), w10 = tx * (1.0f - ty), w01 = (1.0f - tx) * ty,
+              w11 = tx * ty;
+  for (int c = 0; c < 3; ++c) {
+    if (srgb)
+      rgb[c] = srgb_lut[t00[c]] * w00 + srgb_lut[t10[c]] * w10 + srgb_lut[t01[c]] * w01 +
+               srgb_lut[t11[c]] * w11;
+    else
+      rgb[c] = ((float)t00[c] * w00 + (float)t10[c] * w10 + (float)t01[c] * w01 +
+                (float)t11[c] * w11) * (1.0f / 255.0f);
+  }
+}
+
 static void fetch_surface(const lpo_scene *s, const lpo_hit *hit, const float d[3], surface *sf) {
   const lp_instance *inst = &s->instances[hit->instance];
   const lp_blas_entry *e = &s->entries[inst->blas];
@@ -588,8 +631,26 @@ static void fetch_surface(const lpo_scene *s, const lpo_hit *hit, const float d[
     sf->base[a] = m->color[a];
     sf->emission[a] = s->emission ? s->emission[4 * mi + a] : 0.0f;
   }
-  sf->metallic = clampf(m->reflectivity, 0.0f, 1.0f);
-  const float rough = clampf(m->roughness, 0.0f, 1.0f);
+  float metal = m->reflectivity, rough = m->roughness;
+  /* textured materials [ref gltf.rs:117-124]: base colour x sRGB texture, roughness x G and
+   * metallic x B of the metallic-roughness texture; uv rides in the .w lanes of Vertex */
+  const int has_a = m->albedo_texture < s->n_images, has_m = m->mra_texture < s->n_images;
+  if (has_a || has_m) {
+    const float tu = fmaf(bw, v0->u, fmaf(bu, v1->u, bv * v2->u));
+    const float tv = fmaf(bw, v0->v, fmaf(bu, v1->v, bv * v2->v));
+    float t[3];
+    if (has_a) {
+      lpo_sample_image(s, m->albedo_texture, tu, tv, 1, t);
+      for (int a = 0; a < 3; ++a) sf->base[a] *= t[a];
+    }
+    if (has_m) {
+      lpo_sample_image(s, m->mra_texture, tu, tv, 0, t);
+      rough *= t[1];
+      metal *= t[2];
+    }
+  }
+  sf->metallic = clampf(metal, 0.0f, 1.0f);
+  rough = clampf(rough, 0.0f, 1.0f);
   sf->alpha = maxf(rough * rough, 1e-3f);
 }
 
@@ -723,14 +784,100 @@ void lpo_rgbe_decode(const uint8_t rgbe[4], float rgb[3]) {
   rgb[2] = (float)rgbe[2] * f;
 }
 
-static void env_radiance(const lpo_scene *s, const float d[3], float out[3]) {
+/* ---- probe importance sampling: piecewise-constant over texels, luminance x sin(theta) */
+void lpo_probe_tables(const uint8_t *rgbe8, uint32_t w, uint32_t h, float *pmf, float *cdf_row,
+                      float *cdf_col) {
+  const size_t n = (size_t)w * h;
+  double *f = (double *)malloc(n * sizeof(double));
+  double *rowsum = (double *)malloc(h * sizeof(double));
+  double total = 0.0;
+  for (uint32_t y = 0; y < h; ++y) {
+    const double st = sin(3.14159265358979323846 * ((double)y + 0.5) / (double)h);
+    double rs = 0.0;
+    for (uint32_t x = 0; x < w; ++x) {
+      float rgb[3];
+      lpo_rgbe_decode(rgbe8 + 4 * ((size_t)y * w + x), rgb);
+      const double lum = 0.2126 * (double)rgb[0] + 0.7152 * (double)rgb[1] + 0.0722 * (double)rgb[2];
+      f[(size_t)y * w + x] = lum * st;
+      rs += lum * st;
+    }
+    rowsum[y] = rs;
+    total += rs;
+  }
+  if (!(total > 0.0)) { /* black probe: uniform over the sphere */
+    total = 0.0;
+    for (uint32_t y = 0; y < h; ++y) {
+      const double st = sin(3.14159265358979323846 * ((double)y + 0.5) / (double)h);
+      double rs = 0.0;
+      for (uint32_t x = 0; x < w; ++x) {
+        f[(size_t)y * w + x] = st;
+        rs += st;
+      }
+      rowsum[y] = rs;
+      total += rs;
+    }
+  }
+  double acc_rows = 0.0;
+  for (uint32_t y = 0; y < h; ++y) {
+    acc_rows += rowsum[y];
+    cdf_row[y] = (y + 1 == h) ? 1.0f : (float)(acc_rows / total);
+    double acc = 0.0;
+    for (uint32_t x = 0; x < w; ++x) {
+      const size_t i = (size_t)y * w + x;
+      acc += f[i];
+      pmf[i] = (float)(f[i] / total);
+      cdf_col[i] = (x + 1 == w || !(rowsum[y] > 0.0)) ? 1.0f : (float)(acc / rowsum[y]);
+    }
+  }
+  free(f);
+  free(rowsum);
+}
+
+static inline float probe_pdf(const lpo_scene *s, size_t texel, float sin_theta) {
+  return s->probe_pmf[texel] * (float)s->probe_w * (float)s->probe_h /
+         (2.0f * LPO_PI * LPO_PI * maxf(sin_theta, 1e-6f));
+}
+
+/* first index whose CDF entry exceeds u */
+static uint32_t cdf_upper_bound(const float *cdf, uint32_t n, float u) {
+  uint32_t lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+void lpo_probe_sample(const lpo_scene *s, float u1, float u2, float wi[3], float Le[3], float *pdf) {
+  const uint32_t w = s->probe_w, h = s->probe_h;
+  const uint32_t y = cdf_upper_bound(s->probe_cdf_row, h, u1);
+  const float rlo = y ? s->probe_cdf_row[y - 1] : 0.0f, rhi = s->probe_cdf_row[y];
+  const float *cc = s->probe_cdf_col + (size_t)y * w;
+  const uint32_t x = cdf_upper_bound(cc, w, u2);
+  const float clo = x ? cc[x - 1] : 0.0f, chi = cc[x];
+  const float dv = clampf((u1 - rlo) / (rhi - rlo), 0.0f, 0.99999f);
+  const float du = clampf((u2 - clo) / (chi - clo), 0.0f, 0.99999f);
+  const float phi = (((float)x + du) / (float)w - 0.5f) * (2.0f * LPO_PI);
+  const float theta = ((float)y + dv) / (float)h * LPO_PI;
+  const float st = sinf(theta), ct = cosf(theta);
+  wi[0] = st * cosf(phi);
+  wi[1] = ct;
+  wi[2] = st * sinf(phi);
+  const size_t i = (size_t)y * w + x;
+  *pdf = probe_pdf(s, i, st);
+  lpo_rgbe_decode(s->probe_rgbe8 + 4 * i, Le);
+}
+
+void lpo_env_lookup(const lpo_scene *s, const float d[3], float out[3], float *pdf) {
   if (s->probe_rgbe8 && s->probe_w && s->probe_h) {
     /* equirect, +y up: u = atan2(z, x)/(2pi) + 0.5, v = acos(y)/pi; nearest texel */
     const float u = atan2f(d[2], d[0]) * (0.5f * LPO_INV_PI) + 0.5f;
     const float v = acosf(clampf(d[1], -1.0f, 1.0f)) * LPO_INV_PI;
     uint32_t x = (uint32_t)minf(u * (float)s->probe_w, (float)(s->probe_w - 1));
     uint32_t y = (uint32_t)minf(v * (float)s->probe_h, (float)(s->probe_h - 1));
-    lpo_rgbe_decode(s->probe_rgbe8 + 4 * ((size_t)y * s->probe_w + x), out);
+    const size_t i = (size_t)y * s->probe_w + x;
+    lpo_rgbe_decode(s->probe_rgbe8 + 4 * i, out);
+    if (pdf) *pdf = s->probe_pmf ? probe_pdf(s, i, sqrtf(maxf(0.0f, 1.0f - d[1] * d[1]))) : 0.0f;
     return;
   }
   out[0] = s->env_color[0];
@@ -822,9 +969,9 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
 
     if (hit.instance == LP_INVALID_INDEX) {
       if (env_on) {
-        float Le[3];
-        env_radiance(s, d, Le);
-        const float w = pdf_bsdf < 0.0f ? 1.0f : power_heuristic(pdf_bsdf, pdf_env_dir);
+        float Le[3], pdf_e = pdf_env_dir; /* cosine pdf unless a probe is bound */
+        lpo_env_lookup(s, d, Le, &pdf_e);
+        const float w = pdf_bsdf < 0.0f ? 1.0f : power_heuristic(pdf_bsdf, pdf_e);
         for (int a = 0; a < 3; ++a) L[a] += T[a] * Le[a] * w;
       }
       break;
@@ -926,16 +1073,21 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
         }
       }
     }
-    /* ---- next-event estimation: environment (cosine-weighted about ns) */
+    /* ---- next-event estimation: environment (the probe's luminance distribution when a
+     * probe is bound, else cosine-weighted about ns) */
     if (env_on) {
-      float wi[3];
-      cosine_sample(sf.ns, u01(r0[3]), u01(r1[0]), wi);
+      float wi[3], Le[3], pdf_e;
+      if (s->probe_rgbe8) {
+        lpo_probe_sample(s, u01(r0[3]), u01(r1[0]), wi, Le, &pdf_e);
+      } else {
+        cosine_sample(sf.ns, u01(r0[3]), u01(r1[0]), wi);
+        pdf_e = dot3(sf.ns, wi) * LPO_INV_PI;
+        for (int a = 0; a < 3; ++a) Le[a] = s->env_color[a];
+      }
       const float ndl = dot3(sf.ns, wi);
-      if (ndl > 0.0f && dot3(sf.ng, wi) > 0.0f) {
-        float f[3], pdf_b, Le[3];
+      if (ndl > 0.0f && dot3(sf.ng, wi) > 0.0f && pdf_e > 0.0f) {
+        float f[3], pdf_b;
         bsdf_eval(&sf, wo, wi, f, &pdf_b);
-        env_radiance(s, wi, Le);
-        const float pdf_e = ndl * LPO_INV_PI;
         const float w = power_heuristic(pdf_e, pdf_b);
         const float k = ndl * w / pdf_e;
         const float C[3] = {T[0] * f[0] * Le[0] * k, T[1] * f[1] * Le[1] * k,
@@ -979,6 +1131,7 @@ void lpo_render(const lpo_scene *s, const lp_camera *cam, const lp_render_config
                 uint32_t *gbuffer, float *motion, const float prev_world_to_screen[16]) {
   const long n = (long)cam->width * cam->height;
   if (pixel_step == 0) pixel_step = 1;
+  if (!srgb_lut_ready) srgb_lut_init();
   lpo_render_stats total;
   memset(&total, 0, sizeof(total));
 #pragma omp parallel

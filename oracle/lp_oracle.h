@@ -53,6 +53,13 @@ typedef struct lpo_scene {
   float env_color[3];
   const uint8_t *probe_rgbe8;
   uint32_t probe_w, probe_h;
+  /* sampling tables of the probe, filled by lpo_probe_tables (required when a probe is set) */
+  const float *probe_pmf, *probe_cdf_row, *probe_cdf_col;
+  /* scene.images [ref scene.rs:5-35]: RGBA8, row 0 = top; the oracle samples the images
+   * themselves, not the product's atlas */
+  const uint8_t *const *images;
+  const uint32_t *image_w, *image_h;
+  size_t n_images;
 } lpo_scene;
 
 typedef struct lpo_hit {
@@ -121,6 +128,18 @@ int lpo_max_threads(void);
 
 void lpo_tonemap_srgb8(const float *rgba, size_t n_pixels, uint8_t *out);
 void lpo_rgbe_decode(const uint8_t rgbe[4], float rgb[3]);
+
+/* Probe sampling distribution: f = luminance x sin(pi (y+.5)/h) in
+ * double; pmf[w*h] = f / sum; cdf_row[h]; cdf_col[w*h] (per-row, last entry exactly 1). */
+void lpo_probe_tables(const uint8_t *rgbe8, uint32_t w, uint32_t h, float *pmf, float *cdf_row,
+                      float *cdf_col);
+/* importance-sampled probe direction for (u1, u2): wi, radiance, solid-angle pdf */
+void lpo_probe_sample(const lpo_scene *s, float u1, float u2, float wi[3], float Le[3], float *pdf);
+/* environment radiance towards d and the pdf lpo_probe_sample has for d (0 without probe) */
+void lpo_env_lookup(const lpo_scene *s, const float d[3], float Le[3], float *pdf);
+/* bilinear, repeat-wrapped lookup of scene image `image` at glTF texture coordinates;
+ * srgb != 0 decodes the colour channels sRGB8 -> linear before filtering */
+void lpo_sample_image(const lpo_scene *s, uint32_t image, float u, float v, int srgb, float rgb[3]);
 
 /* ---- SVGF (Schied et al. 2017), sequencing per asvgf.rs:240-291 */
 typedef struct lpo_svgf_frame {

@@ -52,7 +52,10 @@ class LpoScene(C.Structure):
                 ("materials", C.c_void_p), ("n_materials", C.c_size_t), ("emission", C.c_void_p),
                 ("lights", C.c_void_p), ("n_lights", C.c_size_t), ("tlas", C.c_void_p),
                 ("n_tlas", C.c_size_t), ("env_color", C.c_float * 3), ("probe_rgbe8", C.c_void_p),
-                ("probe_w", C.c_uint32), ("probe_h", C.c_uint32)]
+                ("probe_w", C.c_uint32), ("probe_h", C.c_uint32),
+                ("probe_pmf", C.c_void_p), ("probe_cdf_row", C.c_void_p),
+                ("probe_cdf_col", C.c_void_p), ("images", C.c_void_p), ("image_w", C.c_void_p),
+                ("image_h", C.c_void_p), ("n_images", C.c_size_t)]
 
 
 class LpoHit(C.Structure):
@@ -125,10 +128,56 @@ class OracleScene:
             self._keep["probe"] = np.ascontiguousarray(data, dtype=np.uint8)
             s.probe_rgbe8 = self._keep["probe"].ctypes.data
             s.probe_w, s.probe_h = w, h
+            pmf, cdf_row, cdf_col = probe_tables(self._keep["probe"], w, h)
+            self._keep.update(probe_pmf=pmf, probe_cdf_row=cdf_row, probe_cdf_col=cdf_col)
+            s.probe_pmf, s.probe_cdf_row = pmf.ctypes.data, cdf_row.ctypes.data
+            s.probe_cdf_col = cdf_col.ctypes.data
+        # scene.images: the oracle samples the images themselves, not the product's atlas
+        imgs = [np.ascontiguousarray(scene.image(i)) for i in range(scene.image_count)]
+        if imgs:
+            self._keep["images"] = imgs
+            ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+            ws = np.array([im.shape[1] for im in imgs], dtype=np.uint32)
+            hs = np.array([im.shape[0] for im in imgs], dtype=np.uint32)
+            self._keep.update(image_ptrs=ptrs, image_w=ws, image_h=hs)
+            s.images = C.cast(ptrs, C.c_void_p)
+            s.image_w, s.image_h = ws.ctypes.data, hs.ctypes.data
+            s.n_images = len(imgs)
         self.c = s
 
     def arrays(self):
         return self._keep
+
+
+def probe_tables(rgbe8, w: int, h: int):
+    """Sampling tables of an RGBE8 equirect probe: pmf (h, w), cdf_row (h,), cdf_col (h, w)."""
+    data = np.ascontiguousarray(rgbe8, dtype=np.uint8)
+    pmf = np.empty((h, w), dtype=np.float32)
+    cdf_row = np.empty(h, dtype=np.float32)
+    cdf_col = np.empty((h, w), dtype=np.float32)
+    lib().lpo_probe_tables(C.c_void_p(data.ctypes.data), C.c_uint32(w), C.c_uint32(h),
+                           C.c_void_p(pmf.ctypes.data), C.c_void_p(cdf_row.ctypes.data),
+                           C.c_void_p(cdf_col.ctypes.data))
+    return pmf, cdf_row, cdf_col
+
+
+def probe_sample(oscene: "OracleScene", u1: float, u2: float):
+    wi, le, pdf = (C.c_float * 3)(), (C.c_float * 3)(), C.c_float()
+    lib().lpo_probe_sample(C.byref(oscene.c), C.c_float(u1), C.c_float(u2), wi, le, C.byref(pdf))
+    return np.array(wi, dtype=np.float32), np.array(le, dtype=np.float32), pdf.value
+
+
+def env_lookup(oscene: "OracleScene", d):
+    le, pdf = (C.c_float * 3)(), C.c_float()
+    lib().lpo_env_lookup(C.byref(oscene.c), (C.c_float * 3)(*d), le, C.byref(pdf))
+    return np.array(le, dtype=np.float32), pdf.value
+
+
+def sample_image(oscene: "OracleScene", image: int, u: float, v: float, srgb: bool):
+    out = (C.c_float * 3)()
+    lib().lpo_sample_image(C.byref(oscene.c), C.c_uint32(image), C.c_float(u), C.c_float(v),
+                           C.c_int(int(srgb)), out)
+    return np.array(out, dtype=np.float32)
 
 
 def camera_from_view(view, w, h, v_fov):

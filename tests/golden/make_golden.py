@@ -38,6 +38,18 @@ def main():
         ray_counts=np.array([rs["primary"], rs["bounce"], rs["shadow"]], dtype=np.int64))
     print("wrote golden:", st, rs["primary"], rs["bounce"], rs["shadow"])
 
+    # textured scene under the procedural probe
+    c = scenes.textured_scene()
+    osc = O.OracleScene(c["scene"], env_color=c["env_color"], probe=c["probe"])
+    cam3 = O.camera_from_view(c["view"], 64, 36, V_FOV)
+    acc, rs, gb, _ = O.render(osc, cam3, cfg, 4, want_gbuffer=True)
+    np.savez_compressed(
+        Path(__file__).resolve().parent / "textured_oracle_golden.npz",
+        radiance_64x36_4spp_4b=(acc[..., :3] / acc[..., 3:4]).astype(np.float32),
+        ray_counts=np.array([rs["primary"], rs["bounce"], rs["shadow"]], dtype=np.int64),
+        gbuffer_albedo=gb[..., 3])
+    print("wrote textured golden:", rs["primary"], rs["bounce"], rs["shadow"])
+
 
 if __name__ == "__main__":
     main()
