@@ -212,8 +212,15 @@ def run_ours(args) -> None:
                     **multi.sample_partition(rank, world))
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
 
-    # the accumulator as a torch tensor (zero copy) for the NCCL reduce
-    accum_t = multi.accum_tensor(r, local_rank)
+    # the accumulator as a torch tensor (zero copy) for the NCCL reduce; looked up again
+    # whenever the renderer may have re-allocated its targets (set_config / resize)
+    accum_ref = {"ptr": None, "t": None}
+
+    def accum_tensor():
+        ptr = r.accum_device_ptr()[0]
+        if ptr != accum_ref["ptr"]:
+            accum_ref["ptr"], accum_ref["t"] = ptr, multi.accum_tensor(r, local_rank)
+        return accum_ref["t"]
 
     def barrier():
         if world > 1:
@@ -223,7 +230,7 @@ def run_ours(args) -> None:
     def reduce_accum():
         if world > 1:
             with torch.cuda.stream(stream):
-                multi.reduce_sum_(accum_t, dst=0)
+                multi.reduce_sum_(accum_tensor(), dst=0)
 
     # ---- canonical traversal statistics (untimed, one step, count_stats on): gives the
     # algorithmic bytes per ray that the roofline is defined on

@@ -47,9 +47,12 @@ struct DevBuf {
     ptr = nullptr;
     count = 0;
   }
+  // keeps the allocation (and so the device address a caller may hold, e.g. the accumulator
+  // handed out by lp_renderer_accum_device_ptr) when the element count does not change
   cudaError_t alloc(size_t n) {
-    release();
     if (n == 0) n = 1;
+    if (ptr && count == n) return cudaSuccess;
+    release();
     cudaError_t e = cudaMalloc((void **)&ptr, n * sizeof(T));
     if (e == cudaSuccess) count = n;
     return e;

@@ -228,3 +228,18 @@ def test_queries_labels(device):
     q = r.queries
     for label in ("ray generation", "primary intersection", "shading 0"):
         assert label in q and q[label] >= 0.0
+
+
+def test_accumulator_address_survives_config_changes(device):
+    """lp_renderer_accum_device_ptr hands the accumulator to the host framework for the
+    multi-GPU reduce: changing spp_per_call / bounces must not move it (only resize may)."""
+    c = scenes.cornell_box()
+    r, sg = make_renderer(device, c["scene"], (64, 48), max_bounces=2, spp_per_call=1)
+    p0, n0, _ = r.accum_device_ptr()
+    r.set_config(max_bounces=4, spp_per_call=8)
+    r.raytrace(c["view"])
+    p1, n1, s1 = r.accum_device_ptr()
+    assert (p0, n0) == (p1, n1) and n1 == 64 * 48 * 4 and s1 == 8
+    r.resize(sg, None, (128, 96))
+    _, n2, _ = r.accum_device_ptr()
+    assert n2 == 128 * 96 * 4
