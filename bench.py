@@ -56,6 +56,20 @@ def algorithmic_bytes_flops(c: dict) -> dict:
     return out
 
 
+def ncu_traffic(workload: str, spp_per_step: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the extend kernels, from the
+    committed ncu --set full capture of this workload (profiles/ncu_traffic.json); None when
+    no capture matches what is being run."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        t = json.loads(p.read_text())
+        if t["workload"] == workload and t["spp_per_step"] == spp_per_step:
+            return t["extend"]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 def measured_peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -344,7 +358,10 @@ def run_ours(args) -> None:
             "rays_per_step": rays / args.steps,
             "roofline_fraction_of_path": value / (world * roof_mrays),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": ncu_traffic(args.workload, args.spp_per_step),
+                         "algorithmic_bytes_per_launch": achieved * 1e9 * ext_ms * 1e-3
+                         / max(ext_launches, 1),
                          "kernel": "extend_kernel", "launch_ms": ext_ms / max(ext_launches, 1),
                          "launches": ext_launches, "peak_source": peaks["source"],
                          "fp32_peak_tflops": fp32,
