@@ -345,6 +345,14 @@ LP_API lp_status lp_renderer_set_config(lp_renderer *r, const lp_render_config *
 LP_API lp_status lp_renderer_get_config(const lp_renderer *r, lp_render_config *cfg);
 /* Main render target as linear RGBA32F (w*h*4 floats), already divided by frame count. */
 LP_API lp_status lp_renderer_read_accum_f32(lp_renderer *r, float *out, size_t cap_floats);
+/* Checkpoint / resume of a long accumulation: the raw FP32 SUM target (w*h*4 floats, alpha =
+ * sample count) and the number of samples in it.  After write_accum_sum the next raytrace
+ * call adds to the restored sum (set lp_render_config.sample_offset to `samples` so the
+ * sample sequence continues where the checkpoint stopped). */
+LP_API lp_status lp_renderer_read_accum_sum(lp_renderer *r, float *out, size_t cap_floats,
+                                            uint32_t *samples);
+LP_API lp_status lp_renderer_write_accum_sum(lp_renderer *r, const float *in, size_t count_floats,
+                                             uint32_t samples);
 /* First-hit ids of the LAST traced sample's primary rays: instance (LP_INVALID_INDEX on
  * miss, 0xFFFFFFFE for an area light) and primitive (triangle index inside its BLAS, or
  * light index); t = hit distance. Any pointer may be NULL. */

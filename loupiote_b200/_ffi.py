@@ -146,6 +146,8 @@ _PROTOTYPES = {
     "lp_renderer_set_config": (C.c_int, [_vp, C.POINTER(RenderConfig)]),
     "lp_renderer_get_config": (C.c_int, [_vp, C.POINTER(RenderConfig)]),
     "lp_renderer_read_accum_f32": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "lp_renderer_read_accum_sum": (C.c_int, [_vp, _vp, C.c_size_t, c_u32_p]),
+    "lp_renderer_write_accum_sum": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32]),
     "lp_renderer_read_first_hit": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t]),
     "lp_renderer_ray_counters": (C.c_int, [_vp, C.POINTER(RayCounters), C.c_int]),
     "lp_renderer_accum_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t), c_u32_p]),

@@ -503,6 +503,20 @@ class Renderer:
         _check(_ffi.lib().lp_renderer_set_config(self._h, C.byref(cfg)))
         return cfg
 
+    def read_accum_sum(self):
+        """Checkpoint: (raw RGBA32F SUM accumulator (h, w, 4), samples in it)."""
+        w, h = self.get_size()
+        out = np.empty((h, w, 4), dtype=np.float32)
+        n = C.c_uint32()
+        _check(_ffi.lib().lp_renderer_read_accum_sum(self._h, out.ctypes.data, out.size,
+                                                     C.byref(n)))
+        return out, n.value
+
+    def write_accum_sum(self, accum: np.ndarray, samples: int) -> None:
+        """Resume: restores a checkpointed SUM accumulator; the next raytrace adds to it."""
+        a = np.ascontiguousarray(accum, dtype=np.float32)
+        _check(_ffi.lib().lp_renderer_write_accum_sum(self._h, a.ctypes.data, a.size, samples))
+
     def read_accum_f32(self) -> np.ndarray:
         w, h = self.get_size()
         out = np.empty((h, w, 4), dtype=np.float32)

@@ -873,6 +873,11 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
   if (svgf) r->svgf_back = !r->svgf_back;  // asvgf.start() [ref renderer.rs:466-467, asvgf.rs:236]
   const int cur = r->svgf_back ? 1 : 0;
   P.write_gbuffer = svgf ? 1 : 0;
+  if (r->use_noise && r->noise.ptr && r->noise_w && r->noise_h) {
+    P.noise = r->noise.ptr;
+    P.noise_w = r->noise_w;
+    P.noise_h = r->noise_h;
+  }
   P.gbuffer = r->pp[cur].gbuffer.ptr;
   P.motion = r->motion.ptr;
 
@@ -1111,6 +1116,35 @@ LP_API lp_status lp_renderer_read_accum_f32(lp_renderer *r, float *out, size_t c
   CUDA_CHECK(cudaMemcpyAsync(out, r->scratch.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost,
                              r->dev->stream));
   CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  return LP_OK;
+}
+
+// Checkpoint / resume of a long accumulation ("resumable accumulators"): the
+// raw FP32 SUM target (alpha = sample count) and the number of samples in it.
+LP_API lp_status lp_renderer_read_accum_sum(lp_renderer *r, float *out, size_t cap_floats,
+                                            uint32_t *samples) {
+  if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  const size_t n = (size_t)r->width * r->height;
+  if (cap_floats < n * 4) return fail(LP_ERR_READBACK, "output buffer too small");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  CUDA_CHECK(cudaMemcpyAsync(out, r->accum.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost,
+                             r->dev->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  if (samples) *samples = r->samples_accumulated;
+  return LP_OK;
+}
+
+LP_API lp_status lp_renderer_write_accum_sum(lp_renderer *r, const float *in, size_t count_floats,
+                                             uint32_t samples) {
+  if (!r || !in) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  const size_t n = (size_t)r->width * r->height;
+  if (count_floats != n * 4) return fail(LP_ERR_INVALID_ARG, "accumulator size mismatch");
+  CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
+  CUDA_CHECK(cudaMemcpyAsync(r->accum.ptr, in, n * sizeof(float4), cudaMemcpyHostToDevice,
+                             r->dev->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
+  r->samples_accumulated = samples;
+  r->accumulate = samples > 0;  // the next raytrace adds to the restored sum
   return LP_OK;
 }
 

@@ -86,12 +86,24 @@ struct Counters {
 // traversal kernels sit at 65-78 % of the L1 wavefront rate), so fetching a 64-byte node
 // with two 256-bit loads instead of four 128-bit ones halves the L1 work of a node visit.
 // `p` must be 32-byte aligned.
+//
+// L2 policy (sm_100 lets a 256-bit load carry an L2 eviction priority): a wave streams ~12 GB
+// of path state through the L2 beside a BVH working set of ~85 MB (fp16 nodes + triangles) on a
+// 126 MB L2 that is two 63 MB partitions, and ncu showed 67 % L2 hits / 4.3 GB of DRAM reads in
+// the bounce-1 kernel (profiles/r01_v4_ncu_full_summary.csv).  Nodes and triangles are
+// therefore loaded evict-LAST, the path-state stream evict-FIRST (LP_L2_KEEP / LP_L2_STREAM;
+// A/B in profiles/r01_ab.txt).
+#if defined(LP_L2_KEEP)
+#define LP_L2_KEEP_Q ".L2::evict_last"
+#else
+#define LP_L2_KEEP_Q ""
+#endif
 struct f8 {
   float4 lo, hi;
 };
 __device__ __forceinline__ f8 ldg256(const void *p) {
   f8 r;
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.nc" LP_L2_KEEP_Q ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x),
                  "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
                : "l"(p));
@@ -99,7 +111,7 @@ __device__ __forceinline__ f8 ldg256(const void *p) {
 }
 // Cache policies.  The ray-pool kernels leave ~30 KB of L1 per SM next to their
 // shared-memory pools (ncu: 8 % L1 hit rate).  Measured one at a time on config 3
-// (profiles/r01_v3_ab.txt): triangles without L1 allocation in the pool kernels +1 % (ON);
+// (profiles/r01_ab.txt): triangles without L1 allocation in the pool kernels +1 % (ON);
 // instance records evict-last +-0 (off, -DLP_HINT_KEEP); ray state evict-first -3.5 % (off,
 // -DLP_HINT_STREAM: the world ray is re-read when a ray leaves an instance); triangles
 // without allocation in the coherent primary kernel: slower (its 65 % L1 hit rate is reuse
@@ -109,7 +121,7 @@ __device__ __forceinline__ f8 ldg256_na(const void *p) {
   return ldg256(p);
 #else
   f8 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.nc.L1::no_allocate" LP_L2_KEEP_Q ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x),
                  "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
                : "l"(p));
@@ -128,30 +140,54 @@ __device__ __forceinline__ float4 ldg_keep(const float4 *p) {
   return r;
 #endif
 }
-// streamed path state: read once / written once per kernel (evict-first)
+// streamed path state: read once / written once per kernel.  LP_L2_STREAM: evict-first in
+// L2 only (the L1 behaviour stays normal: the world ray is re-read from L1 when a ray leaves
+// an instance, which is why the L1+L2 evict-first of LP_HINT_STREAM measured -3.5 %).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ float4 ld_stream(const float4 *p) {
-#ifndef LP_HINT_STREAM
+#if defined(LP_L2_STREAM)
+  float4 r;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(l2_evict_first_policy()));
+  return r;
+#elif !defined(LP_HINT_STREAM)
   return *p;
 #else
   return __ldcs(p);
 #endif
 }
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
-#ifndef LP_HINT_STREAM
+#if defined(LP_L2_STREAM)
+  uint32_t r;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_evict_first_policy()));
+  return r;
+#elif !defined(LP_HINT_STREAM)
   return *p;
 #else
   return __ldcs(p);
 #endif
 }
 __device__ __forceinline__ void st_stream(float4 *p, float4 v) {
-#ifndef LP_HINT_STREAM
+#if defined(LP_L2_STREAM)
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(l2_evict_first_policy())
+               : "memory");
+#elif !defined(LP_HINT_STREAM)
   *p = v;
 #else
   __stcs(p, v);
 #endif
 }
 __device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v) {
-#ifndef LP_HINT_STREAM
+#if defined(LP_L2_STREAM)
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_evict_first_policy())
+               : "memory");
+#elif !defined(LP_HINT_STREAM)
   *p = v;
 #else
   __stcs(p, v);

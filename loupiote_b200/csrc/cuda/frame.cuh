@@ -36,6 +36,10 @@ struct FrameParams {
   float prev_w2s[16];
   int write_gbuffer;
   int overwrite_accum;
+  // blue-noise texture (RGBA8) when RadianceParameters.use_noise_texture is set
+  // [ref renderer.rs:620-673]; nullptr = plain hash sampling
+  const uchar4 *noise;
+  uint32_t noise_w, noise_h;
 };
 
 // slot-local index <-> pixel through 8x4 tiles (one warp = one tile: coherent primary rays)
@@ -61,6 +65,30 @@ __device__ __forceinline__ uint32_t warp_push(bool pred, uint32_t *counter) {
   if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
   base = __shfl_sync(0xFFFFFFFFu, base, leader);
   return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+// The four sample numbers of hash block `block` of one path vertex.  With a noise texture
+// bound they are dithered [ref renderer.rs:620-673]: number c = (texel.c + hash.c) / 256 with
+// texel = the RGBA8 noise texture at the pixel, shifted toroidally by an offset that depends
+// on (sample, block) only, so neighbouring pixels keep the texture's blue-noise decorrelation
+// while every number stays uniform in [0, 1) for a texture with a flat histogram.
+__device__ __forceinline__ float4 sample_block(const FrameParams &P, uint32_t pixel, uint32_t sample,
+                                               uint32_t block) {
+  const uint4 r = rng4(pixel, sample, block, P.seed);
+  float4 u = make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+  if (P.noise) {
+    const uint4 s = rng4(0x9E3779B9u, sample, block, P.seed);
+    const uint32_t px = pixel % P.cam.width, py = pixel / P.cam.width;
+    const uint32_t tx = (px % P.noise_w + s.x % P.noise_w) % P.noise_w;
+    const uint32_t ty = (py % P.noise_h + s.y % P.noise_h) % P.noise_h;
+    const uchar4 t = __ldg(P.noise + (size_t)ty * P.noise_w + tx);
+    const float k = 1.0f / 256.0f, top = 0.99999994f;
+    u.x = fminf(__fmul_rn(__fadd_rn((float)t.x, u.x), k), top);
+    u.y = fminf(__fmul_rn(__fadd_rn((float)t.y, u.y), k), top);
+    u.z = fminf(__fmul_rn(__fadd_rn((float)t.z, u.z), k), top);
+    u.w = fminf(__fmul_rn(__fadd_rn((float)t.w, u.w), k), top);
+  }
+  return u;
 }
 
 // Camera ray of path slot `slot` (RayPass).  Every operation is an explicitly rounded

@@ -17,6 +17,8 @@
 //    instructions, the others need a thousand; the first version ran the long branch with 11
 //    of 32 lanes.  Now a warp settles its misses at once and parks the hit slots in a
 //    shared-memory list, and runs the long branch only on full groups of 32.
+#include <cstdlib>
+
 #include "frame.cuh"
 
 namespace lp {
@@ -124,8 +126,8 @@ __device__ __forceinline__ void shade_hit(const FrameParams &P, uint32_t bounce,
   L.y += T.y * sf.emission.y;
   L.z += T.z * sf.emission.z;
 
-  const uint4 r0 = rng4(in.pixel, in.sample, 2u * bounce + 1u, P.seed);
-  const uint4 r1 = rng4(in.pixel, in.sample, 2u * bounce + 2u, P.seed);
+  const float4 r0 = sample_block(P, in.pixel, in.sample, 2u * bounce + 1u);
+  const float4 r1 = sample_block(P, in.pixel, in.sample, 2u * bounce + 2u);
   const f3 wo = -d;
   const BsdfCtx cx = bsdf_ctx(sf, wo);
   const float eps = 1e-4f * fmaxf(1.0f, fmaxf(fabsf(sf.p.x), fmaxf(fabsf(sf.p.y), fabsf(sf.p.z))));
@@ -133,11 +135,11 @@ __device__ __forceinline__ void shade_hit(const FrameParams &P, uint32_t bounce,
   out.next_o = po;
 
   if (sc.n_active_lights) {
-    uint32_t pick = (uint32_t)(u01(r0.x) * (float)sc.n_active_lights);
+    uint32_t pick = (uint32_t)(r0.x * (float)sc.n_active_lights);
     if (pick >= sc.n_active_lights) pick = sc.n_active_lights - 1u;
     const float4 *lp = sc.lights + 4u * (size_t)sc.active_lights[pick];
     const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2), l3 = __ldg(lp + 3);
-    const float a1 = 2.0f * u01(r0.y) - 1.0f, a2 = 2.0f * u01(r0.z) - 1.0f;
+    const float a1 = 2.0f * r0.y - 1.0f, a2 = 2.0f * r0.z - 1.0f;
     f3 wi = mk3(l0.x + a1 * l1.x + a2 * l2.x - po.x, l0.y + a1 * l1.y + a2 * l2.y - po.y,
                 l0.z + a1 * l1.z + a2 * l2.z - po.z);
     const float dist2 = dot(wi, wi);
@@ -168,9 +170,9 @@ __device__ __forceinline__ void shade_hit(const FrameParams &P, uint32_t bounce,
     f3 wi, Le;
     float pdf_e;
     if (sc.probe) {
-      probe_sample(sc, u01(r0.w), u01(r1.x), wi, Le, pdf_e);
+      probe_sample(sc, r0.w, r1.x, wi, Le, pdf_e);
     } else {
-      wi = cosine_sample(sf.ns, u01(r0.w), u01(r1.x));
+      wi = cosine_sample(sf.ns, r0.w, r1.x);
       pdf_e = dot(sf.ns, wi) * LP_INV_PI;
       Le = mk3(sc.env_color[0], sc.env_color[1], sc.env_color[2]);
     }
@@ -190,7 +192,7 @@ __device__ __forceinline__ void shade_hit(const FrameParams &P, uint32_t bounce,
   }
   if (bounce + 1u < P.max_bounces) {
     f3 wi;
-    if (bsdf_sample(sf, cx, wo, u01(r1.y), u01(r1.z), u01(r1.w), wi)) {
+    if (bsdf_sample(sf, cx, wo, r1.y, r1.z, r1.w, wi)) {
       f3 f;
       float pdf;
       bsdf_eval(sf, cx, wo, wi, f, pdf);
@@ -381,6 +383,11 @@ int shade_grid(K kernel, int sm_count) {
             cudaSuccess ||
         per_sm < 1)
       per_sm = 1;
+    // LP_SHADE_BLOCKS (tuning knob): resident shade blocks per SM, below the occupancy limit
+    if (const char *e = std::getenv("LP_SHADE_BLOCKS")) {
+      const int want = std::atoi(e);
+      if (want > 0 && want < per_sm) per_sm = want;
+    }
     grid = per_sm * sm_count;
   }
   return grid;

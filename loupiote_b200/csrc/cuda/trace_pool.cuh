@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
 
   uint32_t chunk = n / (total_warps * 4u);
   // rays a warp reserves per atomic.  Large reservations leave single warps working long
-  // after the queue is empty: 1024 -> 64 rays was worth 4 % of the frame (r01_v3_ab.txt)
+  // after the queue is empty: 1024 -> 64 rays was worth 4 % of the frame (r01_ab.txt)
   chunk = chunk < 32u ? 32u : (chunk > chunk_max ? chunk_max : chunk);
   uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
   bool exhausted = false;

@@ -285,3 +285,18 @@ def textured_scene(with_light: bool = True) -> dict:
     view = look_at_view((0.0, 3.2, 7.5), d / np.linalg.norm(d))
     return {"scene": scene, "view": view, "env_color": (0.0, 0.0, 0.0), "name": "textured",
             "probe": procedural_probe()}
+
+
+def flat_noise_texture(size: int = 64, seed: int = 0xB10E) -> np.ndarray:
+    """(size, size, 4) uint8 dither texture with an exactly flat histogram per channel (every
+    value 0..255 appears size*size/256 times), shuffled by SplitMix64.  Stands in for the
+    reference's assets/noise_rgb.png (standalone/src/lib.rs:102), which is not in the tree."""
+    n = size * size
+    assert n % 256 == 0
+    out = np.zeros((size, size, 4), dtype=np.uint8)
+    rng = SplitMix64(seed)
+    for c in range(4):
+        vals = np.repeat(np.arange(256, dtype=np.uint8), n // 256)
+        keys = np.array([rng.next_u64() for _ in range(n)], dtype=np.uint64)
+        out[..., c] = vals[np.argsort(keys, kind="stable")].reshape(size, size)
+    return out

@@ -930,6 +930,25 @@ static void unpack_albedo(uint32_t p, float c[3]) {
   for (int a = 0; a < 3; ++a) c[a] = maxf((float)((p >> (8 * a)) & 0xFFu) * (1.0f / 255.0f), 0.03f);
 }
 
+/* The four sample numbers of hash block `block`; dithered by the blue-noise texture when
+ * one is set (RadianceParameters.use_noise_texture, renderer.rs:620-673): number c =
+ * (texel.c + hash.c) / 256, texel toroidally shifted by a per-(sample, block) offset. */
+static void sample_block(const lpo_scene *s, uint32_t width, uint32_t pixel, uint32_t sample,
+                         uint32_t block, uint32_t seed, float u[4]) {
+  uint32_t r[4];
+  lpo_rng(pixel, sample, block, seed, r);
+  for (int c = 0; c < 4; ++c) u[c] = u01(r[c]);
+  if (s->noise_rgba8 && s->noise_w && s->noise_h) {
+    uint32_t o[4];
+    lpo_rng(0x9E3779B9u, sample, block, seed, o);
+    const uint32_t px = pixel % width, py = pixel / width;
+    const uint32_t tx = (px % s->noise_w + o[0] % s->noise_w) % s->noise_w;
+    const uint32_t ty = (py % s->noise_h + o[1] % s->noise_h) % s->noise_h;
+    const uint8_t *t = s->noise_rgba8 + 4 * ((size_t)ty * s->noise_w + tx);
+    for (int c = 0; c < 4; ++c) u[c] = minf(((float)t[c] + u[c]) * (1.0f / 256.0f), 0.99999994f);
+  }
+}
+
 /* One path: renderer.rs:440-510 restated per pixel. Returns radiance in L. */
 static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render_config *cfg,
                        uint32_t pixel, uint32_t sample, float L[3], lpo_render_stats *st,
@@ -963,9 +982,9 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
     lpo_stats *ks = &st->kind[b == 0 ? 0 : 1];
     lpo_closest_hit_bvh(s, o, d, 0.0f, INFINITY, &hit, ks);
     if (b == 0) st->primary++; else st->bounce++;
-    uint32_t r0[4], r1[4];
-    lpo_rng(pixel, sample, 2u * b + 1u, cfg->seed, r0);
-    lpo_rng(pixel, sample, 2u * b + 2u, cfg->seed, r1);
+    float r0[4], r1[4];
+    sample_block(s, cam->width, pixel, sample, 2u * b + 1u, cfg->seed, r0);
+    sample_block(s, cam->width, pixel, sample, 2u * b + 2u, cfg->seed, r1);
 
     if (hit.instance == LP_INVALID_INDEX) {
       if (env_on) {
@@ -1036,7 +1055,7 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
 
     /* ---- next-event estimation: one quad light */
     if (n_active > 0) {
-      uint32_t pick = (uint32_t)(u01(r0[0]) * (float)n_active);
+      uint32_t pick = (uint32_t)(r0[0] * (float)n_active);
       if (pick >= n_active) pick = n_active - 1;
       const lp_light *Lt = NULL;
       for (size_t k = 0; k < s->n_lights; ++k)
@@ -1047,7 +1066,7 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
           }
           pick--;
         }
-      const float a1 = 2.0f * u01(r0[1]) - 1.0f, a2 = 2.0f * u01(r0[2]) - 1.0f;
+      const float a1 = 2.0f * r0[1] - 1.0f, a2 = 2.0f * r0[2] - 1.0f;
       float wi[3], n[3];
       for (int a = 0; a < 3; ++a)
         wi[a] = Lt->center[a] + a1 * Lt->tangent[a] + a2 * Lt->bitangent[a] - po[a];
@@ -1078,9 +1097,9 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
     if (env_on) {
       float wi[3], Le[3], pdf_e;
       if (s->probe_rgbe8) {
-        lpo_probe_sample(s, u01(r0[3]), u01(r1[0]), wi, Le, &pdf_e);
+        lpo_probe_sample(s, r0[3], r1[0], wi, Le, &pdf_e);
       } else {
-        cosine_sample(sf.ns, u01(r0[3]), u01(r1[0]), wi);
+        cosine_sample(sf.ns, r0[3], r1[0], wi);
         pdf_e = dot3(sf.ns, wi) * LPO_INV_PI;
         for (int a = 0; a < 3; ++a) Le[a] = s->env_color[a];
       }
@@ -1103,7 +1122,7 @@ static void trace_path(const lpo_scene *s, const lp_camera *cam, const lp_render
 
     /* ---- BSDF importance sampling -> next ray */
     float wi[3];
-    if (!bsdf_sample(&sf, wo, u01(r1[1]), u01(r1[2]), u01(r1[3]), wi)) break;
+    if (!bsdf_sample(&sf, wo, r1[1], r1[2], r1[3], wi)) break;
     float f[3], pdf;
     bsdf_eval(&sf, wo, wi, f, &pdf);
     if (!(pdf > 0.0f)) break;

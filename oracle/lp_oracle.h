@@ -60,6 +60,10 @@ typedef struct lpo_scene {
   const uint8_t *const *images;
   const uint32_t *image_w, *image_h;
   size_t n_images;
+  /* blue-noise texture (RGBA8) of Renderer::upload_noise_texture when use_noise_texture is
+   * set [ref renderer.rs:620-673]; NULL = plain hash sampling */
+  const uint8_t *noise_rgba8;
+  uint32_t noise_w, noise_h;
 } lpo_scene;
 
 typedef struct lpo_hit {

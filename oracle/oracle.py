@@ -55,7 +55,8 @@ class LpoScene(C.Structure):
                 ("probe_w", C.c_uint32), ("probe_h", C.c_uint32),
                 ("probe_pmf", C.c_void_p), ("probe_cdf_row", C.c_void_p),
                 ("probe_cdf_col", C.c_void_p), ("images", C.c_void_p), ("image_w", C.c_void_p),
-                ("image_h", C.c_void_p), ("n_images", C.c_size_t)]
+                ("image_h", C.c_void_p), ("n_images", C.c_size_t), ("noise_rgba8", C.c_void_p),
+                ("noise_w", C.c_uint32), ("noise_h", C.c_uint32)]
 
 
 class LpoHit(C.Structure):
@@ -104,7 +105,7 @@ class OracleScene:
     """Borrowed numpy views of a loupiote_b200.Scene's public arrays (the same data the
     reference hands to its passes as BLASArray buffers)."""
 
-    def __init__(self, scene, env_color=(0.0, 0.0, 0.0), probe=None):
+    def __init__(self, scene, env_color=(0.0, 0.0, 0.0), probe=None, noise=None):
         from loupiote_b200 import _ffi  # POD array accessors only
         self._keep = {}
         names = {"entries": _ffi.SCENE_ENTRIES, "nodes": _ffi.SCENE_NODES,
@@ -132,6 +133,10 @@ class OracleScene:
             self._keep.update(probe_pmf=pmf, probe_cdf_row=cdf_row, probe_cdf_col=cdf_col)
             s.probe_pmf, s.probe_cdf_row = pmf.ctypes.data, cdf_row.ctypes.data
             s.probe_cdf_col = cdf_col.ctypes.data
+        if noise is not None:  # (h, w, 4) uint8 blue-noise texture, use_noise_texture on
+            self._keep["noise"] = np.ascontiguousarray(noise, dtype=np.uint8)
+            s.noise_rgba8 = self._keep["noise"].ctypes.data
+            s.noise_h, s.noise_w = self._keep["noise"].shape[:2]
         # scene.images: the oracle samples the images themselves, not the product's atlas
         imgs = [np.ascontiguousarray(scene.image(i)) for i in range(scene.image_count)]
         if imgs:

@@ -223,3 +223,23 @@ def test_textured_scene_oracle_golden_and_albedo():
     # the G-buffer albedo of the textured ground is the checker, not the flat factor
     ground = gb[30:, :, 3]
     assert len(np.unique(ground)) > 8
+
+
+def test_noise_texture_sampling_is_unbiased_and_used():
+    """RadianceParameters.use_noise_texture (renderer.rs:666-673): with a flat-histogram
+    texture every dithered number is still uniform, so the converged image does not move;
+    a degenerate texture (all zeros) does bias it, which shows the texture is really used."""
+    c = scenes.cornell_box()
+    cam = O.camera_from_view(c["view"], 40, 40, V_FOV)
+    cfg = _ffi.RenderConfig()
+    _ffi.lib().lp_render_config_default(cfg)
+    cfg.max_bounces, cfg.jitter, cfg.seed = 4, 1, 1
+    means = {}
+    for name, noise in (("off", None), ("flat", scenes.flat_noise_texture(64)),
+                        ("zeros", np.zeros((8, 8, 4), np.uint8))):
+        acc, _ = O.render(O.OracleScene(c["scene"], noise=noise), cam, cfg, 128)
+        means[name] = float((acc[..., :3] / acc[..., 3:4]).mean())
+    assert abs(means["flat"] - means["off"]) / means["off"] < 0.02, means
+    assert abs(means["zeros"] - means["off"]) / means["off"] > 0.05, means
+    t = scenes.flat_noise_texture(64)
+    assert all((np.bincount(t[..., ch].ravel(), minlength=256) == 16).all() for ch in range(4))

@@ -237,9 +237,34 @@ def test_accumulator_address_survives_config_changes(device):
     r, sg = make_renderer(device, c["scene"], (64, 48), max_bounces=2, spp_per_call=1)
     p0, n0, _ = r.accum_device_ptr()
     r.set_config(max_bounces=4, spp_per_call=8)
+    r.accumulate = True
     r.raytrace(c["view"])
     p1, n1, s1 = r.accum_device_ptr()
     assert (p0, n0) == (p1, n1) and n1 == 64 * 48 * 4 and s1 == 8
     r.resize(sg, None, (128, 96))
     _, n2, _ = r.accum_device_ptr()
     assert n2 == 128 * 96 * 4
+
+
+def test_checkpoint_resume_of_the_accumulator(device):
+    """read_accum_sum / write_accum_sum: 4 spp, checkpoint, a NEW renderer restores it and
+    traces samples 4..7 == 8 spp in one go (same sample set, FP32 summation order aside)."""
+    c = scenes.cornell_box()
+    size = (96, 64)
+    full, _ = make_renderer(device, c["scene"], size, max_bounces=4, spp_per_call=8, seed=5)
+    full.raytrace(c["view"])
+    ref = full.read_accum_f32()
+    a, sg = make_renderer(device, c["scene"], size, max_bounces=4, spp_per_call=4, seed=5)
+    a.accumulate = True  # frame_count advances only while accumulating [ref renderer.rs:535-537]
+    a.raytrace(c["view"])
+    ckpt, n = a.read_accum_sum()
+    assert n == 4 and np.all(ckpt[..., 3] == 4.0)
+    b, _ = make_renderer(device, c["scene"], size, max_bounces=4, spp_per_call=4, seed=5,
+                         sample_offset=4)
+    b.write_accum_sum(ckpt, n)
+    b.raytrace(c["view"])
+    out = b.read_accum_f32()
+    assert b.accum_device_ptr()[2] == 8
+    assert np.allclose(out, ref, rtol=1e-5, atol=1e-6)
+    with pytest.raises(lb.Error):
+        b.write_accum_sum(ckpt[:10], 4)

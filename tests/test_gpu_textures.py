@@ -120,3 +120,32 @@ def test_gltf_embedded_textures_render_like_oracle(device):
     assert d.max() <= 1
     hit = ogb[..., 2] < 0xFFFF0000
     assert hit.mean() > 0.15 and len(np.unique(gb[..., 3][hit])) > 200
+
+
+def test_noise_texture_dithering_matches_oracle(device):
+    """upload_noise_texture + use_noise_texture(true) [ref renderer.rs:620-673]: the same
+    dithered sample numbers on both sides (the dither is exact arithmetic), padded rows."""
+    c = scenes.cornell_box()
+    noise = scenes.flat_noise_texture(64)
+    w, h = 128, 96
+    sg = lb.SceneGPU.new_from_scene(c["scene"], device)
+    r = lb.Renderer(device, (w, h), downsample_factor=1.0)
+    r.set_resources(sg, None)
+    r.set_config(max_bounces=4, spp_per_call=8, jitter=1, seed=3, env_color=c["env_color"])
+    padded = np.zeros((64, 80, 4), np.uint8)  # bytes_per_row > width * 4
+    padded[:, :64] = noise
+    r.upload_noise_texture(padded, 64, 64, 80 * 4)
+    osc_on = O.OracleScene(c["scene"], env_color=c["env_color"], noise=noise)
+    osc_off = O.OracleScene(c["scene"], env_color=c["env_color"])
+    cam = O.camera_from_view(c["view"], w, h, V_FOV)
+    images = {}
+    for flag, osc in ((True, osc_on), (False, osc_off)):
+        r.use_noise_texture(flag)
+        r.set_config(seed=3)  # restart the sample sequence
+        r.reset_accumulation()
+        r.raytrace(c["view"])
+        gpu = r.read_accum_f32()[..., :3]
+        acc, _ = O.render(osc, cam, r.config, 8)
+        assert_radiance(gpu, acc[..., :3] / acc[..., 3:4], 5e-3)
+        images[flag] = gpu
+    assert np.abs(images[True] - images[False]).mean() > 1e-3  # the texture changes the samples
