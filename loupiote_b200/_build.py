@@ -52,7 +52,7 @@ def _nvcc() -> str:
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    files = sorted(list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.cpp"))
+    files = sorted([ROOT / "tools" / "cli" / "lp_render.cpp"] + list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.cpp"))
                    + list(CSRC.rglob("*.hpp")) + [ROOT / "include" / "loupiote.h"])
     for f in files:
         h.update(f.name.encode())
@@ -100,8 +100,26 @@ def build(force: bool = False, verbose: bool = False, variant: str = "",
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
         raise RuntimeError("nvcc failed linking libloupiote_b200.so")
+    if not variant:
+        build_cli(lib_path)
     stamp.write_text(fp)
     return lib_path
+
+
+CLI_SRC = ROOT / "tools" / "cli" / "lp_render.cpp"
+CLI_PATH = LIB_DIR / "lp_render"
+
+
+def build_cli(lib_path: Path = LIB_PATH) -> Path:
+    """Headless renderer over the C ABI only (tools/cli/lp_render.cpp), linked against the
+    in-tree library with an $ORIGIN rpath."""
+    cmd = ["g++", "-O2", "-std=c++17", f"-I{ROOT / 'include'}", str(CLI_SRC), "-o", str(CLI_PATH),
+           f"-L{lib_path.parent}", "-l:" + lib_path.name, "-Wl,-rpath,$ORIGIN"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("g++ failed building lp_render")
+    return CLI_PATH
 
 
 if __name__ == "__main__":

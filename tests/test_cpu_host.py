@@ -291,3 +291,31 @@ def test_procedural_scene_sizes():
     assert (m["reflectivity"][1:] <= 1.0).all()
     view = c["view"]
     assert np.allclose(np.linalg.norm(view[:3, :3], axis=0), 1.0, atol=1e-6)
+
+
+def test_rust_sys_crate_matches_the_header():
+    """bindings/rust/loupiote-b200-sys/src/lib.rs is generated from include/loupiote.h; with
+    no Rust toolchain here, the guard is: committed file == generator output, one `pub fn`
+    per exported symbol, struct sizes implied by the field lists == the ctypes mirror."""
+    import subprocess
+    import sys
+    gen = subprocess.run([sys.executable, str(ROOT / "tools" / "gen_rust_ffi.py")],
+                         capture_output=True, text=True, check=True).stdout
+    committed = (ROOT / "bindings" / "rust" / "loupiote-b200-sys" / "src" / "lib.rs").read_text()
+    assert gen == committed, "run: python tools/gen_rust_ffi.py > bindings/rust/loupiote-b200-sys/src/lib.rs"
+    fns = set(re.findall(r"pub fn (lp_\w+)\(", committed))
+    assert fns == set(_ffi.EXPORTED_SYMBOLS)
+    sizes = {"f32": 4, "u32": 4, "u64": 8}
+    for name, ct in (("lp_vertex", _ffi.Vertex), ("lp_material", _ffi.Material),
+                     ("lp_light", _ffi.Light), ("lp_instance", _ffi.Instance),
+                     ("lp_render_config", _ffi.RenderConfig), ("lp_ray_counters", _ffi.RayCounters),
+                     ("lp_camera", _ffi.Camera), ("lp_blas_entry", _ffi.BlasEntry)):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, committed, flags=re.S).group(1)
+        total = 0
+        for ty in re.findall(r"pub \w+: ([^,]+),", body):
+            m = re.match(r"\[(\w+); (\d+)\]", ty)
+            total += sizes[m.group(1)] * int(m.group(2)) if m else sizes[ty]
+        assert total == C.sizeof(ct), name
+    # the wrapper crate only calls functions the sys crate declares
+    wrapper = (ROOT / "bindings" / "rust" / "loupiote-core-b200" / "src" / "lib.rs").read_text()
+    assert set(re.findall(r"ffi::(lp_\w+)\(", wrapper)) <= fns
