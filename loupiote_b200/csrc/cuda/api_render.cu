@@ -981,17 +981,23 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
     T.out_hist = r->pp[cur].history.ptr;
     { KtScope k(r, 3); launch_svgf_temporal(T, sm, st); }
     if (r->mode == LP_BLIT_DENOISED_PATHRACE) {
-      // a-trous ping-pong between `temp` and the main target [ref asvgf.rs:277-290]
+      // a-trous ping-pong between `temp` and the main target [ref asvgf.rs:277-290], phased
+      // so that the LAST iteration lands in the main target: it does the composite too
       const float4 *src = r->pp[cur].radiance.ptr;
-      for (uint32_t it = 0; it < cfg.atrous_iterations; ++it) {
-        float4 *dst = (it & 1u) ? r->accum.ptr : r->temp.ptr;
+      const uint32_t iters = cfg.atrous_iterations;
+      for (uint32_t it = 0; it < iters; ++it) {
+        const bool last = it + 1 == iters;
+        float4 *dst = ((iters - 1u - it) & 1u) ? r->temp.ptr : r->accum.ptr;
         {
           KtScope k(r, 3);
-          launch_svgf_atrous(r->width, r->height, src, r->pp[cur].gbuffer.ptr, it, dst, sm, st);
+          launch_svgf_atrous(r->width, r->height, src, r->pp[cur].gbuffer.ptr, it, dst, last, sm, st);
         }
         src = dst;
       }
-      { KtScope k(r, 3); launch_svgf_composite(n, src, r->pp[cur].gbuffer.ptr, r->accum.ptr, sm, st); }
+      if (iters == 0) {
+        KtScope k(r, 3);
+        launch_svgf_composite(n, src, r->pp[cur].gbuffer.ptr, r->accum.ptr, sm, st);
+      }
     }
     query_end(r);
   }

@@ -27,9 +27,11 @@ struct SvgfTemporalParams {
 };
 
 // launch_svgf_temporal: svgf_temporal.cuh (uncontracted translation unit)
-// One a-trous iteration (5x5 taps at stride 2^iteration) from `in` to `out`.
+// One a-trous iteration (5x5 taps at stride 2^iteration) from `in` to `out`; `composite`
+// folds the CompositingPass into it (last iteration: out = filtered x albedo, alpha 1).
 void launch_svgf_atrous(uint32_t w, uint32_t h, const float4 *in, const uint4 *gbuffer,
-                        uint32_t iteration, float4 *out, int sm_count, cudaStream_t stream);
+                        uint32_t iteration, float4 *out, bool composite, int sm_count,
+                        cudaStream_t stream);
 void launch_svgf_composite(uint32_t n, const float4 *filtered, const uint4 *gbuffer, float4 *out,
                            int sm_count, cudaStream_t stream);
 

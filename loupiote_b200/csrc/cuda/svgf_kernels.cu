@@ -47,7 +47,9 @@ __device__ __forceinline__ constexpr float tap_inv_len(int d2) {
 
 // One a-trous iteration, 5x5 B3-spline taps at stride 2^iteration, edge-stopped by mesh id,
 // normal (power 128), relative depth and variance-guided luminance.  in.a / out.a = variance.
-// Block = 32x8 pixel tile.
+// Block = 32x8 pixel tile.  COMPOSITE: the last iteration also does the CompositingPass
+// (x first-hit albedo, alpha = 1) and writes the main target, which saves one 48 B/px pass.
+template <bool COMPOSITE>
 __global__ void __launch_bounds__(256)
     svgf_atrous_kernel(int w, int h, const float4 *__restrict__ in,
                        const uint4 *__restrict__ gbuffer, int step, float4 *__restrict__ out) {
@@ -57,7 +59,12 @@ __global__ void __launch_bounds__(256)
   const uint4 g = __ldg(gbuffer + i);
   const float4 c = __ldg(in + i);
   if (g.z == LP_INVALID_INDEX) {
-    out[i] = c;
+    if (COMPOSITE) {
+      const f3 albedo = unpack_albedo(g.w);
+      out[i] = make_float4(c.x * albedo.x, c.y * albedo.y, c.z * albedo.z, 1.0f);
+    } else {
+      out[i] = c;
+    }
     return;
   }
   const f3 nrm = unpack_normal_fast(g.x);
@@ -99,7 +106,12 @@ __global__ void __launch_bounds__(256)
     }
   }
   const float inv = frcp(sum_w);
-  out[i] = make_float4(sx * inv, sy * inv, sz * inv, sum_v * inv * inv);
+  if (COMPOSITE) {
+    const f3 albedo = unpack_albedo(g.w);
+    out[i] = make_float4(sx * inv * albedo.x, sy * inv * albedo.y, sz * inv * albedo.z, 1.0f);
+  } else {
+    out[i] = make_float4(sx * inv, sy * inv, sz * inv, sum_v * inv * inv);
+  }
 }
 
 // CompositingPass: filtered illumination x first-hit albedo into the main target (alpha = 1
@@ -119,10 +131,14 @@ __global__ void __launch_bounds__(256)
 }  // namespace
 
 void launch_svgf_atrous(uint32_t w, uint32_t h, const float4 *in, const uint4 *gbuffer,
-                        uint32_t iteration, float4 *out, int sm_count, cudaStream_t stream) {
+                        uint32_t iteration, float4 *out, bool composite, int sm_count,
+                        cudaStream_t stream) {
   (void)sm_count;
   const dim3 grid((w + 31) / 32, (h + 7) / 8);
-  svgf_atrous_kernel<<<grid, 256, 0, stream>>>((int)w, (int)h, in, gbuffer, 1 << iteration, out);
+  if (composite)
+    svgf_atrous_kernel<true><<<grid, 256, 0, stream>>>((int)w, (int)h, in, gbuffer, 1 << iteration, out);
+  else
+    svgf_atrous_kernel<false><<<grid, 256, 0, stream>>>((int)w, (int)h, in, gbuffer, 1 << iteration, out);
 }
 
 void launch_svgf_composite(uint32_t n, const float4 *filtered, const uint4 *gbuffer, float4 *out,

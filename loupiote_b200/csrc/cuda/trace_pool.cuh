@@ -323,6 +323,8 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
         S.state[s] =
             ((next & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode) | flags;
       } else {
+        // (deferring this pop to the next leaf phase, where all lanes pop together, measured
+        // -4.5 %: the ray waits a scheduling round for nothing; profiles/r01_ab.txt run r01i)
         pop(s, stk, spb, flags, e.y, a.w);
       }
     } else if (phase == kStEntry) {
@@ -345,7 +347,11 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       S.e[s].x = spb;
       S.state[s] = ((root & kLeaf) ? kStTri : kStNode) | kFlagInBlas;
     } else {
-      // -------------------------------------------------------------- one triangle
+      // -------------------------------------------------------------- the triangles of a leaf
+      // A lane tests ALL triangles of its leaf (1..4) before the warp re-schedules, so every lane
+      // of the phase ends in the stack pop together: +2.7 % on config 3 over one triangle per
+      // iteration (-DLP_POOL_ONE_TRI, where the pop ran for the ~4 lanes whose leaf just ended
+      // and was 11 % of the kernel's instructions; profiles/r01_ab.txt run r01h).
       const float4 a = S.a[s], c = S.c[s];
       LaneRay r;
       r.o = mk3(a.x, a.y, a.z);
@@ -356,12 +362,47 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       const uint32_t inst = __float_as_uint(c.w) >> 6;
       float tbest = a.w;
       const uint32_t cur = __float_as_uint(S.b[s].w);
-      const uint32_t first = cur & 0x0FFFFFFFu;
-      const uint32_t left = (cur >> 28) & 7u;
+      uint32_t first = cur & 0x0FFFFFFFu;
+      uint32_t left = (cur >> 28) & 7u;
+      bool occluded = false;
+#ifndef LP_POOL_ONE_TRI
+      float4 hd = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool improved = false;
+      if (!ANY) hd = S.d[s];
+      for (;;) {
+        float4 p0, p1, p2;
+        load_tri<true>(sc, first, p0, p1, p2);
+        float t, u, v;
+        if (lane_tri(r, p0, p1, p2, tbest, t, u, v)) {
+          if (ANY) {
+            occluded = true;
+            break;
+          }
+          const uint32_t prim = __float_as_uint(p0.w);
+          Hit best;
+          best.t = tbest;
+          best.inst = __float_as_uint(hd.z);
+          best.prim = __float_as_uint(hd.w);
+          if (hit_better(t, inst, prim, best)) {
+            tbest = t;
+            hd = make_float4(u, v, __uint_as_float(inst), __uint_as_float(prim));
+            improved = true;
+          }
+        }
+        if (!left) break;
+        --left;
+        ++first;
+      }
+      if (!ANY && improved) {
+        S.a[s].w = tbest;
+        S.d[s] = hd;
+      }
+      if (ANY && occluded) finish(s, e.y, true, tbest);
+      else pop(s, stk, e.x, flags, e.y, tbest);
+#else
       float4 p0, p1, p2;
       load_tri<true>(sc, first, p0, p1, p2);
       float t, u, v;
-      bool occluded = false;
       if (lane_tri(r, p0, p1, p2, tbest, t, u, v)) {
         if (ANY) {
           occluded = true;
@@ -386,6 +427,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       } else {
         pop(s, stk, e.x, flags, e.y, tbest);
       }
+#endif
     }
   }
 }
