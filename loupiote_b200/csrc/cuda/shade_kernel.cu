@@ -226,11 +226,20 @@ constexpr int kShadeWarps = 4;
 #define LP_SHADE_MIN_BLOCKS 6  // tuning knob: resident blocks per SM the register budget targets
 #endif
 
+// queue entries a warp settles per round at bounce >= 1, in chunks of 32: the loads of all
+// chunks are issued before the first use (the round is a chain of three dependent gathers --
+// queue -> hit_inst -> throughput / radiance -- at 37 % occupancy; ncu: 55 % of the kernel's
+// stall samples sat on them with one chunk per round)
+#ifndef LP_SHADE_SETTLE
+#define LP_SHADE_SETTLE 2
+#endif
+constexpr int kSettle = LP_SHADE_SETTLE;
+
 template <bool PRIMARY>
 __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
     shade_kernel(const __grid_constant__ FrameParams P, uint32_t bounce) {
-  // slots parked for the long branch (bounce >= 1): < 32 pending + <= 32 new per iteration
-  __shared__ uint32_t parked[PRIMARY ? 1 : kShadeWarps][PRIMARY ? 1 : 64];
+  // slots parked for the long branch (bounce >= 1): < 32 pending + <= 32 * kSettle new per round
+  __shared__ uint32_t parked[PRIMARY ? 1 : kShadeWarps][PRIMARY ? 1 : 32 * (kSettle + 1)];
   const uint32_t n = PRIMARY ? P.n_slots : P.counts[kCntNext + bounce - 1];
   const uint32_t *queue = PRIMARY ? nullptr : P.queue[(bounce - 1) & 1u];
   uint32_t *queue_out = P.queue[bounce & 1u];
@@ -241,87 +250,10 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
   const SceneDev &sc = P.sc;
   uint32_t *park = parked[PRIMARY ? 0 : (threadIdx.x >> 5)];
   uint32_t n_parked = 0;  // warp-uniform
+  constexpr uint32_t kRound = PRIMARY ? 32u : 32u * (uint32_t)kSettle;
 
-  for (uint32_t base = warp * 32u;; base += n_warps * 32u) {
-    const bool more = base < n;  // warp-uniform
-    PathIn in;
-    Hit hit;
-    hit.inst = LP_INVALID_INDEX;
-    bool run_hit = false;  // this lane takes the long branch in this iteration
-
-    if (PRIMARY) {
-      if (!more) break;
-      const uint32_t slot = base + lane;
-      bool alive = slot < n;
-      if (alive) alive = primary_ray(P, slot, in.o, in.d, in.pixel, in.sample, in.ls);
-      if (alive) {
-        load_path<true>(P, slot, in, make_float4(0, 0, 0, 0));
-        const float4 h4 = P.ps.hit[slot];
-        hit.t = h4.x;
-        hit.u = h4.y;
-        hit.v = h4.z;
-        hit.prim = __float_as_uint(h4.w);
-        hit.inst = P.ps.hit_inst[slot];
-        run_hit = hit.inst != LP_INVALID_INDEX;
-        if (!run_hit) {
-          shade_miss(P, in);
-          P.ps.rad[slot] = make_float4(in.L.x, in.L.y, in.L.z, 0.0f);
-          if (in.ls == 0) {
-            P.fh_inst[in.pixel] = LP_INVALID_INDEX;
-            P.fh_prim[in.pixel] = hit.prim;
-            P.fh_t[in.pixel] = hit.t;
-            if (P.write_gbuffer) {
-              P.gbuffer[in.pixel] = make_uint4(0u, 0u, LP_INVALID_INDEX, 0xFFFFFFFFu);
-              P.motion[in.pixel] = make_float2(-1.f, -1.f);
-            }
-          }
-        }
-      }
-    } else {
-      // ---- settle the misses of 32 queue entries, park the hits
-      bool is_hit = false;
-      uint32_t slot = 0;
-      if (more && base + lane < n) {
-        slot = queue[base + lane];
-        is_hit = P.ps.hit_inst[slot] != LP_INVALID_INDEX;
-        if (!is_hit) {
-          const float4 t4 = P.ps.thr[slot], r4 = P.ps.rad[slot];
-          in.T = mk3(t4.x, t4.y, t4.z);
-          in.L = mk3(r4.x, r4.y, r4.z);
-          in.pdf_bsdf = t4.w;
-          in.pdf_env_dir = r4.w;
-          in.d = mk3(0.f, 1.f, 0.f);
-          if (sc.probe) {  // only a probe lookup needs the direction
-            const float4 d4 = P.ps.ray_d[slot];
-            in.d = mk3(d4.x, d4.y, d4.z);
-          }
-          shade_miss(P, in);
-          P.ps.rad[slot] = make_float4(in.L.x, in.L.y, in.L.z, 0.0f);
-        }
-      }
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, is_hit);
-      if (is_hit) park[n_parked + __popc(m & lt_mask)] = slot;
-      n_parked += __popc(m);
-      __syncwarp();
-      if (n_parked < 32u && more) continue;
-      if (n_parked == 0u) break;
-      // ---- one full group (or the tail): newest entries first
-      const uint32_t take = n_parked < 32u ? n_parked : 32u;
-      n_parked -= take;
-      run_hit = (uint32_t)lane < take;
-      if (run_hit) {
-        slot = park[n_parked + lane];
-        load_path<false>(P, slot, in, P.ps.ray_d[slot]);
-        const float4 h4 = P.ps.hit[slot];
-        hit.t = h4.x;
-        hit.u = h4.y;
-        hit.v = h4.z;
-        hit.prim = __float_as_uint(h4.w);
-        hit.inst = P.ps.hit_inst[slot];
-      }
-      __syncwarp();
-    }
-
+  // the long branch for one group of <= 32 paths + compaction into the next queues
+  auto shade_group = [&](bool run_hit, PathIn &in, const Hit &hit) {
     ShadeOut out;
     out.cont = out.want_l = out.want_e = false;
     out.next_o = out.next_d = out.T = out.sl_d = out.sl_c = out.se_d = out.se_c = mk3(0, 0, 0);
@@ -348,7 +280,6 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
         }
       }
     }
-
     // ---- converged: compact into the next queues (one atomic per warp and queue)
     const uint32_t qi = warp_push(out.cont, P.counts + kCntNext + bounce);
     if (out.cont) queue_out[qi] = in.slot;
@@ -370,7 +301,110 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
         P.sq_env.contrib[ei] = make_float4(out.se_c.x, out.se_c.y, out.se_c.z, 0.f);
       }
     }
-    if (!PRIMARY && !more && n_parked == 0u) break;
+  };
+
+  for (uint32_t base = warp * kRound;; base += n_warps * kRound) {
+    const bool more = base < n;  // warp-uniform
+    PathIn in;
+    Hit hit;
+    hit.inst = LP_INVALID_INDEX;
+
+    if (PRIMARY) {
+      if (!more) break;
+      bool run_hit = false;
+      const uint32_t slot = base + lane;
+      bool alive = slot < n;
+      if (alive) alive = primary_ray(P, slot, in.o, in.d, in.pixel, in.sample, in.ls);
+      if (alive) {
+        load_path<true>(P, slot, in, make_float4(0, 0, 0, 0));
+        const float4 h4 = P.ps.hit[slot];
+        hit.t = h4.x;
+        hit.u = h4.y;
+        hit.v = h4.z;
+        hit.prim = __float_as_uint(h4.w);
+        hit.inst = P.ps.hit_inst[slot];
+        run_hit = hit.inst != LP_INVALID_INDEX;
+        if (!run_hit) {
+          shade_miss(P, in);
+          P.ps.rad[slot] = make_float4(in.L.x, in.L.y, in.L.z, 0.0f);
+          if (in.ls == 0) {
+            P.fh_inst[in.pixel] = LP_INVALID_INDEX;
+            P.fh_prim[in.pixel] = hit.prim;
+            P.fh_t[in.pixel] = hit.t;
+            if (P.write_gbuffer) {
+              P.gbuffer[in.pixel] = make_uint4(0u, 0u, LP_INVALID_INDEX, 0xFFFFFFFFu);
+              P.motion[in.pixel] = make_float2(-1.f, -1.f);
+            }
+          }
+        }
+      }
+      shade_group(run_hit, in, hit);
+      continue;
+    }
+
+    // ---- settle the misses of kSettle x 32 queue entries, park the hits
+    if (more) {
+      uint32_t slot[kSettle];
+      bool valid[kSettle], is_hit[kSettle];
+#pragma unroll
+      for (int k = 0; k < kSettle; ++k) {
+        const uint32_t idx = base + 32u * (uint32_t)k + (uint32_t)lane;
+        valid[k] = idx < n;
+        slot[k] = valid[k] ? queue[idx] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < kSettle; ++k)
+        is_hit[k] = valid[k] && P.ps.hit_inst[slot[k]] != LP_INVALID_INDEX;
+      float4 t4[kSettle], r4[kSettle], d4[kSettle];
+#pragma unroll
+      for (int k = 0; k < kSettle; ++k) {
+        t4[k] = r4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        d4[k] = make_float4(0.f, 1.f, 0.f, 0.f);
+        if (valid[k] && !is_hit[k]) {
+          t4[k] = P.ps.thr[slot[k]];
+          r4[k] = P.ps.rad[slot[k]];
+          if (sc.probe) d4[k] = P.ps.ray_d[slot[k]];  // only a probe lookup needs the direction
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kSettle; ++k) {
+        if (valid[k] && !is_hit[k]) {
+          in.T = mk3(t4[k].x, t4[k].y, t4[k].z);
+          in.L = mk3(r4[k].x, r4[k].y, r4[k].z);
+          in.pdf_bsdf = t4[k].w;
+          in.pdf_env_dir = r4[k].w;
+          in.d = mk3(d4[k].x, d4[k].y, d4[k].z);
+          shade_miss(P, in);
+          P.ps.rad[slot[k]] = make_float4(in.L.x, in.L.y, in.L.z, 0.0f);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kSettle; ++k) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, is_hit[k]);
+        if (is_hit[k]) park[n_parked + __popc(m & lt_mask)] = slot[k];
+        n_parked += __popc(m);
+      }
+      __syncwarp();
+    }
+    // ---- the long branch on full groups of 32 (and on the tail once the queue is empty)
+    while (n_parked >= 32u || (!more && n_parked > 0u)) {
+      const uint32_t take = n_parked < 32u ? n_parked : 32u;
+      n_parked -= take;
+      const bool run_hit = (uint32_t)lane < take;
+      if (run_hit) {
+        const uint32_t slot = park[n_parked + lane];
+        load_path<false>(P, slot, in, P.ps.ray_d[slot]);
+        const float4 h4 = P.ps.hit[slot];
+        hit.t = h4.x;
+        hit.u = h4.y;
+        hit.v = h4.z;
+        hit.prim = __float_as_uint(h4.w);
+        hit.inst = P.ps.hit_inst[slot];
+      }
+      __syncwarp();
+      shade_group(run_hit, in, hit);
+    }
+    if (!more) break;
   }
 }
 
