@@ -253,6 +253,11 @@ typedef enum lp_scene_array {
 } lp_scene_array;
 LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const void **out_ptr,
                                     size_t *out_count, size_t *out_elem_size);
+/* Which 4-wide node layout the renderer will traverse for this scene: 1 = boxes in binary16
+ * rounded outwards (64-byte nodes, the production layout), 0 = boxes in fp32 (128-byte nodes),
+ * chosen when some tree root is too far from the origin for binary16 to resolve 1/16 of
+ * its extent.  Results are identical either way. */
+LP_API lp_status lp_scene_node_precision(lp_scene *scene, int *fp16_boxes);
 LP_API lp_status lp_scene_image_count(const lp_scene *scene, size_t *out_count);
 /* ImageData::{data, width, height} of scene.images[index] [ref scene.rs:5-28]. */
 LP_API lp_status lp_scene_get_image(const lp_scene *scene, size_t index, const uint8_t **rgba8,

@@ -111,6 +111,7 @@ _PROTOTYPES = {
     "lp_scene_push_image": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, c_u32_p]),
     "lp_scene_get_array": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_size_t)]),
+    "lp_scene_node_precision": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "lp_scene_image_count": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
     "lp_scene_get_image": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp), c_u32_p, c_u32_p]),
     "lp_scene_push_encoded_image": (C.c_int, [_vp, _vp, C.c_size_t, c_u32_p]),

@@ -213,6 +213,14 @@ class Scene:
         _check(_ffi.lib().lp_scene_image_count(self._h, C.byref(n)))
         return n.value
 
+    @property
+    def fp16_node_boxes(self) -> bool:
+        """True when the renderer traverses this scene with binary16 node boxes (the production
+        layout); False when it falls back to fp32 boxes (scene too far from the origin)."""
+        f = C.c_int()
+        _check(_ffi.lib().lp_scene_node_precision(self._h, C.byref(f)))
+        return bool(f.value)
+
     def image(self, index: int) -> np.ndarray:
         """(h, w, 4) uint8 copy of scene.images[index] (ImageData, scene.rs:5-28)."""
         ptr, w, h = C.c_void_p(), C.c_uint32(), C.c_uint32()

@@ -84,6 +84,7 @@ struct lp_scene_gpu {
   SceneDev sc{};
   size_t node_bytes = 0, tri_bytes = 0, total_bytes = 0;
   uint32_t max_depth = 0;
+  bool half_boxes_ok = true;  // Scene::half_boxes_ok: fp16 node boxes resolve this scene
 };
 
 struct lp_probe {
@@ -370,13 +371,16 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
         else extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
         break;
       }
+      // 12, 14: fp16 node boxes -- unless the scene is too far from the origin for binary16
+      // (Scene::half_boxes_ok), where the same kernels run on the fp32 4-wide nodes
+      const bool il = variant != 11 && r->sg->half_boxes_ok;
       if (variant == 14 && !any && b == 0) {
         // coherent primary rays: one ray per thread keeps the 8x4-tile locality in L1; the
         // camera rays are generated in the kernel (no generate_kernel, see fused_raygen)
-        extend4_kernel<true, true><<<cached_grid(extend4_kernel<true, true>, sm), 128, 0, st>>>(P, b);
+        if (il) extend4_kernel<true, true><<<cached_grid(extend4_kernel<true, true>, sm), 128, 0, st>>>(P, b);
+        else extend4_kernel<false, true><<<cached_grid(extend4_kernel<false, true>, sm), 128, 0, st>>>(P, b);
         break;
       }
-      const bool il = variant != 11;  // 12, 14: fp16 node boxes
       // LP_POOL_BLOCKS (tuning knob): resident pool blocks per SM.  Fewer blocks than the
       // shared-memory limit leave more of the SM's 256 KB to the L1 cache (the carve-out is
       // set to what the chosen number of blocks needs).
@@ -657,6 +661,7 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
                    s.materials.size() * 48 + s.lights.size() * sizeof(lp_light) +
                    s.atlas.texels.size() + s.atlas.gpu_blocks.size() * 4;
   g->max_depth = s.gpu_max_depth;
+  g->half_boxes_ok = s.half_boxes_ok;
   *out = g;
   return LP_OK;
 }

@@ -155,6 +155,11 @@ LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const
   return LP_OK;
 }
 
+LP_API lp_status lp_scene_node_precision(lp_scene *scene, int *fp16_boxes) {
+  if (!scene || !fp16_boxes) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  LP_TRY(scene->s.build_derived(); *fp16_boxes = scene->s.half_boxes_ok ? 1 : 0; return LP_OK;)
+}
+
 LP_API lp_status lp_scene_image_count(const lp_scene *scene, size_t *out_count) {
   if (!scene || !out_count) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   *out_count = scene->s.images.size();

@@ -456,6 +456,32 @@ void Scene::build_derived() {
     }
   }
 
+  // ---- are fp16 boxes good enough?  One criterion per tree root (TLAS and every BLAS, each
+  // in its own space): the binary16 spacing at the root box's largest |coordinate| must be
+  // <= 1/16 of the box's largest extent (an object of size s is fine up to 64 s away).  A scene far from the origin fails it (outward
+  // rounding keeps fp16 boxes conservative, so results would still be right, but every box
+  // would swell to the quantisation step and the traversal degenerate towards brute force).
+  half_boxes_ok = true;
+  auto check_root = [&](const lp_bvh_node &n) {
+    float max_abs = 0.f, extent = 0.f;
+    for (int a = 0; a < 3; ++a) {
+      if (!(n.aabb_min[a] <= n.aabb_max[a])) return;  // empty tree
+      max_abs = std::max(max_abs, std::max(std::fabs(n.aabb_min[a]), std::fabs(n.aabb_max[a])));
+      extent = std::max(extent, n.aabb_max[a] - n.aabb_min[a]);
+    }
+    if (!(max_abs < 60000.f)) {
+      half_boxes_ok = false;
+      return;
+    }
+    int e = 0;
+    std::frexp(std::max(max_abs, 6.1e-5f), &e);              // max_abs = m * 2^e, m in [0.5, 1)
+    const float ulp16 = std::ldexp(1.0f, e - 11);             // binary16 spacing at max_abs
+    if (ulp16 * 16.f > extent && extent > 0.f) half_boxes_ok = false;
+  };
+  if (!tlas.empty()) check_root(tlas[0]);
+  for (size_t e = 0; e < entries.size(); ++e)
+    if (entries[e].primitive_count) check_root(nodes[entries[e].node_offset]);
+
   gpu_instances.assign(instances.size(), GpuInstance{});
   for (size_t i = 0; i < instances.size(); ++i) {
     const lp_instance &s = instances[i];

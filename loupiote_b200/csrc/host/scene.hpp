@@ -107,6 +107,9 @@ struct Scene {
   std::vector<GpuNode4h> gpu_nodes4h;
   uint32_t gpu_tlas_root4 = 0;
   uint32_t gpu_max_stack4 = 0;
+  // false when some tree's root box sits so far from the origin that binary16 cannot resolve
+  // 1/16 of its extent (or overflows): the renderer then traverses the fp32 4-wide nodes
+  bool half_boxes_ok = true;
   Atlas atlas;
   bool derived_dirty = true;
 

@@ -319,3 +319,20 @@ def test_rust_sys_crate_matches_the_header():
     # the wrapper crate only calls functions the sys crate declares
     wrapper = (ROOT / "bindings" / "rust" / "loupiote-core-b200" / "src" / "lib.rs").read_text()
     assert set(re.findall(r"ffi::(lp_\w+)\(", wrapper)) <= fns
+
+
+def test_node_precision_choice():
+    """fp16 node boxes unless a tree root is too far from the origin for binary16."""
+    assert scenes.cornell_box()["scene"].fp16_node_boxes
+    assert scenes.spheres_1m(grid=2, subdivisions=1)["scene"].fp16_node_boxes
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    for offset, expect in ((0.0, True), (100.0, True), (3000.0, False), (1.0e5, False)):
+        s = lb.Scene()
+        b = s.blas.add_bvh(tri)
+        m = np.eye(4, dtype=np.float32)
+        m[0, 3] = offset
+        s.blas.add_instance(b, m, s.push_material())
+        assert s.fp16_node_boxes == expect, offset
+    s = lb.Scene()  # the BLAS itself far away in its own space
+    s.blas.add_instance(s.blas.add_bvh(tri + np.float32(70000.0)), np.eye(4), s.push_material())
+    assert not s.fp16_node_boxes

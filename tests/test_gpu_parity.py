@@ -70,6 +70,13 @@ def check_first_hit(device, scene, view, size):
     assert counters["n_int"][0] == st["n_int"]
     assert counters["n_tri"][0] == st["n_tri"]
     assert counters["n_inst"][0] == st["n_inst"]
+    # the PRODUCTION kernels (4-wide fp16 / fp32 nodes, no counters): same ids, same t bits --
+    # the closest hit is the lexicographic minimum over all triangles, whatever the tree
+    r.set_config(count_stats=0)
+    r.raytrace(view)
+    pi, pp, pt = r.read_first_hit()
+    assert np.array_equal(pi, oi) and np.array_equal(pp, op)
+    assert np.array_equal(pt.view(np.uint32), ot.view(np.uint32))
     return (inst != LP_MISS).mean()
 
 
@@ -268,3 +275,22 @@ def test_checkpoint_resume_of_the_accumulator(device):
     assert np.allclose(out, ref, rtol=1e-5, atol=1e-6)
     with pytest.raises(lb.Error):
         b.write_accum_sum(ckpt[:10], 4)
+
+
+def test_first_hit_far_from_origin_uses_fp32_nodes(device):
+    """A scene 1e5 units from the origin cannot use binary16 node boxes: the renderer switches
+    to the fp32 4-wide nodes and the ids stay exact."""
+    scene, view = soup_scene(n_tris=1500, n_inst=5, seed=11)
+    far = lb.Scene()
+    rng = np.random.default_rng(2)
+    c = rng.uniform(-1, 1, size=(1500, 1, 3))
+    pos = (c + rng.normal(scale=0.08, size=(1500, 3, 3))).reshape(-1, 3).astype(np.float32)
+    b = far.blas.add_bvh(pos)
+    mat = far.push_material(color=(0.7, 0.6, 0.5, 1.0), roughness=0.8)
+    for k in range(4):
+        m = np.eye(4, dtype=np.float32)
+        m[:3, 3] = (1.0e5 + 2.5 * k, -2.0e4, 3.0e4 + k)
+        far.blas.add_instance(b, m, mat)
+    assert not far.fp16_node_boxes and scene.fp16_node_boxes
+    view = lb.look_at_view((1.0e5 + 3.5, -2.0e4 + 0.3, 3.0e4 + 12.0), (0.0, 0.0, -1.0))
+    check_first_hit(device, far, view, (200, 120))
