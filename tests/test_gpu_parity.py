@@ -294,3 +294,43 @@ def test_first_hit_far_from_origin_uses_fp32_nodes(device):
     assert not far.fp16_node_boxes and scene.fp16_node_boxes
     view = lb.look_at_view((1.0e5 + 3.5, -2.0e4 + 0.3, 3.0e4 + 12.0), (0.0, 0.0, -1.0))
     check_first_hit(device, far, view, (200, 120))
+
+
+def test_first_hit_degenerate_geometry(device):
+    """Zero-area triangles, repeated vertices, a triangle seen exactly edge-on, a sliver and
+    a BLAS made only of degenerate triangles: never hit on either side, ids exact elsewhere."""
+    rng = np.random.default_rng(4)
+    good = (rng.uniform(-1, 1, size=(300, 1, 3)) + rng.normal(scale=0.15, size=(300, 3, 3)))
+    p = rng.uniform(-1, 1, size=(40, 3))
+    points = np.repeat(p[:, None, :], 3, axis=1)                       # three equal vertices
+    a, d = rng.uniform(-1, 1, size=(40, 1, 3)), rng.normal(size=(40, 1, 3))
+    lines = a + d * np.array([0.0, 0.3, 0.9])[None, :, None]           # collinear vertices
+    edge_on = np.array([[[0.2, -0.5, 1.0], [0.2, 0.5, 1.0], [0.2, 0.0, -1.0]]])  # in the plane x = 0.2
+    sliver = np.array([[[-0.9, 0.8, 0.0], [0.9, 0.8, 0.0], [0.0, 0.8 + 1e-6, 0.0]]])
+    soup = np.concatenate([good, points, lines, edge_on, sliver]).reshape(-1, 3).astype(np.float32)
+    scene = lb.Scene()
+    mat = scene.push_material(color=(0.8, 0.8, 0.8, 1.0))
+    scene.blas.add_instance(scene.blas.add_bvh(soup), np.eye(4), mat)
+    only_bad = np.concatenate([points, lines]).reshape(-1, 3).astype(np.float32)
+    m = np.eye(4, dtype=np.float32)
+    m[0, 3] = 0.5
+    scene.blas.add_instance(scene.blas.add_bvh(only_bad), m, mat)
+    # pixel-centre rays of an odd-width image: the middle column looks straight down -z
+    # from x = 0.2, i.e. along the plane of the edge-on triangle
+    view = lb.look_at_view((0.2, 0.0, 6.0), (0.0, 0.0, -1.0))
+    frac = check_first_hit(device, scene, view, (129, 97))
+    assert 0.05 < frac < 0.9
+
+
+def test_max_bounces_and_tiny_images(device):
+    """32 bounces (the ABI's maximum) with Russian roulette off in a closed box, and 1x1 / 3x2
+    images (a single ragged tile) match the oracle."""
+    c = scenes.cornell_box()
+    for size, bounces, spp in (((1, 1), 6, 64), ((3, 2), 32, 16), ((9, 5), 32, 8)):
+        gpu, cpu, counters, st = radiance_compare(device, c, size, spp, bounces)
+        assert np.allclose(gpu, cpu, rtol=5e-3, atol=1e-4), (size, np.abs(gpu - cpu).max())
+        assert counters["primary"] == st["primary"] == size[0] * size[1] * spp
+    with pytest.raises(lb.Error):
+        make_renderer(device, c["scene"], (8, 8), max_bounces=33)
+    with pytest.raises(lb.Error):
+        make_renderer(device, c["scene"], (8, 8), max_bounces=0)
