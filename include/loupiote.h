@@ -282,6 +282,13 @@ LP_API lp_status lp_load_binary_from_path(const char *path, lp_scene *scene);
 /* SceneGPU::new_from_scene(scene, device, queue) [ref scene.rs:151-187]: builds the TLAS,
  * re-lays the canonical tree out into the 64-byte GPU node format and uploads. */
 LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp_scene_gpu **out);
+/* Refreshes a SceneGPU after lp_scene_set_instance_transform (Instance::set_transform
+ * [ref standalone/src/lib.rs:118-121]) or edits of existing materials / emission / lights:
+ * rebuilds the TLAS on the host and uploads the TLAS node region, the instance records and the
+ * small tables only (the BLAS nodes, triangles, vertices and atlas are not touched).
+ * LP_ERR_INVALID_ARG when geometry or any count changed since new_from_scene (make a new
+ * SceneGPU then).  Synchronises the device; the renderer keeps its binding. */
+LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene);
 LP_API lp_status lp_scene_gpu_destroy(lp_scene_gpu *sg);
 /* Size report used by the app's log [ref app.rs:216-236]. */
 LP_API lp_status lp_scene_gpu_stats(const lp_scene_gpu *sg, size_t *node_bytes, size_t *tri_bytes,

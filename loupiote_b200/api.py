@@ -351,6 +351,11 @@ class SceneGPU:
         _check(_ffi.lib().lp_scene_gpu_new_from_scene(scene._h, device._h, C.byref(h)))
         return cls(h, device, scene)
 
+    def update_instances(self, scene: Optional[Scene] = None) -> None:
+        """After Scene.set_instance_transform (or edits of existing materials / lights):
+        re-uploads the TLAS region + instance records only."""
+        _check(_ffi.lib().lp_scene_gpu_update_instances(self._h, (scene or self.scene)._h))
+
     def stats(self) -> dict:
         a, b, c, d = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_uint32()
         _check(_ffi.lib().lp_scene_gpu_stats(self._h, C.byref(a), C.byref(b), C.byref(c),

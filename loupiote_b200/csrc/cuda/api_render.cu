@@ -85,6 +85,8 @@ struct lp_scene_gpu {
   size_t node_bytes = 0, tri_bytes = 0, total_bytes = 0;
   uint32_t max_depth = 0;
   bool half_boxes_ok = true;  // Scene::half_boxes_ok: fp16 node boxes resolve this scene
+  uint64_t layout_version = 0;  // Scene::layout_version this copy was made from
+  size_t n_instances = 0, n_materials = 0, n_lights = 0;
 };
 
 struct lp_probe {
@@ -662,7 +664,67 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
                    s.atlas.texels.size() + s.atlas.gpu_blocks.size() * 4;
   g->max_depth = s.gpu_max_depth;
   g->half_boxes_ok = s.half_boxes_ok;
+  g->layout_version = s.layout_version;
+  g->n_instances = s.gpu_instances.size();
+  g->n_materials = s.materials.size();
+  g->n_lights = s.lights.size();
   *out = g;
+  return LP_OK;
+}
+
+// Instance::set_transform after the upload [ref standalone/src/lib.rs:118-121, where the
+// reference moves an instance BEFORE its one upload]: the TLAS region of the node arrays, the
+// instance records and the (small) material / emission / light tables are refreshed; the
+// BLAS nodes, triangles, vertices and the atlas stay where they are.
+LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene) {
+  if (!sg || !scene) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  Scene &s = scene_of(scene);
+  try {
+    s.build_derived();
+  } catch (const std::exception &e) {
+    return fail(LP_ERR_ACCEL_BUILD, e.what());
+  }
+  if (s.layout_version != sg->layout_version || s.gpu_instances.size() != sg->n_instances ||
+      s.materials.size() != sg->n_materials || s.lights.size() != sg->n_lights)
+    return fail(LP_ERR_INVALID_ARG,
+                "geometry, instance count, materials or lights changed since this SceneGPU was "
+                "made: create a new one with lp_scene_gpu_new_from_scene");
+  if (s.gpu_max_depth + 2 > (uint32_t)kStackSize || s.gpu_max_stack4 > (uint32_t)kStackSize4)
+    return fail(LP_ERR_ACCEL_BUILD, "BVH too deep for the traversal stack");
+  lp_device *dev = sg->dev;
+  CUDA_CHECK(cudaSetDevice(dev->ordinal));
+  CUDA_CHECK(cudaStreamSynchronize(dev->stream));  // frames in flight still read the old TLAS
+  CUDA_CHECK(cudaStreamSynchronize(dev->stream2));
+  cudaStream_t st = dev->stream;
+  const size_t cap = s.tlas_capacity;
+  CUDA_CHECK(cudaMemcpyAsync(sg->nodes.ptr, s.gpu_nodes.data(), cap * sizeof(GpuNode),
+                             cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(sg->nodes4.ptr, s.gpu_nodes4.data(), cap * sizeof(GpuNode4),
+                             cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(sg->nodes4h.ptr, s.gpu_nodes4h.data(), cap * sizeof(GpuNode4h),
+                             cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(sg->instances.ptr, s.gpu_instances.data(),
+                             s.gpu_instances.size() * sizeof(GpuInstance), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(sg->materials.ptr, s.materials.data(),
+                             s.materials.size() * sizeof(lp_material), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(sg->emission.ptr, s.emission.data(), s.emission.size() * 16,
+                             cudaMemcpyHostToDevice, st));
+  std::vector<uint32_t> active;
+  for (uint32_t i = 0; i < s.lights.size(); ++i)
+    if (s.lights[i].intensity > 0.0f) active.push_back(i);
+  if (active.size() > sg->active_lights.count)
+    return fail(LP_ERR_INVALID_ARG, "more active lights than at upload: create a new SceneGPU");
+  CUDA_CHECK(cudaMemcpyAsync(sg->lights.ptr, s.lights.data(), s.lights.size() * sizeof(lp_light),
+                             cudaMemcpyHostToDevice, st));
+  if (!active.empty())
+    CUDA_CHECK(cudaMemcpyAsync(sg->active_lights.ptr, active.data(), active.size() * 4,
+                               cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  sg->sc.n_active_lights = (uint32_t)active.size();
+  sg->sc.tlas_root = s.gpu_tlas_root;
+  sg->sc.tlas_root4 = s.gpu_tlas_root4;
+  sg->max_depth = s.gpu_max_depth;
+  sg->half_boxes_ok = s.half_boxes_ok;
   return LP_OK;
 }
 

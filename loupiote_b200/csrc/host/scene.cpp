@@ -144,7 +144,7 @@ void Scene::add_instance(uint32_t blas, const float m[16], uint32_t material) {
 void Scene::set_instance_transform(uint32_t i, const float m[16]) {
   std::memcpy(instances[i].model_to_world, m, 64);
   invert_affine(m, instances[i].world_to_model);
-  derived_dirty = true;
+  instances_dirty = true;  // TLAS + instance records only; the BLAS layout stays valid
 }
 
 namespace {
@@ -368,9 +368,42 @@ uint32_t relayout4(const lp_bvh_node *tree, const LeafEncoder &enc, std::vector<
 
 }  // namespace
 
-void Scene::build_derived() {
-  if (!derived_dirty) return;
-  // ---- TLAS over instances that reference a non-empty BLAS
+namespace {
+
+void to_half_nodes(const GpuNode4 *src, GpuNode4h *dst, size_t count) {
+  // child boxes in fp16, rounded OUTWARDS (lo towards -inf, hi towards +inf) so the slab test
+  // stays conservative
+  for (size_t i = 0; i < count; ++i) {
+    const GpuNode4 &n = src[i];
+    GpuNode4h &h = dst[i];
+    for (int s = 0; s < 4; ++s) {
+      h.lo_x[s] = float_to_half_down(n.lo_x[s]);
+      h.lo_y[s] = float_to_half_down(n.lo_y[s]);
+      h.lo_z[s] = float_to_half_down(n.lo_z[s]);
+      h.hi_x[s] = float_to_half_up(n.hi_x[s]);
+      h.hi_y[s] = float_to_half_up(n.hi_y[s]);
+      h.hi_z[s] = float_to_half_up(n.hi_z[s]);
+      h.child[s] = n.child[s];
+    }
+  }
+}
+
+GpuNode4 empty_node4() {
+  GpuNode4 g;
+  for (int s = 0; s < 4; ++s) {
+    g.lo_x[s] = g.lo_y[s] = g.lo_z[s] = INFINITY;
+    g.hi_x[s] = g.hi_y[s] = g.hi_z[s] = -INFINITY;
+    g.child[s] = kNoChild;
+    g.pad[s] = 0;
+  }
+  return g;
+}
+
+}  // namespace
+
+// TLAS over the instances that reference a non-empty BLAS + its GPU layouts, written into the
+// first `tlas_capacity` slots of the node arrays (the BLAS trees follow and never move).
+void Scene::build_tlas() {
   std::vector<BuildBox> boxes;
   std::vector<uint32_t> ids;
   for (uint32_t i = 0; i < instances.size(); ++i) {
@@ -405,62 +438,37 @@ void Scene::build_derived() {
     ids.push_back(i);
   }
   std::vector<uint32_t> perm;
+  tlas.clear();
   build_bvh2(boxes, 1, tlas, perm);
   for (auto &n : tlas)
     if (n.count > 0) n.left_first = ids[perm[n.left_first]];
 
-  // ---- GPU layout: [TLAS | BLAS 1 | BLAS 2 | ...], each tree in BFS order
-  gpu_nodes.clear();
-  gpu_nodes.reserve(tlas.size() + nodes.size());
+  // GPU layouts of the TLAS: built at index 0, so child indices are already global
   LeafEncoder tenc{true, 0};
-  uint32_t tdepth = relayout(tlas.data(), tenc, gpu_nodes, gpu_tlas_root);
-  std::vector<uint32_t> blas_root(entries.size(), 0);
-  uint32_t bdepth = 0;
-  for (size_t e = 0; e < entries.size(); ++e) {
-    if (entries[e].primitive_count == 0) continue;
-    LeafEncoder benc{false, entries[e].primitive_offset};
-    uint32_t d = relayout(nodes.data() + entries[e].node_offset, benc, gpu_nodes, blas_root[e]);
-    bdepth = std::max(bdepth, d);
+  std::vector<GpuNode> t2;
+  std::vector<GpuNode4> t4;
+  tlas_depth = relayout(tlas.data(), tenc, t2, gpu_tlas_root);
+  tlas_depth4 = relayout4(tlas.data(), tenc, t4, gpu_tlas_root4);
+  if (t2.size() > tlas_capacity || t4.size() > tlas_capacity)
+    throw std::logic_error("TLAS larger than its reserved node region");
+  GpuNode empty2{};
+  put_box(empty2, 0, nullptr);
+  put_box(empty2, 1, nullptr);
+  empty2.child[0] = empty2.child[1] = kNoChild;
+  for (size_t i = 0; i < tlas_capacity; ++i) {
+    gpu_nodes[i] = i < t2.size() ? t2[i] : empty2;
+    gpu_nodes4[i] = i < t4.size() ? t4[i] : empty_node4();
   }
-  gpu_max_depth = tdepth + bdepth + 1;
-  if (primitives.size() >= (1u << 28)) throw std::invalid_argument("too many triangles (>= 2^28)");
-
-  // ---- 4-wide collapse of the same trees (production traversal layout)
-  gpu_nodes4.clear();
-  gpu_nodes4.reserve((tlas.size() + nodes.size()) / 2 + 1);
-  uint32_t tdepth4 = relayout4(tlas.data(), tenc, gpu_nodes4, gpu_tlas_root4);
-  std::vector<uint32_t> blas_root4(entries.size(), 0);
-  uint32_t bdepth4 = 0;
-  for (size_t e = 0; e < entries.size(); ++e) {
-    if (entries[e].primitive_count == 0) continue;
-    LeafEncoder benc{false, entries[e].primitive_offset};
-    uint32_t d = relayout4(nodes.data() + entries[e].node_offset, benc, gpu_nodes4, blas_root4[e]);
-    bdepth4 = std::max(bdepth4, d);
-  }
-  gpu_max_stack4 = 3u * (tdepth4 + bdepth4) + 2u;  // <= 3 pushes per visited node + sentinel
-
-  // ---- 64-byte variant of the 4-wide nodes: child boxes in fp16, rounded OUTWARDS (lo
-  // towards -inf, hi towards +inf) so the slab test stays conservative
-  gpu_nodes4h.resize(gpu_nodes4.size());
-  for (size_t i = 0; i < gpu_nodes4.size(); ++i) {
-    const GpuNode4 &n = gpu_nodes4[i];
-    GpuNode4h &h = gpu_nodes4h[i];
-    for (int s = 0; s < 4; ++s) {
-      h.lo_x[s] = float_to_half_down(n.lo_x[s]);
-      h.lo_y[s] = float_to_half_down(n.lo_y[s]);
-      h.lo_z[s] = float_to_half_down(n.lo_z[s]);
-      h.hi_x[s] = float_to_half_up(n.hi_x[s]);
-      h.hi_y[s] = float_to_half_up(n.hi_y[s]);
-      h.hi_z[s] = float_to_half_up(n.hi_z[s]);
-      h.child[s] = n.child[s];
-    }
-  }
+  to_half_nodes(gpu_nodes4.data(), gpu_nodes4h.data(), tlas_capacity);
+  gpu_max_depth = tlas_depth + blas_depth + 1;
+  gpu_max_stack4 = 3u * (tlas_depth4 + blas_depth4) + 2u;  // <= 3 pushes per visited node + sentinel
 
   // ---- are fp16 boxes good enough?  One criterion per tree root (TLAS and every BLAS, each
   // in its own space): the binary16 spacing at the root box's largest |coordinate| must be
-  // <= 1/16 of the box's largest extent (an object of size s is fine up to 64 s away).  A scene far from the origin fails it (outward
-  // rounding keeps fp16 boxes conservative, so results would still be right, but every box
-  // would swell to the quantisation step and the traversal degenerate towards brute force).
+  // <= 1/16 of the box's largest extent (an object of size s is fine up to 64 s away).  A
+  // scene far from the origin fails it (outward rounding keeps fp16 boxes conservative, so
+  // results would still be right, but every box would swell to the quantisation step and the
+  // traversal degenerate towards brute force).
   half_boxes_ok = true;
   auto check_root = [&](const lp_bvh_node &n) {
     float max_abs = 0.f, extent = 0.f;
@@ -474,8 +482,8 @@ void Scene::build_derived() {
       return;
     }
     int e = 0;
-    std::frexp(std::max(max_abs, 6.1e-5f), &e);              // max_abs = m * 2^e, m in [0.5, 1)
-    const float ulp16 = std::ldexp(1.0f, e - 11);             // binary16 spacing at max_abs
+    std::frexp(std::max(max_abs, 6.1e-5f), &e);   // max_abs = m * 2^e, m in [0.5, 1)
+    const float ulp16 = std::ldexp(1.0f, e - 11);  // binary16 spacing at max_abs
     if (ulp16 * 16.f > extent && extent > 0.f) half_boxes_ok = false;
   };
   if (!tlas.empty()) check_root(tlas[0]);
@@ -499,8 +507,51 @@ void Scene::build_derived() {
     g.vertex_offset = e.vertex_offset;
     g.blas = s.blas;
   }
+}
+
+// GPU layout: [TLAS region (tlas_capacity nodes) | BLAS 1 | BLAS 2 | ...], each tree in BFS
+// order.  The TLAS region has room for the largest TLAS the current instance count can give
+// (a binary tree over n leaves has n - 1 interior nodes; the 4-wide collapse has fewer), so
+// moving an instance (set_instance_transform) rebuilds and re-uploads the TLAS region and the
+// instance records only: `layout_version` tells a SceneGPU whether its BLAS copy is still valid.
+void Scene::build_derived() {
+  if (!derived_dirty) {
+    if (instances_dirty) {
+      build_tlas();
+      instances_dirty = false;
+    }
+    return;
+  }
+  if (primitives.size() >= (1u << 28)) throw std::invalid_argument("too many triangles (>= 2^28)");
+  tlas_capacity = (uint32_t)std::max<size_t>(1, instances.size());
+  GpuNode empty2{};
+  put_box(empty2, 0, nullptr);
+  put_box(empty2, 1, nullptr);
+  empty2.child[0] = empty2.child[1] = kNoChild;
+  gpu_nodes.assign(tlas_capacity, empty2);
+  gpu_nodes.reserve(tlas_capacity + nodes.size());
+  gpu_nodes4.assign(tlas_capacity, empty_node4());
+  gpu_nodes4.reserve(tlas_capacity + nodes.size() / 2 + 1);
+  blas_root.assign(entries.size(), 0);
+  blas_root4.assign(entries.size(), 0);
+  blas_depth = blas_depth4 = 0;
+  for (size_t e = 0; e < entries.size(); ++e) {
+    if (entries[e].primitive_count == 0) continue;
+    LeafEncoder benc{false, entries[e].primitive_offset};
+    blas_depth = std::max(blas_depth, relayout(nodes.data() + entries[e].node_offset, benc,
+                                               gpu_nodes, blas_root[e]));
+    // 4-wide collapse of the same tree (production traversal layout)
+    blas_depth4 = std::max(blas_depth4, relayout4(nodes.data() + entries[e].node_offset, benc,
+                                                  gpu_nodes4, blas_root4[e]));
+  }
+  gpu_nodes4h.resize(gpu_nodes4.size());
+  to_half_nodes(gpu_nodes4.data() + tlas_capacity, gpu_nodes4h.data() + tlas_capacity,
+                gpu_nodes4.size() - tlas_capacity);
+  build_tlas();
   build_atlas(images, 16384u, atlas);
+  ++layout_version;
   derived_dirty = false;
+  instances_dirty = false;
 }
 
 }  // namespace lp

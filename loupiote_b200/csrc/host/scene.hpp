@@ -111,7 +111,13 @@ struct Scene {
   // 1/16 of its extent (or overflows): the renderer then traverses the fp32 4-wide nodes
   bool half_boxes_ok = true;
   Atlas atlas;
+  // layout bookkeeping: [TLAS region of tlas_capacity nodes | BLAS trees]
+  uint32_t tlas_capacity = 1;
+  uint32_t tlas_depth = 0, tlas_depth4 = 0, blas_depth = 0, blas_depth4 = 0;
+  std::vector<uint32_t> blas_root, blas_root4;  // child reference of every BLAS root
+  uint64_t layout_version = 0;  // bumped by every full rebuild (geometry / counts changed)
   bool derived_dirty = true;
+  bool instances_dirty = false;  // only instance transforms changed since the last build
 
   Scene();
   uint32_t add_bvh(const void *positions, size_t pstride, const void *normals, size_t nstride,
@@ -119,7 +125,8 @@ struct Scene {
                    size_t index_count);
   void add_instance(uint32_t blas, const float m[16], uint32_t material);
   void set_instance_transform(uint32_t instance, const float m[16]);
-  void build_derived();  // TLAS + GPU layout
+  void build_derived();  // TLAS + GPU layout (full, or TLAS-only after set_instance_transform)
+  void build_tlas();
 };
 
 // Binned-SAH BVH2 over boxes (16 bins, all three axes, traversal cost 1, intersection

@@ -336,3 +336,32 @@ def test_node_precision_choice():
     s = lb.Scene()  # the BLAS itself far away in its own space
     s.blas.add_instance(s.blas.add_bvh(tri + np.float32(70000.0)), np.eye(4), s.push_material())
     assert not s.fp16_node_boxes
+
+
+def test_instance_move_rebuilds_only_the_tlas_region():
+    """set_instance_transform (Instance::set_transform, standalone/src/lib.rs:118-121) leaves
+    the BLAS part of every GPU node array untouched: [TLAS region | BLAS trees]."""
+    c = scenes.spheres_1m(grid=2, subdivisions=2)
+    s = c["scene"]
+    n_inst = len(s.blas.instances)
+    before = {k: s.array(k).copy() for k in (_ffi.SCENE_GPU_NODES, _ffi.SCENE_GPU_NODES4,
+                                             _ffi.SCENE_GPU_INSTANCES, _ffi.SCENE_TLAS_NODES)}
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = (7.0, 3.0, -2.0)
+    s.set_instance_transform(2, m)
+    after = {k: s.array(k) for k in before}
+    for k in (_ffi.SCENE_GPU_NODES, _ffi.SCENE_GPU_NODES4):
+        assert after[k].shape == before[k].shape
+        assert np.array_equal(after[k][n_inst:], before[k][n_inst:])        # BLAS trees
+        assert not np.array_equal(after[k][:n_inst], before[k][:n_inst])    # TLAS region
+    gi0, gi1 = before[_ffi.SCENE_GPU_INSTANCES], after[_ffi.SCENE_GPU_INSTANCES]
+    assert np.array_equal(gi0["root4"], gi1["root4"]) and np.array_equal(gi0["root"], gi1["root"])
+    assert np.allclose(gi1["o2w"][2].reshape(3, 4)[:, 3], (7.0, 3.0, -2.0))
+    # the canonical TLAS (what the oracle walks) moved with it: its root box now reaches y > 3.5
+    assert after[_ffi.SCENE_TLAS_NODES][0]["aabb_max"][1] > 3.5 > before[_ffi.SCENE_TLAS_NODES][0]["aabb_max"][1]
+    # children of interior nodes are real indices inside the array or leaves
+    n4 = after[_ffi.SCENE_GPU_NODES4]
+    refs = n4["child"].reshape(-1)
+    interior = refs[(refs & 0x80000000) == 0]
+    interior = interior[interior != 0x7FFFFFFF]
+    assert interior.max() < len(n4)

@@ -334,3 +334,40 @@ def test_max_bounces_and_tiny_images(device):
         make_renderer(device, c["scene"], (8, 8), max_bounces=33)
     with pytest.raises(lb.Error):
         make_renderer(device, c["scene"], (8, 8), max_bounces=0)
+
+
+def test_update_instances_matches_fresh_upload_and_oracle(device):
+    """Moving instances after the upload: lp_scene_gpu_update_instances refreshes the TLAS
+    region + instance records in place; ids equal the oracle's and a fresh SceneGPU's."""
+    c = scenes.spheres_1m(grid=3, subdivisions=3)
+    scene, view = c["scene"], c["view"]
+    size = (192, 108)
+    r, sg = make_renderer(device, scene, size, max_bounces=3, spp_per_call=2, jitter=0, seed=2,
+                          env_color=c["env_color"])
+    cam = O.camera_from_view(view, size[0], size[1], V_FOV)
+    rng = np.random.default_rng(8)
+    for step in range(3):
+        for inst in (1, 4, 7):
+            m = np.eye(4, dtype=np.float32)
+            a = rng.uniform(0, 2 * np.pi)
+            m[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]) * rng.uniform(0.6, 1.4)
+            m[:3, 3] = rng.uniform(-4, 4, 3) + (0, 2.5, 0)
+            scene.set_instance_transform(inst, m)
+        sg.update_instances()
+        r.reset_accumulation()
+        r.set_config(seed=2)
+        r.raytrace(view)
+        inst_u, prim_u, t_u = r.read_first_hit()
+        img_u = r.read_accum_f32()
+        oi, op, ot, _, _ = O.first_hit_image(O.OracleScene(scene), cam, 1)
+        assert np.array_equal(inst_u, oi) and np.array_equal(prim_u, op)
+        assert np.array_equal(t_u.view(np.uint32), ot.view(np.uint32))
+        r2, sg2 = make_renderer(device, scene, size, max_bounces=3, spp_per_call=2, jitter=0,
+                                seed=2, env_color=c["env_color"])
+        r2.raytrace(view)
+        assert np.array_equal(r2.read_accum_f32(), img_u)
+    # a count change invalidates the fast path
+    scene.blas.add_instance(1, np.eye(4), 1)
+    with pytest.raises(lb.Error) as e:
+        sg.update_instances()
+    assert e.value.code == lb.Error.InvalidArg

@@ -2,13 +2,16 @@
 """Runs the BASELINE.json configurations that are not the bench.py headline on ONE GPU and
 prints one JSON line each (GPU only):
 
+  config1  cornell-box 512x512, 16 spp, 4 bounces on the HOST CORES: the CPU restatement (oracle)
+           standing in for the reference's wgpu-on-lavapipe render, which cannot be produced
+           here, with the GPU render of the same samples beside it
   config2  cornell-box 1920x1080, 256 spp, 8 bounces: first-hit id check vs the oracle +
            converged-image tolerance (RMSE self-calibrated against the oracle)
   config4  procedural 10,240,000-triangle instanced lattice, 3840x2160, 8 bounces (1-GPU share)
   config5  interactive 1080p, 1 spp/frame, 4 bounces + SVGF (temporal + 5 a-trous + composite):
            frame latency median / p99 over 200 frames, denoise time vs its HBM bound
 
-    python tools/run_configs.py [config2 config4 config5]
+    python tools/run_configs.py [config1 config2 config4 config5]
 """
 import json
 import sys
@@ -36,6 +39,44 @@ def normalised_rmse(a, ref):
     ref = np.clip(ref, 0, 4)
     lum = max(float((0.2126 * ref[..., 0] + 0.7152 * ref[..., 1] + 0.0722 * ref[..., 2]).mean()), 1e-6)
     return float(np.sqrt(((a - ref) ** 2).mean()) / lum)
+
+
+def config1(dev):
+    import os
+    from oracle import oracle as O
+    c = scenes.cornell_box()
+    w = h = 512
+    threads = O.set_threads(os.cpu_count() or 1)
+    osc = O.OracleScene(c["scene"])
+    cam = O.camera_from_view(c["view"], w, h, V_FOV)
+    sg = lb.SceneGPU.new_from_scene(c["scene"], dev)
+    r = lb.Renderer(dev, (w, h), downsample_factor=1.0)
+    r.set_resources(sg, None)
+    r.set_config(max_bounces=4, spp_per_call=16, jitter=1, seed=0)
+    r.raytrace(c["view"])   # warm-up
+    dev.synchronize()
+    r.ray_counters(reset=True)
+    t0 = time.perf_counter()
+    r.raytrace(c["view"])
+    dev.synchronize()
+    gpu_s = time.perf_counter() - t0
+    gpu = r.read_accum_f32()[..., :3]
+    cnt = r.ray_counters(reset=True)
+    t0 = time.perf_counter()
+    acc, st = O.render(osc, cam, r.config, 16)
+    cpu_s = time.perf_counter() - t0
+    cpu = acc[..., :3] / acc[..., 3:4]
+    cpu_rays = st["primary"] + st["bounce"] + st["shadow"]
+    err = np.abs(gpu - cpu).max(axis=-1)
+    bad = float((err > 1e-3 * np.maximum(cpu.max(axis=-1), 1e-3) + 1e-5).mean())
+    return {"config": "assets/cornell-box.glb 512x512, 16 spp, 4 bounces: CPU restatement on the "
+                      "host cores (not wgpu/lavapipe) and the GPU on the same samples",
+            "cpu": {"threads": threads, "seconds": cpu_s, "mrays_s": cpu_rays / cpu_s / 1e6,
+                    "spp_per_s": 16 / cpu_s, "rays": cpu_rays},
+            "gpu": {"seconds": gpu_s, "mrays_s": rays(cnt) / gpu_s / 1e6, "rays": rays(cnt)},
+            "same_samples": {"pixels_outside_tolerance": bad,
+                             "mean_rel_diff": abs(float(gpu.mean()) - float(cpu.mean())) / float(cpu.mean()),
+                             "rmse": normalised_rmse(gpu, cpu)}}
 
 
 def config2(dev):
@@ -180,7 +221,7 @@ def config5(dev):
 
 
 def main():
-    todo = sys.argv[1:] or ["config2", "config4", "config5"]
+    todo = sys.argv[1:] or ["config1", "config2", "config4", "config5"]
     dev = lb.Device(0)
     for name in todo:
         out = {"name": name, **globals()[name](dev)}
