@@ -404,7 +404,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="spheres-1M-1080p-8b", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-per-step", type=int, default=32,
+    ap.add_argument("--spp-per-step", type=int, default=64,
                     help="samples per pixel traced by one step (one raytrace call = one batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (tuning)")

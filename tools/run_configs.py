@@ -55,6 +55,8 @@ def config1(dev):
     r.set_config(max_bounces=4, spp_per_call=16, jitter=1, seed=0)
     r.raytrace(c["view"])   # warm-up
     dev.synchronize()
+    r.set_config(seed=0)    # restart the sample sequence: the timed call traces samples 0..15
+    r.reset_accumulation()
     r.ray_counters(reset=True)
     t0 = time.perf_counter()
     r.raytrace(c["view"])
@@ -154,7 +156,7 @@ def config4(dev):
                  count_stats=1)
     r.raytrace(c["view"])
     stats = bench.algorithmic_bytes_flops(r.ray_counters(reset=True))
-    spp = int(__import__("os").environ.get("LP_CONFIG4_SPP", "7"))  # samples per wave
+    spp = int(__import__("os").environ.get("LP_CONFIG4_SPP", "15"))  # samples per wave
     r.set_config(max_bounces=bounces, spp_per_call=spp, jitter=1, seed=0,
                  env_color=c["env_color"], count_stats=0)
     for _ in range(2):
