@@ -33,6 +33,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+_JSON_OUT = sys.stdout  # main() re-points it at the real stdout and sends fd 1 to stderr
+
 WORKLOADS = {
     # name: (scene factory name, kwargs, width, height, bounces)
     "spheres-1M-1080p-8b": ("spheres_1m", {}, 1920, 1080, 8),
@@ -196,7 +198,7 @@ def run_reference(args) -> None:
                              "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def run_ours(args) -> None:
@@ -391,7 +393,7 @@ def run_ours(args) -> None:
                                     "kind": "port",
                                     "sample": f"{cspp} spp of every {step}th pixel of "
                                               f"{args.workload} ({crays} rays, {cdt:.1f} s)"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -409,10 +411,17 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (tuning)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints there while the bench
+    # runs (NCCL announces its version on stdout when a communicator is created) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    _JSON_OUT.flush()
 
 
 if __name__ == "__main__":
