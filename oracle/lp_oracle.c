@@ -773,6 +773,33 @@ static int bsdf_sample(const surface *sf, const float wo[3], float ul, float u1,
   return dot3(sf->ns, wi) > 0.0f && dot3(sf->ng, wi) > 0.0f;
 }
 
+/* ---- BSDF probes for the known-answer tests (reciprocity, energy, pdf normalisation,
+ * sample / pdf consistency): the SAME bsdf_eval / bsdf_sample the path tracer calls, on a
+ * surface given by its shading normal and material constants (ng = ns). */
+static void probe_surface(surface *sf, const float base[3], float metallic, float roughness,
+                          const float n[3]) {
+  memset(sf, 0, sizeof(*sf));
+  for (int a = 0; a < 3; ++a) {
+    sf->base[a] = base[a];
+    sf->ns[a] = sf->ng[a] = n[a];
+  }
+  sf->metallic = clampf(metallic, 0.0f, 1.0f);
+  const float rough = clampf(roughness, 0.0f, 1.0f);
+  sf->alpha = maxf(rough * rough, 1e-3f);
+}
+void lpo_bsdf_eval(const float base[3], float metallic, float roughness, const float n[3],
+                   const float wo[3], const float wi[3], float f[3], float *pdf) {
+  surface sf;
+  probe_surface(&sf, base, metallic, roughness, n);
+  bsdf_eval(&sf, wo, wi, f, pdf);
+}
+int lpo_bsdf_sample(const float base[3], float metallic, float roughness, const float n[3],
+                    const float wo[3], float ul, float u1, float u2, float wi[3]) {
+  surface sf;
+  probe_surface(&sf, base, metallic, roughness, n);
+  return bsdf_sample(&sf, wo, ul, u1, u2, wi);
+}
+
 void lpo_rgbe_decode(const uint8_t rgbe[4], float rgb[3]) {
   if (rgbe[3] == 0) {
     rgb[0] = rgb[1] = rgb[2] = 0.0f;

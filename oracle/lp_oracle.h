@@ -130,6 +130,14 @@ void lpo_render(const lpo_scene *s, const lp_camera *cam, const lp_render_config
 void lpo_set_threads(int n);
 int lpo_max_threads(void);
 
+/* BSDF of DESIGN.md section 3 on a surface with shading normal n (= geometric normal):
+ * f (rgb, without the cosine) and the lobe-mixture pdf of wi; sample returns 0 when the
+ * sampled direction leaves the upper hemisphere. */
+void lpo_bsdf_eval(const float base[3], float metallic, float roughness, const float n[3],
+                   const float wo[3], const float wi[3], float f[3], float *pdf);
+int lpo_bsdf_sample(const float base[3], float metallic, float roughness, const float n[3],
+                    const float wo[3], float ul, float u1, float u2, float wi[3]);
+
 void lpo_tonemap_srgb8(const float *rgba, size_t n_pixels, uint8_t *out);
 void lpo_rgbe_decode(const uint8_t rgbe[4], float rgb[3]);
 

@@ -277,6 +277,27 @@ def render(oscene: OracleScene, cam, cfg, spp: int, pixel_step: int = 1, accum=N
     return accum, stats
 
 
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def bsdf_eval(base, metallic: float, roughness: float, n, wo, wi):
+    """(f rgb without the cosine, pdf of wi) of the spec's BSDF on a surface with normal n."""
+    f, pdf = (C.c_float * 3)(), C.c_float()
+    lib().lpo_bsdf_eval(_f3(base), C.c_float(metallic), C.c_float(roughness), _f3(n), _f3(wo),
+                        _f3(wi), f, C.byref(pdf))
+    return np.array(f[:], np.float32), float(pdf.value)
+
+
+def bsdf_sample(base, metallic: float, roughness: float, n, wo, ul: float, u1: float, u2: float):
+    """(valid, wi) for the three sampling numbers (lobe, direction x 2)."""
+    wi = (C.c_float * 3)()
+    lib().lpo_bsdf_sample.restype = C.c_int
+    ok = lib().lpo_bsdf_sample(_f3(base), C.c_float(metallic), C.c_float(roughness), _f3(n),
+                               _f3(wo), C.c_float(ul), C.c_float(u1), C.c_float(u2), wi)
+    return bool(ok), np.array(wi[:], np.float32)
+
+
 def tonemap_srgb8(rgba: np.ndarray) -> np.ndarray:
     a = np.ascontiguousarray(rgba, dtype=np.float32)
     n = a.size // 4
