@@ -166,6 +166,13 @@ impl SceneGPU {
         check(unsafe { ffi::lp_scene_gpu_new_from_scene(scene.raw, device.raw, &mut raw) })?;
         Ok(SceneGPU { raw })
     }
+    /// Extension: the same upload with every BLAS and the TLAS built on the device (LBVH),
+    /// for scenes whose host SAH build would dominate the load time.
+    pub fn new_from_scene_device_built(scene: &Scene, device: &Device) -> Result<Self, Error> {
+        let mut raw = null_mut();
+        check(unsafe { ffi::lp_scene_gpu_new_from_scene_lbvh(scene.raw, device.raw, &mut raw) })?;
+        Ok(SceneGPU { raw })
+    }
 }
 impl Drop for SceneGPU {
     fn drop(&mut self) {

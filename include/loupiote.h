@@ -289,6 +289,17 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
  * LP_ERR_INVALID_ARG when geometry or any count changed since new_from_scene (make a new
  * SceneGPU then).  Synchronises the device; the renderer keeps its binding. */
 LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene);
+/* SceneGPU::new_from_scene with the acceleration structures built ON THE DEVICE
+ * (SURVEY 8(f) row 4): replaces the host BVH build behind BLASArray::add_bvh
+ * [ref loaders/gltf.rs:97-105] and the node upload [ref scene.rs:151-170] by an LBVH build
+ * from the uploaded vertex / index arrays -- 63-bit Morton order, Karras radix tree, bottom-up
+ * fit, leaves of <= 4 triangles, 4-wide collapse, fp16 boxes rounded outwards -- for every
+ * BLAS at once, then the TLAS.  The tree differs from the host's binned-SAH tree; hits and
+ * images do not (closest hit is traversal-order independent).  The canonical traversal counters
+ * (lp_render_config.count_stats) of such a SceneGPU describe ITS tree, not the canonical one.
+ * lp_scene_gpu_update_instances on it rebuilds the TLAS on the device as well. */
+LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp_device *dev,
+                                                  lp_scene_gpu **out);
 LP_API lp_status lp_scene_gpu_destroy(lp_scene_gpu *sg);
 /* Size report used by the app's log [ref app.rs:216-236]. */
 LP_API lp_status lp_scene_gpu_stats(const lp_scene_gpu *sg, size_t *node_bytes, size_t *tri_bytes,

@@ -26,6 +26,7 @@ SOURCES = [
     CSRC / "host" / "textures.cpp",
     CSRC / "host" / "api_scene.cpp",
     CSRC / "cuda" / "api_render.cu",
+    CSRC / "cuda" / "lbvh_build.cu",
 ]
 # translation units whose arithmetic never decides a hit: FMA contraction on
 SOURCES_FMAD = [
@@ -52,7 +53,7 @@ def _nvcc() -> str:
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    files = sorted([ROOT / "tools" / "cli" / "lp_render.cpp"] + list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.cpp"))
+    files = sorted([ROOT / "tools" / "cli" / "lp_render.cpp"] + list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.cpp")) + list(CSRC.rglob("*.h"))
                    + list(CSRC.rglob("*.hpp")) + [ROOT / "include" / "loupiote.h"])
     for f in files:
         h.update(f.name.encode())

@@ -122,6 +122,7 @@ _PROTOTYPES = {
     "lp_load_binary_from_path": (C.c_int, [C.c_char_p, _vp]),
     "lp_scene_gpu_new_from_scene": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "lp_scene_gpu_update_instances": (C.c_int, [_vp, _vp]),
+    "lp_scene_gpu_new_from_scene_lbvh": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "lp_scene_gpu_destroy": (C.c_int, [_vp]),
     "lp_scene_gpu_stats": (C.c_int, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_size_t), c_u32_p]),

@@ -346,9 +346,16 @@ class SceneGPU:
         self._h, self.device, self.scene = handle, device, scene
 
     @classmethod
-    def new_from_scene(cls, scene: Scene, device: Device) -> "SceneGPU":
+    def new_from_scene(cls, scene: Scene, device: Device, builder: str = "host") -> "SceneGPU":
+        """builder="host": the scene's binned-SAH trees, re-laid out and uploaded (the
+        reference's SceneGPU::new_from_scene); builder="lbvh": every BLAS and the TLAS built on
+        the device from the vertex / index arrays (lp_scene_gpu_new_from_scene_lbvh)."""
+        if builder not in ("host", "lbvh"):
+            raise ValueError(f"unknown builder {builder!r}")
         h = C.c_void_p()
-        _check(_ffi.lib().lp_scene_gpu_new_from_scene(scene._h, device._h, C.byref(h)))
+        fn = (_ffi.lib().lp_scene_gpu_new_from_scene if builder == "host"
+              else _ffi.lib().lp_scene_gpu_new_from_scene_lbvh)
+        _check(fn(scene._h, device._h, C.byref(h)))
         return cls(h, device, scene)
 
     def update_instances(self, scene: Optional[Scene] = None) -> None:

@@ -13,6 +13,7 @@
 
 #include "../host/api_common.hpp"
 #include "../host/scene.hpp"
+#include "api_gpu.cuh"
 #include "kernels.cuh"
 #include "svgf.cuh"
 #include "svgf_temporal.cuh"
@@ -20,74 +21,12 @@
 #include "traverse4.cuh"
 #include "trace_pool.cuh"
 
+#include "lbvh_core.h"
+
 using namespace lp;
 
-#define CUDA_CHECK(expr)                                                                  \
-  do {                                                                                    \
-    cudaError_t _e = (expr);                                                              \
-    if (_e != cudaSuccess) {                                                              \
-      return lp::fail(_e == cudaErrorMemoryAllocation ? LP_ERR_OOM : LP_ERR_CUDA,         \
-                      std::string(#expr) + ": " + cudaGetErrorString(_e));                \
-    }                                                                                     \
-  } while (0)
-
-namespace {
-
-// gpu::Buffer<T> [ref albedo_backend::gpu::Buffer, renderer.rs:233-241]: RAII cudaMalloc.
-template <typename T>
-struct DevBuf {
-  T *ptr = nullptr;
-  size_t count = 0;
-  DevBuf() = default;
-  DevBuf(const DevBuf &) = delete;
-  DevBuf &operator=(const DevBuf &) = delete;
-  ~DevBuf() { release(); }
-  void release() {
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    count = 0;
-  }
-  // keeps the allocation (and so the device address a caller may hold, e.g. the accumulator
-  // handed out by lp_renderer_accum_device_ptr) when the element count does not change
-  cudaError_t alloc(size_t n) {
-    if (n == 0) n = 1;
-    if (ptr && count == n) return cudaSuccess;
-    release();
-    cudaError_t e = cudaMalloc((void **)&ptr, n * sizeof(T));
-    if (e == cudaSuccess) count = n;
-    return e;
-  }
-  cudaError_t upload(const void *src, size_t n, cudaStream_t s) {
-    cudaError_t e = alloc(n);
-    if (e != cudaSuccess || n == 0) return e;
-    return cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
-  }
-};
-
-}  // namespace
-
-struct lp_device {
-  int ordinal = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // shadow rays of bounce b overlap the extend of bounce b+1
-  int sm_count = 0;
-  cudaDeviceProp prop{};
-};
-
-struct lp_scene_gpu {
-  lp_device *dev = nullptr;
-  DevBuf<float4> nodes, nodes4, nodes4h, tris, instances, vertices, materials, emission, lights;
-  DevBuf<uint32_t> indices, active_lights;
-  DevBuf<uchar4> atlas;
-  DevBuf<uint4> tex_blocks;
-  DevBuf<float> srgb_lut;
-  SceneDev sc{};
-  size_t node_bytes = 0, tri_bytes = 0, total_bytes = 0;
-  uint32_t max_depth = 0;
-  bool half_boxes_ok = true;  // Scene::half_boxes_ok: fp16 node boxes resolve this scene
-  uint64_t layout_version = 0;  // Scene::layout_version this copy was made from
-  size_t n_instances = 0, n_materials = 0, n_lights = 0;
-};
+static_assert(3 * lp::lbvh::kMaxLevels + 3 == kStackSize4,
+              "lbvh_build.cu's depth limit must match the 4-wide traversal stack");
 
 struct lp_probe {
   lp_device *dev = nullptr;
@@ -583,6 +522,98 @@ LP_API lp_status lp_device_info(lp_device *dev, char *name, size_t name_cap, int
 }
 
 // ------------------------------------------------------------------ SceneGPU / ProbeGPU
+}  // extern "C"
+
+// Everything a SceneGPU holds besides nodes, triangles and instance records: vertices,
+// indices, materials, emission, lights, the texture atlas [ref scene.rs:172-184] and the
+// sRGB8 -> linear table (IEC 61966-2-1 EOTF evaluated in double, rounded once: the same 256
+// floats the CPU restatement uses).  Shared with the device-side build (lbvh_build.cu).
+cudaError_t lp::upload_shading_data(lp_scene_gpu *g, Scene &s, cudaStream_t st, uint32_t *n_active) {
+  std::vector<uint32_t> active;
+  for (uint32_t i = 0; i < s.lights.size(); ++i)
+    if (s.lights[i].intensity > 0.0f) active.push_back(i);
+  *n_active = (uint32_t)active.size();
+  cudaError_t e = cudaSuccess;
+  auto up = [&](auto &buf, const void *src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = buf.upload(src, bytes / sizeof(*buf.ptr), st);
+  };
+  up(g->vertices, s.vertices.data(), s.vertices.size() * sizeof(lp_vertex));
+  up(g->materials, s.materials.data(), s.materials.size() * sizeof(lp_material));
+  up(g->emission, s.emission.data(), s.emission.size() * 16);
+  up(g->lights, s.lights.data(), s.lights.size() * sizeof(lp_light));
+  up(g->indices, s.indices.data(), s.indices.size() * sizeof(uint32_t));
+  up(g->active_lights, active.data(), active.size() * sizeof(uint32_t));
+  up(g->atlas, s.atlas.texels.data(), s.atlas.texels.size());
+  up(g->tex_blocks, s.atlas.gpu_blocks.data(), s.atlas.gpu_blocks.size() * sizeof(uint32_t));
+  float lut[256];
+  for (int i = 0; i < 256; ++i) {
+    const double c = i / 255.0;
+    lut[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+  }
+  up(g->srgb_lut, lut, sizeof(lut));
+  // the pageable host sources above (active, lut) must outlive the copies
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+
+// Kernel-side view of the buffers + the bookkeeping lp_scene_gpu_stats reports.
+void lp::bind_scene(lp_scene_gpu *g, const Scene &s, uint32_t n_active, size_t n_nodes2,
+                    size_t n_nodes4) {
+  SceneDev &sc = g->sc;
+  sc.nodes = g->nodes.ptr;
+  sc.tris = g->tris.ptr;
+  sc.instances = g->instances.ptr;
+  sc.vertices = g->vertices.ptr;
+  sc.indices = g->indices.ptr;
+  sc.materials = g->materials.ptr;
+  sc.emission = g->emission.ptr;
+  sc.lights = g->lights.ptr;
+  sc.active_lights = g->active_lights.ptr;
+  sc.n_active_lights = n_active;
+  sc.n_materials = (uint32_t)s.materials.size();
+  sc.nodes4 = g->nodes4.ptr;
+  sc.nodes4h = g->nodes4h.ptr;
+  sc.atlas = g->atlas.ptr;
+  sc.tex_blocks = g->tex_blocks.ptr;
+  sc.srgb_lut = g->srgb_lut.ptr;
+  sc.atlas_size = s.atlas.size;
+  sc.n_textures = (uint32_t)s.atlas.blocks.size();
+  g->node_bytes = n_nodes2 * sizeof(GpuNode) + n_nodes4 * sizeof(GpuNode4);
+  g->tri_bytes = s.primitives.size() * 64;
+  g->total_bytes = g->node_bytes + g->tri_bytes + s.instances.size() * sizeof(GpuInstance) +
+                   s.vertices.size() * sizeof(lp_vertex) + s.indices.size() * 4 +
+                   s.materials.size() * 48 + s.lights.size() * sizeof(lp_light) +
+                   s.atlas.texels.size() + s.atlas.gpu_blocks.size() * 4;
+  g->n_instances = s.instances.size();
+  g->n_materials = s.materials.size();
+  g->n_lights = s.lights.size();
+}
+
+// Materials, emission and lights may change between frames without a new SceneGPU (their
+// counts may not): refreshed together with the instances.
+lp_status lp::refresh_small_tables(lp_scene_gpu *sg, Scene &s, cudaStream_t st) {
+  CUDA_CHECK(cudaMemcpyAsync(sg->materials.ptr, s.materials.data(),
+                             s.materials.size() * sizeof(lp_material), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(sg->emission.ptr, s.emission.data(), s.emission.size() * 16,
+                             cudaMemcpyHostToDevice, st));
+  std::vector<uint32_t> active;
+  for (uint32_t i = 0; i < s.lights.size(); ++i)
+    if (s.lights[i].intensity > 0.0f) active.push_back(i);
+  if (active.size() > sg->active_lights.count)
+    return fail(LP_ERR_INVALID_ARG, "more active lights than at upload: create a new SceneGPU");
+  CUDA_CHECK(cudaMemcpyAsync(sg->lights.ptr, s.lights.data(), s.lights.size() * sizeof(lp_light),
+                             cudaMemcpyHostToDevice, st));
+  if (!active.empty())
+    CUDA_CHECK(cudaMemcpyAsync(sg->active_lights.ptr, active.data(), active.size() * 4,
+                               cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  sg->sc.n_active_lights = (uint32_t)active.size();
+  return LP_OK;
+}
+
+extern "C" {
+
 LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp_scene_gpu **out) {
   if (!scene || !dev || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   Scene &s = scene_of(scene);
@@ -598,9 +629,6 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   if (!g) return fail(LP_ERR_OOM, "out of host memory");
   g->dev = dev;
   cudaStream_t st = dev->stream;
-  std::vector<uint32_t> active;
-  for (uint32_t i = 0; i < s.lights.size(); ++i)
-    if (s.lights[i].intensity > 0.0f) active.push_back(i);
   cudaError_t e = cudaSuccess;
   auto up = [&](auto &buf, const void *src, size_t bytes) {
     if (e != cudaSuccess) return;
@@ -615,60 +643,18 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
     std::memcpy(&tris64[16 * i], &s.primitives[i], sizeof(lp_bvh_primitive));
   up(g->tris, tris64.data(), tris64.size() * sizeof(float));
   up(g->instances, s.gpu_instances.data(), s.gpu_instances.size() * sizeof(GpuInstance));
-  up(g->vertices, s.vertices.data(), s.vertices.size() * sizeof(lp_vertex));
-  up(g->materials, s.materials.data(), s.materials.size() * sizeof(lp_material));
-  up(g->emission, s.emission.data(), s.emission.size() * 16);
-  up(g->lights, s.lights.data(), s.lights.size() * sizeof(lp_light));
-  up(g->indices, s.indices.data(), s.indices.size() * sizeof(uint32_t));
-  up(g->active_lights, active.data(), active.size() * sizeof(uint32_t));
-  // texture atlas + block table [ref scene.rs:172-184]; sRGB8 -> linear table (IEC 61966-2-1
-  // EOTF evaluated in double, rounded once: the same 256 floats the CPU restatement uses)
-  up(g->atlas, s.atlas.texels.data(), s.atlas.texels.size());
-  up(g->tex_blocks, s.atlas.gpu_blocks.data(), s.atlas.gpu_blocks.size() * sizeof(uint32_t));
-  float lut[256];
-  for (int i = 0; i < 256; ++i) {
-    const double c = i / 255.0;
-    lut[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
-  }
-  up(g->srgb_lut, lut, sizeof(lut));
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  uint32_t n_active = 0;
+  if (e == cudaSuccess) e = upload_shading_data(g, s, st, &n_active);  // synchronises
   if (e != cudaSuccess) {
     delete g;
     return fail(e == cudaErrorMemoryAllocation ? LP_ERR_OOM : LP_ERR_CUDA, cudaGetErrorString(e));
   }
-  SceneDev &sc = g->sc;
-  sc.nodes = g->nodes.ptr;
-  sc.tris = g->tris.ptr;
-  sc.instances = g->instances.ptr;
-  sc.vertices = g->vertices.ptr;
-  sc.indices = g->indices.ptr;
-  sc.materials = g->materials.ptr;
-  sc.emission = g->emission.ptr;
-  sc.lights = g->lights.ptr;
-  sc.active_lights = g->active_lights.ptr;
-  sc.n_active_lights = (uint32_t)active.size();
-  sc.n_materials = (uint32_t)s.materials.size();
-  sc.tlas_root = s.gpu_tlas_root;
-  sc.nodes4 = g->nodes4.ptr;
-  sc.nodes4h = g->nodes4h.ptr;
-  sc.tlas_root4 = s.gpu_tlas_root4;
-  sc.atlas = g->atlas.ptr;
-  sc.tex_blocks = g->tex_blocks.ptr;
-  sc.srgb_lut = g->srgb_lut.ptr;
-  sc.atlas_size = s.atlas.size;
-  sc.n_textures = (uint32_t)s.atlas.blocks.size();
-  g->node_bytes = s.gpu_nodes.size() * sizeof(GpuNode) + s.gpu_nodes4.size() * sizeof(GpuNode4);
-  g->tri_bytes = s.primitives.size() * 64;
-  g->total_bytes = g->node_bytes + g->tri_bytes + s.gpu_instances.size() * sizeof(GpuInstance) +
-                   s.vertices.size() * sizeof(lp_vertex) + s.indices.size() * 4 +
-                   s.materials.size() * 48 + s.lights.size() * sizeof(lp_light) +
-                   s.atlas.texels.size() + s.atlas.gpu_blocks.size() * 4;
+  bind_scene(g, s, n_active, s.gpu_nodes.size(), s.gpu_nodes4.size());
+  g->sc.tlas_root = s.gpu_tlas_root;
+  g->sc.tlas_root4 = s.gpu_tlas_root4;
   g->max_depth = s.gpu_max_depth;
   g->half_boxes_ok = s.half_boxes_ok;
   g->layout_version = s.layout_version;
-  g->n_instances = s.gpu_instances.size();
-  g->n_materials = s.materials.size();
-  g->n_lights = s.lights.size();
   *out = g;
   return LP_OK;
 }
@@ -680,6 +666,7 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
 LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene) {
   if (!sg || !scene) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   Scene &s = scene_of(scene);
+  if (sg->lbvh) return lbvh_update_instances(sg, s);  // TLAS rebuilt on the device
   try {
     s.build_derived();
   } catch (const std::exception &e) {
@@ -706,22 +693,8 @@ LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene
                              cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaMemcpyAsync(sg->instances.ptr, s.gpu_instances.data(),
                              s.gpu_instances.size() * sizeof(GpuInstance), cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaMemcpyAsync(sg->materials.ptr, s.materials.data(),
-                             s.materials.size() * sizeof(lp_material), cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaMemcpyAsync(sg->emission.ptr, s.emission.data(), s.emission.size() * 16,
-                             cudaMemcpyHostToDevice, st));
-  std::vector<uint32_t> active;
-  for (uint32_t i = 0; i < s.lights.size(); ++i)
-    if (s.lights[i].intensity > 0.0f) active.push_back(i);
-  if (active.size() > sg->active_lights.count)
-    return fail(LP_ERR_INVALID_ARG, "more active lights than at upload: create a new SceneGPU");
-  CUDA_CHECK(cudaMemcpyAsync(sg->lights.ptr, s.lights.data(), s.lights.size() * sizeof(lp_light),
-                             cudaMemcpyHostToDevice, st));
-  if (!active.empty())
-    CUDA_CHECK(cudaMemcpyAsync(sg->active_lights.ptr, active.data(), active.size() * 4,
-                               cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
-  sg->sc.n_active_lights = (uint32_t)active.size();
+  const lp_status rs = refresh_small_tables(sg, s, st);  // synchronises
+  if (rs != LP_OK) return rs;
   sg->sc.tlas_root = s.gpu_tlas_root;
   sg->sc.tlas_root4 = s.gpu_tlas_root4;
   sg->max_depth = s.gpu_max_depth;
