@@ -300,6 +300,15 @@ LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene
  * lp_scene_gpu_update_instances on it rebuilds the TLAS on the device as well. */
 LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp_device *dev,
                                                   lp_scene_gpu **out);
+/* Extension (tests, tools): copies one of a SceneGPU's DEVICE arrays back to the host.
+ * which: 0 = 64-byte 2-wide nodes, 1 = 128-byte 4-wide nodes (fp32 boxes), 2 = 64-byte 4-wide
+ * nodes (fp16 boxes), 3 = 64-byte triangles, 4 = 128-byte instance records.  dst may be NULL
+ * to query the size; *out_bytes receives the array's size in bytes.  Synchronises. */
+LP_API lp_status lp_scene_gpu_read_array(lp_scene_gpu *sg, int which, void *dst, size_t cap_bytes,
+                                         size_t *out_bytes);
+/* Extension: child references of the TLAS root in the 2-wide and the 4-wide node arrays. */
+LP_API lp_status lp_scene_gpu_roots(const lp_scene_gpu *sg, uint32_t *tlas_root,
+                                    uint32_t *tlas_root4);
 LP_API lp_status lp_scene_gpu_destroy(lp_scene_gpu *sg);
 /* Size report used by the app's log [ref app.rs:216-236]. */
 LP_API lp_status lp_scene_gpu_stats(const lp_scene_gpu *sg, size_t *node_bytes, size_t *tri_bytes,

@@ -123,6 +123,8 @@ _PROTOTYPES = {
     "lp_scene_gpu_new_from_scene": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "lp_scene_gpu_update_instances": (C.c_int, [_vp, _vp]),
     "lp_scene_gpu_new_from_scene_lbvh": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "lp_scene_gpu_read_array": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "lp_scene_gpu_roots": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "lp_scene_gpu_destroy": (C.c_int, [_vp]),
     "lp_scene_gpu_stats": (C.c_int, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_size_t), c_u32_p]),

@@ -363,6 +363,30 @@ class SceneGPU:
         re-uploads the TLAS region + instance records only."""
         _check(_ffi.lib().lp_scene_gpu_update_instances(self._h, (scene or self.scene)._h))
 
+    DEVICE_ARRAYS = {"nodes2": (0, _ARRAY_DTYPES[_ffi.SCENE_GPU_NODES]),
+                     "nodes4": (1, _ARRAY_DTYPES[_ffi.SCENE_GPU_NODES4]),
+                     "nodes4h": (2, np.dtype([("box", "<f2", (6, 4)), ("child", "<u4", 4)])),
+                     "tris": (3, np.dtype([("v0", "<f4", 3), ("id", "<u4"), ("v1", "<f4", 4),
+                                           ("v2", "<f4", 4), ("pad", "<f4", 4)])),
+                     "instances": (4, _ARRAY_DTYPES[_ffi.SCENE_GPU_INSTANCES])}
+
+    def device_array(self, name: str) -> np.ndarray:
+        """Copy of one of the DEVICE arrays (tests, tools): nodes2 / nodes4 / nodes4h / tris /
+        instances."""
+        which, dt = self.DEVICE_ARRAYS[name]
+        n = C.c_size_t()
+        _check(_ffi.lib().lp_scene_gpu_read_array(self._h, which, None, 0, C.byref(n)))
+        out = np.zeros(n.value // dt.itemsize, dt)
+        _check(_ffi.lib().lp_scene_gpu_read_array(self._h, which, out.ctypes.data_as(C.c_void_p),
+                                                  out.nbytes, C.byref(n)))
+        return out
+
+    def roots(self):
+        """(tlas_root, tlas_root4): child references of the TLAS root in both node arrays."""
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(_ffi.lib().lp_scene_gpu_roots(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def stats(self) -> dict:
         a, b, c, d = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_uint32()
         _check(_ffi.lib().lp_scene_gpu_stats(self._h, C.byref(a), C.byref(b), C.byref(c),

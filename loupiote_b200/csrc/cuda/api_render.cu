@@ -702,6 +702,35 @@ LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene
   return LP_OK;
 }
 
+LP_API lp_status lp_scene_gpu_read_array(lp_scene_gpu *sg, int which, void *dst, size_t cap_bytes,
+                                         size_t *out_bytes) {
+  if (!sg || !out_bytes) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  const DevBuf<float4> *buf = nullptr;
+  switch (which) {
+    case 0: buf = &sg->nodes; break;
+    case 1: buf = &sg->nodes4; break;
+    case 2: buf = &sg->nodes4h; break;
+    case 3: buf = &sg->tris; break;
+    case 4: buf = &sg->instances; break;
+    default: return fail(LP_ERR_INVALID_ARG, "unknown array");
+  }
+  *out_bytes = buf->count * sizeof(float4);
+  if (!dst) return LP_OK;
+  if (cap_bytes < *out_bytes) return fail(LP_ERR_INVALID_ARG, "buffer too small");
+  CUDA_CHECK(cudaSetDevice(sg->dev->ordinal));
+  CUDA_CHECK(cudaStreamSynchronize(sg->dev->stream));
+  CUDA_CHECK(cudaMemcpy(dst, buf->ptr, *out_bytes, cudaMemcpyDeviceToHost));
+  return LP_OK;
+}
+
+LP_API lp_status lp_scene_gpu_roots(const lp_scene_gpu *sg, uint32_t *tlas_root,
+                                    uint32_t *tlas_root4) {
+  if (!sg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (tlas_root) *tlas_root = sg->sc.tlas_root;
+  if (tlas_root4) *tlas_root4 = sg->sc.tlas_root4;
+  return LP_OK;
+}
+
 LP_API lp_status lp_scene_gpu_destroy(lp_scene_gpu *sg) {
   if (sg) cudaSetDevice(sg->dev->ordinal);
   delete sg;

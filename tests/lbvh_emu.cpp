@@ -95,7 +95,11 @@ struct Workspace {
 
 }  // namespace
 
+static uint32_t g_max_leaf = 4;
+
 extern "C" {
+
+void lbvh_emu_set_max_leaf(uint32_t n) { g_max_leaf = n; }
 
 // Builds every BLAS of a scene.  seg arrays have n_segments entries; nodes2 / nodes4 / tris
 // are caller-allocated with the given capacities (in nodes / triangles).  out[0] = 2-wide
@@ -110,7 +114,7 @@ int lbvh_emu_build_blas(const float *vertices, const uint32_t *indices, const ui
   Workspace w;
   w.init(counts, prim_base, n_segments);
   Job &j = w.job;
-  j.max_leaf = 4;
+  j.max_leaf = g_max_leaf;
   j.tlas = 0;
   j.base2 = base2;
   j.base4 = base4;

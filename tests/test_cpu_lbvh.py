@@ -127,10 +127,14 @@ def walk2(b, ref, seen):
 
 
 def check_blas(b):
+    """`b` = the builder's outputs (emulated, or read back from the device: then root_box /
+    depth4 are None and only the BLASes some instance uses have a known root)."""
     assert b["rc"] == 0
     deepest = 0
     for e, ent in enumerate(b["entries"]):
         n, base = int(ent["primitive_count"]), int(ent["primitive_offset"])
+        if b.get("known_roots") is not None and e not in b["known_roots"]:
+            continue
         if n == 0:
             assert b["root2"][e] == NONE and b["root4"][e] == NONE
             continue
@@ -138,8 +142,9 @@ def check_blas(b):
             seen = []
             res = walk(b, int(root[e]), seen)
             assert sorted(seen) == list(range(base, base + n)), "every triangle exactly once"
-            assert np.array_equal(res[0], b["root_box"][e, :3])
-            assert np.array_equal(res[1], b["root_box"][e, 3:])
+            if b.get("root_box") is not None:
+                assert np.array_equal(res[0], b["root_box"][e, :3])
+                assert np.array_equal(res[1], b["root_box"][e, 3:])
             if walk is walk4:
                 deepest = max(deepest, res[2])
         # the triangle records are the BLAS's triangles, each once, with their original index
@@ -151,7 +156,8 @@ def check_blas(b):
         assert np.array_equal(t["v1"][:, :3], pos[ix[t["id"], 1]])
         assert np.array_equal(t["v2"][:, :3], pos[ix[t["id"], 2]])
         assert not t["v1"][:, 3].any() and not t["v2"][:, 3].any() and not t["pad"].any()
-    assert deepest == b["depth4"]
+    if b.get("depth4") is not None:
+        assert deepest == b["depth4"]
     return deepest
 
 
