@@ -232,6 +232,14 @@ LP_API lp_status lp_scene_push_light(lp_scene *scene, const lp_light *light, uin
 LP_API lp_status lp_scene_push_image(lp_scene *scene, const uint8_t *rgba8, uint32_t width,
                                      uint32_t height, uint32_t *out_index);
 
+/* Extension: with defer != 0, lp_scene_add_bvh[_indexed] and the loaders record vertices,
+ * indices and the BLAS entry but leave the host binned-SAH build [ref BLASArray::add_bvh behind
+ * gltf.rs:97-105] to the first call that needs the canonical tree (lp_scene_get_array of
+ * entries / nodes / primitives / derived arrays, lp_scene_gpu_new_from_scene).  A SceneGPU built
+ * on the device (lp_scene_gpu_new_from_scene_lbvh) never triggers it.  defer == 0 builds what is
+ * pending.  Results are identical to the eager build. */
+LP_API lp_status lp_scene_set_deferred_build(lp_scene *scene, int defer);
+
 /* Read access to the pub fields of Scene / BLASArray [ref scene.rs:30-35,43-49].
  * Pointers stay valid until the next mutating call on the scene. */
 typedef enum lp_scene_array {

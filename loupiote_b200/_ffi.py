@@ -121,6 +121,7 @@ _PROTOTYPES = {
     "lp_load_gltf_path": (C.c_int, [C.c_char_p, _vp]),
     "lp_load_binary_from_path": (C.c_int, [C.c_char_p, _vp]),
     "lp_scene_gpu_new_from_scene": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "lp_scene_set_deferred_build": (C.c_int, [_vp, C.c_int]),
     "lp_scene_gpu_update_instances": (C.c_int, [_vp, _vp]),
     "lp_scene_gpu_new_from_scene_lbvh": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "lp_scene_gpu_read_array": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),

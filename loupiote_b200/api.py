@@ -305,6 +305,11 @@ class Scene:
         _check(_ffi.lib().lp_scene_push_image(self._h, img.ctypes.data, w, h, C.byref(out)))
         return out.value
 
+    def set_deferred_build(self, flag: bool) -> None:
+        """True: add_bvh / the loaders leave the host SAH build to the first use of the
+        canonical tree (a device-built SceneGPU never needs it); False builds what is pending."""
+        _check(_ffi.lib().lp_scene_set_deferred_build(self._h, int(bool(flag))))
+
     def set_instance_transform(self, instance_index: int, model_to_world) -> None:
         m = _mat4(model_to_world)
         _check(_ffi.lib().lp_scene_set_instance_transform(self._h, instance_index,

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -414,7 +415,9 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
       (e = cudaMemsetAsync(g->tris.ptr, 0, s.primitives.size() * 64, st)) != cudaSuccess)
     return bail(cuda_fail(e, "BLAS inputs"));
   Job &j = w.job;
-  j.max_leaf = 4;
+  // LP_LBVH_MAX_LEAF (tuning knob, 1..4): triangles per leaf; measured in profiles/r01_v7_lbvh_*
+  const char *ml = std::getenv("LP_LBVH_MAX_LEAF");
+  j.max_leaf = ml ? (uint32_t)std::min(4, std::max(1, std::atoi(ml))) : 4u;
   j.tlas = 0;
   BlasInput in;
   in.vertices = g->vertices.ptr;

@@ -130,6 +130,8 @@ LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const
   Scene &s = scene->s;
   size_t es = 0;
   try {
+    if (which == LP_SCENE_ENTRIES || which == LP_SCENE_NODES || which == LP_SCENE_PRIMITIVES)
+      s.ensure_host_bvh();  // trees deferred by lp_scene_set_deferred_build
     switch (which) {
       case LP_SCENE_ENTRIES: *out_ptr = s.entries.data(); *out_count = s.entries.size(); es = sizeof(lp_blas_entry); break;
       case LP_SCENE_NODES: *out_ptr = s.nodes.data(); *out_count = s.nodes.size(); es = sizeof(lp_bvh_node); break;
@@ -152,6 +154,13 @@ LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const
     return fail(LP_ERR_ACCEL_BUILD, e.what());
   }
   if (out_elem_size) *out_elem_size = es;
+  return LP_OK;
+}
+
+LP_API lp_status lp_scene_set_deferred_build(lp_scene *scene, int defer) {
+  if (!scene) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  scene->s.defer_host_bvh = defer != 0;
+  if (!defer) LP_TRY(scene->s.ensure_host_bvh();)
   return LP_OK;
 }
 

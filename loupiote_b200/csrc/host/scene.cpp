@@ -96,39 +96,55 @@ uint32_t Scene::add_bvh(const void *positions, size_t pstride, const void *norma
   indices.reserve(indices.size() + tri_count * 3);
   for (size_t i = 0; i < tri_count * 3; ++i) indices.push_back(idx ? idx[i] : (uint32_t)i);
 
-  std::vector<BuildBox> boxes(tri_count);
-  const lp_vertex *vb = vertices.data() + e.vertex_offset;
-  const uint32_t *ib = indices.data() + e.index_offset;
-  for (size_t t = 0; t < tri_count; ++t) {
-    BuildBox b;
-    for (int a = 0; a < 3; ++a) {
-      const float p0 = vb[ib[3 * t]].position[a], p1 = vb[ib[3 * t + 1]].position[a],
-                  p2 = vb[ib[3 * t + 2]].position[a];
-      b.lo[a] = std::min(p0, std::min(p1, p2));
-      b.hi[a] = std::max(p0, std::max(p1, p2));
-      if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a]))
-        throw std::invalid_argument("non-finite vertex position");
-    }
-    boxes[t] = b;
-  }
-  std::vector<lp_bvh_node> tree;
-  std::vector<uint32_t> perm;
-  build_bvh2(boxes, 4, tree, perm);
-  e.node_count = (uint32_t)tree.size();
-  nodes.insert(nodes.end(), tree.begin(), tree.end());
-  primitives.reserve(primitives.size() + tri_count);
-  for (size_t k = 0; k < tri_count; ++k) {
-    const uint32_t t = perm[k];
-    lp_bvh_primitive p{};
-    std::memcpy(p.v0, vb[ib[3 * t]].position, 12);
-    std::memcpy(p.v1, vb[ib[3 * t + 1]].position, 12);
-    std::memcpy(p.v2, vb[ib[3 * t + 2]].position, 12);
-    std::memcpy(&p.v0[3], &t, 4);
-    primitives.push_back(p);
-  }
+  // the triangles' slots exist from now on (primitive_offset is final); their content and the
+  // tree follow from build_entry_tree, now or -- deferred -- on first use
+  primitives.resize(primitives.size() + tri_count, lp_bvh_primitive{});
+  e.node_offset = 0;
+  e.node_count = 0;
   entries.push_back(e);
+  pending_bvh.push_back((uint32_t)entries.size() - 1);
   derived_dirty = true;
+  if (!defer_host_bvh) ensure_host_bvh();
   return (uint32_t)entries.size() - 1;
+}
+
+// Binned-SAH tree of every entry add_bvh left pending, in add order (node offsets are the
+// running size of `nodes`, exactly as if each tree had been built inside add_bvh).
+void Scene::ensure_host_bvh() {
+  for (const uint32_t ei : pending_bvh) {
+    lp_blas_entry &e = entries[ei];
+    const size_t tri_count = e.primitive_count;
+    std::vector<BuildBox> boxes(tri_count);
+    const lp_vertex *vb = vertices.data() + e.vertex_offset;
+    const uint32_t *ib = indices.data() + e.index_offset;
+    for (size_t t = 0; t < tri_count; ++t) {
+      BuildBox b;
+      for (int a = 0; a < 3; ++a) {
+        const float p0 = vb[ib[3 * t]].position[a], p1 = vb[ib[3 * t + 1]].position[a],
+                    p2 = vb[ib[3 * t + 2]].position[a];
+        b.lo[a] = std::min(p0, std::min(p1, p2));
+        b.hi[a] = std::max(p0, std::max(p1, p2));
+      }
+      boxes[t] = b;
+    }
+    std::vector<lp_bvh_node> tree;
+    std::vector<uint32_t> perm;
+    build_bvh2(boxes, 4, tree, perm);
+    e.node_offset = (uint32_t)nodes.size();
+    e.node_count = (uint32_t)tree.size();
+    nodes.insert(nodes.end(), tree.begin(), tree.end());
+    for (size_t k = 0; k < tri_count; ++k) {
+      const uint32_t t = perm[k];
+      lp_bvh_primitive p{};
+      std::memcpy(p.v0, vb[ib[3 * t]].position, 12);
+      std::memcpy(p.v1, vb[ib[3 * t + 1]].position, 12);
+      std::memcpy(p.v2, vb[ib[3 * t + 2]].position, 12);
+      std::memcpy(&p.v0[3], &t, 4);
+      primitives[e.primitive_offset + k] = p;
+    }
+  }
+  if (!pending_bvh.empty()) derived_dirty = true;
+  pending_bvh.clear();
 }
 
 void Scene::add_instance(uint32_t blas, const float m[16], uint32_t material) {
@@ -515,6 +531,7 @@ void Scene::build_tlas() {
 // moving an instance (set_instance_transform) rebuilds and re-uploads the TLAS region and the
 // instance records only: `layout_version` tells a SceneGPU whether its BLAS copy is still valid.
 void Scene::build_derived() {
+  ensure_host_bvh();
   if (!derived_dirty) {
     if (instances_dirty) {
       build_tlas();

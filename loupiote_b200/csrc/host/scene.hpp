@@ -118,6 +118,12 @@ struct Scene {
   uint64_t layout_version = 0;  // bumped by every full rebuild (geometry / counts changed)
   bool derived_dirty = true;
   bool instances_dirty = false;  // only instance transforms changed since the last build
+  // Deferred host builds (lp_scene_set_deferred_build): add_bvh records vertices, indices and
+  // the entry, and leaves the binned-SAH tree to ensure_host_bvh() -- which everything that
+  // reads nodes / primitives calls first.  A SceneGPU built on the device
+  // (lp_scene_gpu_new_from_scene_lbvh) never needs them.
+  bool defer_host_bvh = false;
+  std::vector<uint32_t> pending_bvh;  // entries whose tree is not built yet, in add order
 
   Scene();
   uint32_t add_bvh(const void *positions, size_t pstride, const void *normals, size_t nstride,
@@ -126,6 +132,7 @@ struct Scene {
   void add_instance(uint32_t blas, const float m[16], uint32_t material);
   void set_instance_transform(uint32_t instance, const float m[16]);
   void build_derived();  // TLAS + GPU layout (full, or TLAS-only after set_instance_transform)
+  void ensure_host_bvh();  // builds the trees add_bvh deferred
   void build_tlas();
 };
 

@@ -104,11 +104,13 @@ def cornell_box() -> dict:
     return {"scene": scene, "view": view, "env_color": (0.0, 0.0, 0.0), "name": "cornell-box"}
 
 
-def spheres_1m(grid: int = 7, subdivisions: int = 5) -> dict:
+def spheres_1m(grid: int = 7, subdivisions: int = 5, deferred_build: bool = False) -> dict:
     """BASELINE config 3: grid x grid displaced icospheres (unique BLAS each) + ground quad.
-    Defaults give 49 * 20,480 + 2 = 1,003,522 triangles, 50 BLAS, 50 instances."""
+    Defaults give 49 * 20,480 + 2 = 1,003,522 triangles, 50 BLAS, 50 instances.
+    deferred_build: leave the host SAH trees unbuilt (Scene.set_deferred_build)."""
     rng = SplitMix64(SCENE_SEED)
     scene = Scene()
+    scene.set_deferred_build(deferred_build)
     base_v, base_f = icosphere(subdivisions)
     nv = base_v.shape[0]
     spacing = 2.5

@@ -365,3 +365,35 @@ def test_instance_move_rebuilds_only_the_tlas_region():
     interior = refs[(refs & 0x80000000) == 0]
     interior = interior[interior != 0x7FFFFFFF]
     assert interior.max() < len(n4)
+
+
+def test_deferred_host_build_equals_the_eager_one():
+    """lp_scene_set_deferred_build: add_bvh leaves the SAH trees to the first use of the
+    canonical arrays; entries, nodes, primitives and the derived GPU layouts then equal an
+    eagerly built scene's byte for byte."""
+    import time
+    from loupiote_b200 import scenes
+    t0 = time.perf_counter()
+    eager = scenes.spheres_1m(grid=3, subdivisions=4)["scene"]
+    t_eager = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lazy = scenes.spheres_1m(grid=3, subdivisions=4, deferred_build=True)["scene"]
+    t_lazy = time.perf_counter() - t0
+    assert t_lazy < t_eager  # the SAH build is the bulk of add_bvh
+    # arrays that do not need the trees are there at once
+    for which in (_ffi.SCENE_VERTICES, _ffi.SCENE_INDICES, _ffi.SCENE_INSTANCES,
+                  _ffi.SCENE_MATERIALS):
+        assert lazy.array(which).tobytes() == eager.array(which).tobytes()
+    # ... and the first use of a canonical array builds every pending tree
+    for which in (_ffi.SCENE_PRIMITIVES, _ffi.SCENE_ENTRIES, _ffi.SCENE_NODES,
+                  _ffi.SCENE_TLAS_NODES, _ffi.SCENE_GPU_NODES, _ffi.SCENE_GPU_NODES4,
+                  _ffi.SCENE_GPU_INSTANCES):
+        assert lazy.array(which).tobytes() == eager.array(which).tobytes(), which
+    # adding to a built scene while deferred, then turning deferral off
+    pos = np.random.default_rng(2).random((30, 3), np.float32)
+    for s in (eager, lazy):
+        s.blas.add_bvh(pos)
+    assert lazy.array(_ffi.SCENE_VERTICES).tobytes() == eager.array(_ffi.SCENE_VERTICES).tobytes()
+    lazy.set_deferred_build(False)
+    assert lazy.array(_ffi.SCENE_NODES).tobytes() == eager.array(_ffi.SCENE_NODES).tobytes()
+    assert lazy.array(_ffi.SCENE_ENTRIES).tobytes() == eager.array(_ffi.SCENE_ENTRIES).tobytes()

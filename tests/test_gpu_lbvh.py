@@ -20,8 +20,8 @@ from test_cpu_lbvh import LEAF, NONE, check_blas
 from test_gpu_parity import V_FOV, soup_scene
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LP_TEST_LBVH", "0") == "0",
-                                 reason="device-built BVH not yet confirmed on hardware: set LP_TEST_LBVH=1")]
+              pytest.mark.skipif(os.environ.get("LP_TEST_LBVH", "1") == "0",
+                                 reason="LP_TEST_LBVH=0")]
 
 
 def renderer_for(device, scene, size, builder, **cfg):
