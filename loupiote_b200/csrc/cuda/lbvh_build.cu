@@ -415,9 +415,11 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
       (e = cudaMemsetAsync(g->tris.ptr, 0, s.primitives.size() * 64, st)) != cudaSuccess)
     return bail(cuda_fail(e, "BLAS inputs"));
   Job &j = w.job;
-  // LP_LBVH_MAX_LEAF (tuning knob, 1..4): triangles per leaf; measured in profiles/r01_v7_lbvh_*
+  // triangles per leaf.  Measured on config 3 (profiles/r01_v7_lbvh_bench.jsonl): 4 / 3 / 2 =
+  // 4391 / 4486 / 4555 Mrays/s (host SAH tree: 4880): the pool kernels test a whole leaf per
+  // scheduling round, so smaller leaves waste fewer tests.  LP_LBVH_MAX_LEAF (1..4) overrides.
   const char *ml = std::getenv("LP_LBVH_MAX_LEAF");
-  j.max_leaf = ml ? (uint32_t)std::min(4, std::max(1, std::atoi(ml))) : 4u;
+  j.max_leaf = ml ? (uint32_t)std::min(4, std::max(1, std::atoi(ml))) : 2u;
   j.tlas = 0;
   BlasInput in;
   in.vertices = g->vertices.ptr;

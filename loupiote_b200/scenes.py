@@ -138,12 +138,13 @@ def spheres_1m(grid: int = 7, subdivisions: int = 5, deferred_build: bool = Fals
     return {"scene": scene, "view": view, "env_color": ENV_COLOR, "name": "spheres-1M"}
 
 
-def lattice_10m(n: int = 5, subdivisions: int = 6) -> dict:
+def lattice_10m(n: int = 5, subdivisions: int = 6, deferred_build: bool = False) -> dict:
     """BASELINE config 4: ONE icosphere BLAS (81,920 triangles at subdivision 6) instanced on
     an n^3 lattice with per-instance rotation + uniform scale: 125 * 81,920 = 10,240,000
     instanced triangles, + ground."""
     rng = SplitMix64(SCENE_SEED)
     scene = Scene()
+    scene.set_deferred_build(deferred_build)
     v, f = icosphere(subdivisions)
     blas = scene.blas.add_bvh_indexed(v.astype(np.float32), f.reshape(-1), v.astype(np.float32))
     spacing = 2.6

@@ -34,8 +34,9 @@ TRI = np.dtype([("v0", "<f4", 3), ("id", "<u4"), ("v1", "<f4", 4), ("v2", "<f4",
                 ("pad", "<f4", 4)])
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=[2, 4], ids=["leaf2", "leaf4"])
+def emu(request):
+    """The emulated builder with leaves of <= 2 (the device default) or <= 4 triangles."""
     OUT.parent.mkdir(exist_ok=True)
     h = hashlib.sha256(SRC.read_bytes() + CORE.read_bytes()).hexdigest()
     stamp = OUT.with_suffix(".stamp")
@@ -46,6 +47,8 @@ def emu():
     lib = C.CDLL(str(OUT))
     lib.lbvh_emu_morton.restype = C.c_uint64
     lib.lbvh_emu_morton.argtypes = [C.c_float] * 3
+    lib.lbvh_emu_set_max_leaf(C.c_uint32(request.param))
+    lib.max_leaf = request.param
     return lib
 
 
@@ -75,6 +78,7 @@ def build_blas(emu, scene, base2=3, base4=5):
                                  _p(nodes2), C.c_uint32(cap), _p(nodes4), C.c_uint32(cap), _p(tris),
                                  _p(root2), _p(root4), _p(root_box), _p(out))
     return dict(rc=rc, nodes2=nodes2, nodes4=nodes4, tris=tris, root2=root2, root4=root4,
+                max_leaf=emu.max_leaf,
                 root_box=root_box, n2=int(out[0]), n4=int(out[1]), depth4=int(out[2]),
                 entries=entries, vertices=vertices, indices=indices, base2=base2, base4=base4)
 
@@ -89,7 +93,7 @@ def walk4(b, ref, seen, depth=1):
     """(lo, hi, depth) of the subtree behind child reference `ref` of the 4-wide array."""
     if ref & LEAF:
         count, first = ((ref >> 28) & 7) + 1, ref & 0x0FFFFFFF
-        assert count <= 4
+        assert count <= b.get("max_leaf", 4)
         seen.extend(range(first, first + count))
         return (*_tri_bounds(b["tris"], first, count), depth - 1)
     assert b["base4"] <= ref < b["base4"] + b["n4"], ref
@@ -179,9 +183,9 @@ def test_cornell_box_every_blas_is_a_single_leaf_or_tiny_tree(emu):
     c = scenes.cornell_box()
     b = build_blas(emu, c["scene"])
     check_blas(b)
-    # 5 meshes of 2..12 triangles; <= 4 triangles => the root is a leaf
+    # 5 meshes of 2..12 triangles; <= max_leaf triangles => the root is a leaf
     for e, ent in enumerate(b["entries"]):
-        if 0 < ent["primitive_count"] <= 4:
+        if 0 < ent["primitive_count"] <= emu.max_leaf:
             assert b["root4"][e] & LEAF and b["root4"][e] == b["root2"][e]
 
 
@@ -192,10 +196,10 @@ def test_icosphere_tree_is_valid_and_shallow(emu):
     s.blas.add_bvh_indexed(pos * 0.25 + 3.0, idx[: 3 * 777])
     b = build_blas(emu, s)
     depth = check_blas(b)
-    assert 4 <= depth <= 14, depth            # ~log4(5120 / 4) + slack for the Morton splits
+    assert 4 <= depth <= 14, depth            # ~log4(5120 / leaf) + slack for the Morton splits
     assert b["n4"] < b["n2"] <= 5120 + 777    # the collapse removes levels
-    # node counts of a tree with leaves of <= 4: at least n/4 leaves => >= n/4 - 1 interior
-    assert b["n2"] >= (5120 + 777) // 4 - 2
+    # a tree with leaves of <= L triangles has >= n/L leaves => >= n/L - 1 interior nodes
+    assert b["n2"] >= (5120 + 777) // emu.max_leaf - 2
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 33])
@@ -205,7 +209,7 @@ def test_small_counts(emu, n):
     s.blas.add_bvh(rng.random((3 * n, 3), np.float32) * 4 - 2)
     b = build_blas(emu, s, base2=0, base4=0)
     check_blas(b)
-    if n <= 4:
+    if n <= emu.max_leaf:
         assert b["n2"] == 0 and b["n4"] == 0 and b["depth4"] == 0
 
 
@@ -221,7 +225,7 @@ def test_duplicate_and_degenerate_triangles(emu):
     s.blas.add_bvh(pts)
     b = build_blas(emu, s)
     depth = check_blas(b)
-    assert depth <= 5  # 100 equal codes: positions split evenly => depth log4(100 / 4) + 1
+    assert depth <= 5  # 100 equal codes: positions split evenly => depth ~ log4(100 / leaf) + 1
 
 
 def test_clustered_soup_stays_within_the_stack_limit(emu):
