@@ -177,20 +177,23 @@ struct DeviceExec {
   }
   uint32_t read(const uint32_t *p) {
     uint32_t v = 0;
-    if (err != cudaSuccess) return 0;
-    note(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, st));
-    note(cudaStreamSynchronize(st));
+    read_n(p, 1, &v);
     return v;
+  }
+  void read_n(const uint32_t *p, uint32_t n, uint32_t *out) {
+    if (err != cudaSuccess) return;
+    note(cudaMemcpyAsync(out, p, 4ull * n, cudaMemcpyDeviceToHost, st));
+    note(cudaStreamSynchronize(st));
   }
 };
 
-// every work array of one Job, on the device
+// Every work array of one Job, carved out of ONE device allocation (a build is a few dozen
+// arrays; one cudaMalloc / cudaFree instead of thirty keeps the build's fixed cost down).
 struct Workspace {
-  DevBuf<Segment> segs;
-  DevBuf<uint32_t> slot_seg, vals, vals_tmp, left, right, parent, leaf_parent, range_first,
-      range_last, visits, big, idx2, frontier, level_count, n_nodes4, root2, root4, tlas_ids;
-  DevBuf<uint64_t> keys, keys_tmp;
-  DevBuf<float4> seg_lo, seg_hi, prim_lo, prim_hi, leaf_lo, leaf_hi, node_lo, node_hi;
+  DevBuf<uint8_t> arena;
+  uint32_t *tlas_ids = nullptr, *root2 = nullptr, *root4 = nullptr, *vals_tmp = nullptr;
+  uint64_t *keys_tmp = nullptr;
+  float4 *seg_lo = nullptr, *seg_hi = nullptr;
   Job job;
 
   cudaError_t init(const std::vector<Segment> &host_segs, cudaStream_t st) {
@@ -200,45 +203,71 @@ struct Workspace {
       host_slot_seg.insert(host_slot_seg.end(), host_segs[s].count, s);
       n += host_segs[s].count;
     }
-    cudaError_t e = cudaSuccess;
-    auto a = [&](auto &buf, size_t count) {
-      if (e == cudaSuccess) e = buf.alloc(count);
-    };
     const size_t m = std::max<uint32_t>(n, 1u), ns = std::max<size_t>(host_segs.size(), 1);
-    if (e == cudaSuccess) e = segs.upload(host_segs.data(), host_segs.size(), st);
-    if (e == cudaSuccess) e = slot_seg.upload(host_slot_seg.data(), host_slot_seg.size(), st);
-    for (auto *b : {&vals, &vals_tmp, &left, &right, &parent, &leaf_parent, &range_first,
-                    &range_last, &visits, &big, &idx2})
-      a(*b, m);
-    a(frontier, 4 * m);
-    a(level_count, kMaxLevels + 1);
-    a(n_nodes4, 1);
-    a(root2, ns);
-    a(root4, ns);
-    a(keys, m);
-    a(keys_tmp, m);
-    for (auto *b : {&prim_lo, &prim_hi, &leaf_lo, &leaf_hi, &node_lo, &node_hi}) a(*b, m);
-    a(seg_lo, ns);
-    a(seg_hi, ns);
+    // pass 1 sizes the arena, pass 2 hands out the pointers (256-byte aligned)
+    uint8_t *base = nullptr;
+    size_t offset = 0;
+    auto take = [&](size_t bytes) -> void * {
+      void *p = base ? base + offset : nullptr;
+      offset += (bytes + 255) & ~(size_t)255;
+      return p;
+    };
+    Segment *d_segs = nullptr;
+    uint32_t *d_slot_seg = nullptr;
+    Job &j = job;
+    for (int pass = 0; pass < 2; ++pass) {
+      offset = 0;
+      d_segs = (Segment *)take(ns * sizeof(Segment));
+      d_slot_seg = (uint32_t *)take(m * 4);
+      j.vals = (uint32_t *)take(m * 4);
+      vals_tmp = (uint32_t *)take(m * 4);
+      j.left = (uint32_t *)take(m * 4);
+      j.right = (uint32_t *)take(m * 4);
+      j.parent = (uint32_t *)take(m * 4);
+      j.leaf_parent = (uint32_t *)take(m * 4);
+      j.range_first = (uint32_t *)take(m * 4);
+      j.range_last = (uint32_t *)take(m * 4);
+      j.visits = (uint32_t *)take(m * 4);
+      j.big = (uint32_t *)take(m * 4);
+      j.idx2 = (uint32_t *)take(m * 4);
+      tlas_ids = (uint32_t *)take(m * 4);
+      j.frontier = (uint32_t *)take(4 * m * 4);
+      j.level_count = (uint32_t *)take((kMaxLevels + 2) * 4);
+      root2 = (uint32_t *)take(ns * 4);
+      root4 = (uint32_t *)take(ns * 4);
+      j.keys = (uint64_t *)take(m * 8);
+      keys_tmp = (uint64_t *)take(m * 8);
+      j.prim_lo = (float4 *)take(m * 16);
+      j.prim_hi = (float4 *)take(m * 16);
+      j.leaf_lo = (float4 *)take(m * 16);
+      j.leaf_hi = (float4 *)take(m * 16);
+      j.node_lo = (float4 *)take(m * 16);
+      j.node_hi = (float4 *)take(m * 16);
+      seg_lo = (float4 *)take(ns * 16);
+      seg_hi = (float4 *)take(ns * 16);
+      if (pass == 0) {
+        const cudaError_t e = arena.alloc(offset);
+        if (e != cudaSuccess) return e;
+        base = arena.ptr;
+      }
+    }
+    cudaError_t e = cudaSuccess;
+    if (!host_segs.empty())
+      e = cudaMemcpyAsync(d_segs, host_segs.data(), host_segs.size() * sizeof(Segment),
+                          cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n)
+      e = cudaMemcpyAsync(d_slot_seg, host_slot_seg.data(), 4ull * n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host_slot_seg is pageable
     if (e != cudaSuccess) return e;
-    Job &j = job;
     j.n_slots = n;
     j.n_segments = (uint32_t)host_segs.size();
-    j.segs = segs.ptr;
-    j.slot_seg = slot_seg.ptr;
-    j.seg_lo = seg_lo.ptr; j.seg_hi = seg_hi.ptr;
-    j.prim_lo = prim_lo.ptr; j.prim_hi = prim_hi.ptr;
-    j.keys = keys.ptr; j.vals = vals.ptr;
-    j.leaf_lo = leaf_lo.ptr; j.leaf_hi = leaf_hi.ptr;
-    j.left = left.ptr; j.right = right.ptr;
-    j.parent = parent.ptr; j.leaf_parent = leaf_parent.ptr;
-    j.range_first = range_first.ptr; j.range_last = range_last.ptr;
-    j.node_lo = node_lo.ptr; j.node_hi = node_hi.ptr;
-    j.visits = visits.ptr; j.big = big.ptr; j.idx2 = idx2.ptr;
-    j.frontier = frontier.ptr; j.level_count = level_count.ptr;
-    j.n_nodes4 = n_nodes4.ptr;
-    j.root2 = root2.ptr; j.root4 = root4.ptr;
+    j.segs = d_segs;
+    j.slot_seg = d_slot_seg;
+    j.seg_lo = seg_lo;
+    j.seg_hi = seg_hi;
+    j.n_nodes4 = j.level_count + kMaxLevels + 1;
+    j.root2 = root2;
+    j.root4 = root4;
     return cudaSuccess;
   }
 };
@@ -301,14 +330,15 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
   if (e != cudaSuccess) return cuda_fail(e, "TLAS workspace");
   DevBuf<uint32_t> d_blas_of;
   DevBuf<float> d_root_box;
-  if ((e = w.tlas_ids.upload(ids.data(), ids.size(), st)) != cudaSuccess ||
+  if ((!ids.empty() && (e = cudaMemcpyAsync(w.tlas_ids, ids.data(), 4 * ids.size(),
+                                            cudaMemcpyHostToDevice, st)) != cudaSuccess) ||
       (e = d_blas_of.upload(blas_of.data(), blas_of.size(), st)) != cudaSuccess ||
       (e = d_root_box.upload(sg->lbvh_root_box.data(), sg->lbvh_root_box.size(), st)) != cudaSuccess)
     return cuda_fail(e, "TLAS inputs");
   Job &j = w.job;
   j.max_leaf = 1;
   j.tlas = 1;
-  j.tlas_ids = w.tlas_ids.ptr;
+  j.tlas_ids = w.tlas_ids;
   j.base2 = j.base4 = 0;
   j.nodes2 = sg->nodes.ptr;
   j.nodes4 = sg->nodes4.ptr;
@@ -319,7 +349,7 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
   fill_empty_nodes<<<blocks_for(sg->tlas_capacity), 256, 0, st>>>(sg->nodes.ptr, sg->nodes4.ptr,
                                                                   sg->tlas_capacity);
   DeviceExec ex{st, dev->sm_count};
-  const uint32_t n_big = phase_a(ex, j, nullptr, &in, w.keys_tmp.ptr, w.vals_tmp.ptr);
+  const uint32_t n_big = phase_a(ex, j, nullptr, &in, w.keys_tmp, w.vals_tmp);
   if (ex.err != cudaSuccess) return cuda_fail(ex.err, "TLAS build");
   if (n_big > sg->tlas_capacity) return fail(LP_ERR_ACCEL_BUILD, "TLAS larger than its node region");
   uint32_t n4 = 0;
@@ -328,11 +358,11 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
       sg->nodes4.ptr, (uint4 *)sg->nodes4h.ptr, 0u, sg->tlas_capacity);
   uint32_t roots[2] = {kRefNone, kRefNone};
   float box[8] = {0};
-  ex.note(cudaMemcpyAsync(&roots[0], w.root2.ptr, 4, cudaMemcpyDeviceToHost, st));
-  ex.note(cudaMemcpyAsync(&roots[1], w.root4.ptr, 4, cudaMemcpyDeviceToHost, st));
+  ex.note(cudaMemcpyAsync(&roots[0], w.root2, 4, cudaMemcpyDeviceToHost, st));
+  ex.note(cudaMemcpyAsync(&roots[1], w.root4, 4, cudaMemcpyDeviceToHost, st));
   if (!ids.empty()) {
-    ex.note(cudaMemcpyAsync(&box[0], w.seg_lo.ptr, 16, cudaMemcpyDeviceToHost, st));
-    ex.note(cudaMemcpyAsync(&box[4], w.seg_hi.ptr, 16, cudaMemcpyDeviceToHost, st));
+    ex.note(cudaMemcpyAsync(&box[0], w.seg_lo, 16, cudaMemcpyDeviceToHost, st));
+    ex.note(cudaMemcpyAsync(&box[4], w.seg_hi, 16, cudaMemcpyDeviceToHost, st));
   }
   ex.note(cudaStreamSynchronize(st));
   if (ex.err != cudaSuccess) return cuda_fail(ex.err, "TLAS build");
@@ -428,7 +458,7 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
   in.seg_index_offset = d_ioff.ptr;
   in.tris = g->tris.ptr;
   DeviceExec ex{st, dev->sm_count};
-  const uint32_t n_big = phase_a(ex, j, &in, nullptr, w.keys_tmp.ptr, w.vals_tmp.ptr);
+  const uint32_t n_big = phase_a(ex, j, &in, nullptr, w.keys_tmp, w.vals_tmp);
   if (ex.err != cudaSuccess) return bail(cuda_fail(ex.err, "BLAS build"));
 
   // ---- node arrays: [TLAS region | BLAS trees]; n_big bounds the 4-wide count too
@@ -449,11 +479,11 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
   g->lbvh_root4.assign(ne, kRefNone);
   g->lbvh_root_box.assign(6 * ne, 0.f);
   std::vector<float4> lo(ne), hi(ne);
-  ex.note(cudaMemcpyAsync(g->lbvh_root2.data(), w.root2.ptr, 4 * ne, cudaMemcpyDeviceToHost, st));
-  ex.note(cudaMemcpyAsync(g->lbvh_root4.data(), w.root4.ptr, 4 * ne, cudaMemcpyDeviceToHost, st));
+  ex.note(cudaMemcpyAsync(g->lbvh_root2.data(), w.root2, 4 * ne, cudaMemcpyDeviceToHost, st));
+  ex.note(cudaMemcpyAsync(g->lbvh_root4.data(), w.root4, 4 * ne, cudaMemcpyDeviceToHost, st));
   if (n_slots) {
-    ex.note(cudaMemcpyAsync(lo.data(), w.seg_lo.ptr, 16 * ne, cudaMemcpyDeviceToHost, st));
-    ex.note(cudaMemcpyAsync(hi.data(), w.seg_hi.ptr, 16 * ne, cudaMemcpyDeviceToHost, st));
+    ex.note(cudaMemcpyAsync(lo.data(), w.seg_lo, 16 * ne, cudaMemcpyDeviceToHost, st));
+    ex.note(cudaMemcpyAsync(hi.data(), w.seg_hi, 16 * ne, cudaMemcpyDeviceToHost, st));
   }
   ex.note(cudaStreamSynchronize(st));
   if (ex.err != cudaSuccess) return bail(cuda_fail(ex.err, "BLAS build"));

@@ -44,13 +44,14 @@ struct HostExec {
     }
   }
   uint32_t read(const uint32_t *p) { return *p; }
+  void read_n(const uint32_t *p, uint32_t n, uint32_t *out) { std::memcpy(out, p, 4ull * n); }
 };
 
 // owns every work array of a Job
 struct Workspace {
   std::vector<Segment> segs;
   std::vector<uint32_t> slot_seg, vals, left, right, parent, leaf_parent, range_first, range_last,
-      visits, big, idx2, frontier, level_count, n_nodes4, vals_tmp;
+      visits, big, idx2, frontier, level_count, vals_tmp;
   std::vector<uint64_t> keys, keys_tmp;
   std::vector<float4> seg_lo, seg_hi, prim_lo, prim_hi, leaf_lo, leaf_hi, node_lo, node_hi;
   Job job;
@@ -66,8 +67,7 @@ struct Workspace {
                     &visits, &big, &idx2, &vals_tmp})
       v->assign(m, 0xCDCDCDCDu);  // poison: nothing may rely on zero-initialised memory
     frontier.assign(4 * m, 0xCDCDCDCDu);
-    level_count.assign(kMaxLevels + 1, 0xCDCDCDCDu);
-    n_nodes4.assign(1, 0xCDCDCDCDu);
+    level_count.assign(kMaxLevels + 2, 0xCDCDCDCDu);  // + the node counter
     keys.assign(m, 0);
     keys_tmp.assign(m, 0);
     for (auto *v : {&prim_lo, &prim_hi, &leaf_lo, &leaf_hi, &node_lo, &node_hi})
@@ -89,7 +89,7 @@ struct Workspace {
     j.node_lo = node_lo.data(); j.node_hi = node_hi.data();
     j.visits = visits.data(); j.big = big.data(); j.idx2 = idx2.data();
     j.frontier = frontier.data(); j.level_count = level_count.data();
-    j.n_nodes4 = n_nodes4.data();
+    j.n_nodes4 = level_count.data() + kMaxLevels + 1;
   }
 };
 
