@@ -19,8 +19,8 @@ def main(path: str) -> None:
         v *= {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3}.get(row["Metric Unit"], 1.0)
         name = row["Kernel Name"]
         m = re.search(r"(\w+Op)\b", name)  # for_each_kernel<lbvh::XxxOp>
-        short = m.group(1) if m else re.sub(r"^void ", "", name).split("<")[0].split("(")[0]
-        short = short.replace("<unnamed>::", "")
+        plain = re.sub(r"^void ", "", name).replace("<unnamed>::", "")
+        short = m.group(1) if m else plain.split("<")[0].split("(")[0]
         a = agg.setdefault(short, [0, 0.0])
         a[0] += 1
         a[1] += v
