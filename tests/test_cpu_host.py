@@ -397,3 +397,15 @@ def test_deferred_host_build_equals_the_eager_one():
     lazy.set_deferred_build(False)
     assert lazy.array(_ffi.SCENE_NODES).tobytes() == eager.array(_ffi.SCENE_NODES).tobytes()
     assert lazy.array(_ffi.SCENE_ENTRIES).tobytes() == eager.array(_ffi.SCENE_ENTRIES).tobytes()
+
+
+def test_ingest_survives_mutated_inputs():
+    """tools/fuzz_ingest.py: mutated GLB / PNG / JPEG bytes come back as LP_OK or an error
+    status, never a crash (run in a child process so that a crash cannot take the suite
+    down; the --asan mode of the tool rebuilds the host sources with ASan + UBSan)."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "tools" / "fuzz_ingest.py"), "--n", "600",
+                          "--seed", "3"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "'rejected'" in out.stdout

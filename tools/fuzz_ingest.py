@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Mutation fuzzing of the ingest path that takes untrusted bytes: lp_load_gltf
+[ref loaders/gltf.rs:46-156] and the PNG / JPEG decoders behind it [ref gltf.rs:12-44].
+
+Every mutated input must come back as LP_OK or an error status -- never a crash, never a
+sanitizer report.  Seeds: the reference's one fixture (tests/golden/cornell-box.glb) and the
+image fixtures of tests/golden/image_fixtures.npz; mutations: byte overwrites, bit flips,
+truncation, extreme 16/32-bit values, with PNG chunk CRCs recomputed most of the time so that
+the mutation reaches the decoder proper.
+
+    python tools/fuzz_ingest.py --n 3000 --seed 1            # the product library
+    python tools/fuzz_ingest.py --n 3000 --seed 1 --asan     # host sources rebuilt with
+                                                             # -fsanitize=address,undefined
+(--asan re-executes itself with libasan preloaded; the sanitized library holds the host
+sources only, which is all the ingest path needs.)
+"""
+import argparse
+import ctypes as C
+import os
+import random
+import struct
+import subprocess
+import sys
+import zlib
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ASAN_LIB = ROOT / "oracle" / "_build" / "libloupiote_host_asan.so"
+
+
+def fix_png_crcs(b: bytes) -> bytes:
+    if b[:8] != b"\x89PNG\r\n\x1a\n":
+        return b
+    out, p = bytearray(b[:8]), 8
+    while p + 8 <= len(b):
+        ln = struct.unpack(">I", b[p:p + 4])[0]
+        if p + 12 + ln > len(b):
+            break
+        typ, body = b[p + 4:p + 8], b[p + 8:p + 8 + ln]
+        out += b[p:p + 8] + body + struct.pack(">I", zlib.crc32(typ + body) & 0xFFFFFFFF)
+        p += 12 + ln
+    return bytes(out + b[p:])
+
+
+def mutate(rng: random.Random, data: bytes) -> bytes:
+    b, mode = bytearray(data), rng.randrange(5)
+    if mode == 0:
+        for _ in range(rng.randrange(1, 6)):
+            b[rng.randrange(len(b))] = rng.randrange(256)
+    elif mode == 1:
+        b = b[:rng.randrange(len(b))]
+    elif mode == 2:
+        p = rng.randrange(len(b) - 2)
+        b[p:p + 2] = bytes([rng.choice([0, 255, 0x7F, 0x80]), rng.choice([0, 255, 1])])
+    elif mode == 3:
+        for _ in range(rng.randrange(1, 4)):
+            b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+    elif len(b) > 8:
+        struct.pack_into("<I", b, rng.randrange(len(b) - 4),
+                         rng.choice([0, 0xFFFFFFFF, 0x7FFFFFFF, len(b), len(b) + 1]))
+    return bytes(b)
+
+
+def run(lib: C.CDLL, n: int, seed: int) -> dict:
+    z = np.load(ROOT / "tests" / "golden" / "image_fixtures.npz")
+    images = [bytes(z[k].tobytes()) for k in sorted(z.keys()) if k.startswith("file_")]
+    glb = (ROOT / "tests" / "golden" / "cornell-box.glb").read_bytes()
+    lib.lp_scene_push_encoded_image.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t,
+                                                C.POINTER(C.c_uint32)]
+    lib.lp_load_gltf.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    rng = random.Random(seed)
+    counts = {"ok": 0, "rejected": 0}
+    for _ in range(n):
+        h = C.c_void_p()
+        assert lib.lp_scene_create(C.byref(h)) == 0
+        if rng.random() < 0.6:
+            b = mutate(rng, rng.choice(images))
+            if rng.random() < 0.7:
+                b = fix_png_crcs(b)
+            idx = C.c_uint32()
+            st = lib.lp_scene_push_encoded_image(h, b, len(b), C.byref(idx))
+        else:
+            b = mutate(rng, glb)
+            st = lib.lp_load_gltf(b, len(b), h)
+        counts["ok" if st == 0 else "rejected"] += 1
+        lib.lp_scene_destroy(h)
+    return counts
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=2000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--asan", action="store_true")
+    args = ap.parse_args()
+    if args.asan and os.environ.get("LP_FUZZ_CHILD") != "1":
+        ASAN_LIB.parent.mkdir(exist_ok=True)
+        srcs = sorted(str(p) for p in (ROOT / "loupiote_b200" / "csrc" / "host").glob("*.cpp"))
+        subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                        "-std=c++17", "-shared", "-fPIC", f"-I{ROOT / 'include'}", *srcs, "-o",
+                        str(ASAN_LIB)], check=True)
+        asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True,
+                              text=True, check=True).stdout.strip()
+        cxx = subprocess.run(["gcc", "-print-file-name=libstdc++.so.6"], capture_output=True,
+                             text=True, check=True).stdout.strip()
+        env = dict(os.environ, LP_FUZZ_CHILD="1", LD_PRELOAD=f"{asan} {cxx}",
+                   ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
+        sys.exit(subprocess.run([sys.executable, __file__, *sys.argv[1:]], env=env).returncode)
+    if args.asan:
+        lib = C.CDLL(str(ASAN_LIB))
+    else:
+        sys.path.insert(0, str(ROOT))
+        from loupiote_b200 import _ffi
+        lib = _ffi.lib()
+    print({"n": args.n, "seed": args.seed, "sanitized": bool(args.asan), **run(lib, args.n, args.seed)})
+
+
+if __name__ == "__main__":
+    main()
