@@ -81,7 +81,7 @@ struct lp_scene_gpu {
   bool lbvh = false;
   std::vector<uint32_t> lbvh_root2, lbvh_root4;   // child reference of every BLAS root
   std::vector<float> lbvh_root_box;               // 6 floats per BLAS (lo.xyz, hi.xyz)
-  uint32_t lbvh_blas_depth4 = 0, tlas_capacity = 1;
+  uint32_t lbvh_blas_depth4 = 0, lbvh_blas_depth2 = 0, tlas_capacity = 1;
 };
 
 

@@ -232,7 +232,7 @@ struct Workspace {
       j.idx2 = (uint32_t *)take(m * 4);
       tlas_ids = (uint32_t *)take(m * 4);
       j.frontier = (uint32_t *)take(4 * m * 4);
-      j.level_count = (uint32_t *)take((kMaxLevels + 2) * 4);
+      j.level_count = (uint32_t *)take((kMaxLevels + 3) * 4);
       root2 = (uint32_t *)take(ns * 4);
       root4 = (uint32_t *)take(ns * 4);
       j.keys = (uint64_t *)take(m * 8);
@@ -338,6 +338,7 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
   Job &j = w.job;
   j.max_leaf = 1;
   j.tlas = 1;
+  j.collapse_by_area = 1;
   j.tlas_ids = w.tlas_ids;
   j.base2 = j.base4 = 0;
   j.nodes2 = sg->nodes.ptr;
@@ -352,8 +353,8 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
   const uint32_t n_big = phase_a(ex, j, nullptr, &in, w.keys_tmp, w.vals_tmp);
   if (ex.err != cudaSuccess) return cuda_fail(ex.err, "TLAS build");
   if (n_big > sg->tlas_capacity) return fail(LP_ERR_ACCEL_BUILD, "TLAS larger than its node region");
-  uint32_t n4 = 0;
-  const int depth4 = phase_b(ex, j, nullptr, &n4);
+  uint32_t n4 = 0, tlas_depth2 = 0;
+  const int depth4 = phase_b(ex, j, nullptr, &n4, &tlas_depth2);
   to_half_nodes_kernel<<<blocks_for(sg->tlas_capacity), 256, 0, st>>>(
       sg->nodes4.ptr, (uint4 *)sg->nodes4h.ptr, 0u, sg->tlas_capacity);
   uint32_t roots[2] = {kRefNone, kRefNone};
@@ -368,8 +369,8 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
   if (ex.err != cudaSuccess) return cuda_fail(ex.err, "TLAS build");
   if (depth4 < 0) return fail(LP_ERR_ACCEL_BUILD, "TLAS too deep for the traversal stack");
   const uint32_t total4 = (uint32_t)depth4 + sg->lbvh_blas_depth4;
-  // every 4-wide level spans at most two levels of the 2-wide tree
-  const uint32_t depth2 = 2u * total4 + 1u;
+  // 2-wide depth as Scene::build_derived counts it (levels incl. the leaves, + 1 between trees)
+  const uint32_t depth2 = (tlas_depth2 + 1u) + (sg->lbvh_blas_depth2 + 1u) + 1u;
   if (3u * total4 + 2u > kStackSize4 || depth2 + 2u > (uint32_t)kStackSize)
     return fail(LP_ERR_ACCEL_BUILD, "BVH too deep for the traversal stack");
   sg->sc.tlas_root = roots[0];
@@ -451,6 +452,12 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
   const char *ml = std::getenv("LP_LBVH_MAX_LEAF");
   j.max_leaf = ml ? (uint32_t)std::min(4, std::max(1, std::atoi(ml))) : 2u;
   j.tlas = 0;
+  // 4-wide collapse: largest-area slot first (like the host's relayout4) instead of plain
+  // grandchildren: -4 % surface-area cost on the emulated build (tests/test_cpu_lbvh.py's
+  // trees; 181.0 -> 173.4 expected node + triangle tests per ray).  LP_LBVH_COLLAPSE=0 restores
+  // the grandchildren rule.
+  const char *cb = std::getenv("LP_LBVH_COLLAPSE");
+  j.collapse_by_area = cb ? (uint32_t)(std::atoi(cb) != 0) : 1u;
   BlasInput in;
   in.vertices = g->vertices.ptr;
   in.indices = g->indices.ptr;
@@ -470,8 +477,8 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
   j.base2 = j.base4 = g->tlas_capacity;
   j.nodes2 = g->nodes.ptr;
   j.nodes4 = g->nodes4.ptr;
-  uint32_t n4 = 0;
-  const int depth4 = phase_b(ex, j, &in, &n4);
+  uint32_t n4 = 0, blas_depth2 = 0;
+  const int depth4 = phase_b(ex, j, &in, &n4, &blas_depth2);
   if (n4) to_half_nodes_kernel<<<blocks_for(n4), 256, 0, st>>>(g->nodes4.ptr, (uint4 *)g->nodes4h.ptr,
                                                                g->tlas_capacity, n4);
   const size_t ne = s.entries.size();
@@ -493,6 +500,7 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
     if (s.entries[b].primitive_count) std::memcpy(&g->lbvh_root_box[6 * b], box, sizeof(box));
   }
   g->lbvh_blas_depth4 = (uint32_t)depth4;
+  g->lbvh_blas_depth2 = blas_depth2;
   bind_scene(g, s, n_active, (size_t)g->tlas_capacity + n_big, (size_t)g->tlas_capacity + n4);
 
   // ---- instance records + TLAS

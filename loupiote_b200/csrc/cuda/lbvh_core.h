@@ -59,6 +59,7 @@ struct Job {
   uint32_t n_slots = 0, n_segments = 0;
   uint32_t max_leaf = 4;  // 4 for a BLAS, 1 for the TLAS
   uint32_t tlas = 0;      // leaf reference = instance id instead of a triangle range
+  uint32_t collapse_by_area = 0;  // 4-wide collapse: 0 = grandchildren, 1 = largest area first
   const Segment *segs = nullptr;
   const uint32_t *slot_seg = nullptr;  // segment of every slot
   float4 *seg_lo = nullptr, *seg_hi = nullptr;    // bounds of every segment
@@ -81,7 +82,8 @@ struct Job {
   uint32_t *frontier = nullptr;        // 2 (ping-pong) x n_slots x 2: (slot, node index)
   uint32_t *level_count = nullptr;     // kMaxLevels + 1 frontier sizes, zeroed ...
   uint32_t *n_nodes4 = nullptr;        // ... + the 4-wide node allocation counter, which MUST be
-                                       // level_count + kMaxLevels + 1 (one read-back for all)
+                                       // level_count + kMaxLevels + 1 (one read-back for all),
+                                       // ... + [kMaxLevels + 2] = depth of the 2-wide trees
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -122,6 +124,7 @@ __device__ __forceinline__ void grow_segment(float4 *seg_lo, float4 *seg_hi, uin
   atomic_max_f(&seg_hi[s].x, hx); atomic_max_f(&seg_hi[s].y, hy); atomic_max_f(&seg_hi[s].z, hz);
 }
 __device__ __forceinline__ uint32_t atomic_inc_u32(uint32_t *a, uint32_t n) { return atomicAdd(a, n); }
+__device__ __forceinline__ void atomic_max_u32(uint32_t *a, uint32_t v) { atomicMax(a, v); }
 __device__ __forceinline__ void fence() { __threadfence(); }
 __device__ __forceinline__ int clz64(uint64_t x) { return __clzll((long long)x); }
 __device__ __forceinline__ int clz32(uint32_t x) { return __clz((int)x); }
@@ -138,6 +141,7 @@ inline void grow_segment(float4 *seg_lo, float4 *seg_hi, uint32_t s, const float
   atomic_max_f(&seg_hi[s].x, hi.x); atomic_max_f(&seg_hi[s].y, hi.y); atomic_max_f(&seg_hi[s].z, hi.z);
 }
 inline uint32_t atomic_inc_u32(uint32_t *a, uint32_t n) { const uint32_t o = *a; *a += n; return o; }
+inline void atomic_max_u32(uint32_t *a, uint32_t v) { if (v > *a) *a = v; }
 inline void fence() {}
 inline int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
 inline int clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
@@ -319,6 +323,15 @@ LBVH_HD void fit_from_leaf(const Job &j, uint32_t pos) {
   }
 }
 
+// interior nodes above sorted position `pos` (what a 2-wide traversal stack has to hold);
+// the maximum over all primitives lands in level_count[kMaxLevels + 2]
+LBVH_HD void depth_from_leaf(const Job &j, uint32_t pos) {
+  if (j.segs[j.slot_seg[pos]].count < 2) return;
+  uint32_t depth = 0;
+  for (uint32_t cur = j.leaf_parent[pos]; cur != kNone; cur = j.parent[cur]) ++depth;
+  atomic_max_u32(j.level_count + kMaxLevels + 2, depth);
+}
+
 // ------------------------------------------------------------------ 5. node emission
 // a link is a LEAF of the output tree when it is a single primitive or an interior node of
 // <= max_leaf primitives
@@ -389,13 +402,42 @@ LBVH_HD void collapse_node(const Job &j, uint32_t level, uint32_t entry) {
   const uint32_t slot = in[2ull * entry], node = in[2ull * entry + 1];
   uint32_t links[4];
   int n = 0;
-  const uint32_t kids[2] = {j.left[slot], j.right[slot]};
-  for (int c = 0; c < 2; ++c) {
-    if (link_is_leaf(j, kids[c])) {
-      links[n++] = kids[c];
-    } else {
-      links[n++] = j.left[kids[c]];
-      links[n++] = j.right[kids[c]];
+  if (j.collapse_by_area) {
+    // like the host's relayout4: while a slot is free, the interior slot with the largest
+    // surface area is replaced by its two children (the pair takes the slot's place)
+    links[0] = j.left[slot];
+    links[1] = j.right[slot];
+    n = 2;
+    while (n < 4) {
+      int best = -1;
+      float best_area = -1.0f;
+      for (int k = 0; k < n; ++k) {
+        if (link_is_leaf(j, links[k])) continue;
+        float4 l, h;
+        link_box(j, links[k], l, h);
+        const float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
+        const float area = dx * dy + dy * dz + dz * dx;
+        if (area > best_area) {
+          best_area = area;
+          best = k;
+        }
+      }
+      if (best < 0) break;
+      const uint32_t open = links[best];
+      for (int k = n; k > best + 1; --k) links[k] = links[k - 1];
+      links[best] = j.left[open];
+      links[best + 1] = j.right[open];
+      ++n;
+    }
+  } else {
+    const uint32_t kids[2] = {j.left[slot], j.right[slot]};
+    for (int c = 0; c < 2; ++c) {
+      if (link_is_leaf(j, kids[c])) {
+        links[n++] = kids[c];
+      } else {
+        links[n++] = j.left[kids[c]];
+        links[n++] = j.right[kids[c]];
+      }
     }
   }
   int n_kept = 0;
@@ -531,6 +573,10 @@ struct FitOp {
   Job j;
   LBVH_HD void operator()(uint32_t i) const { fit_from_leaf(j, i); }
 };
+struct DepthOp {
+  Job j;
+  LBVH_HD void operator()(uint32_t i) const { depth_from_leaf(j, i); }
+};
 struct EmitNode2Op {
   Job j;
   LBVH_HD void operator()(uint32_t i) const { emit_node2(j, i); }
@@ -563,23 +609,27 @@ inline uint32_t phase_a(Exec &ex, const Job &j, const BlasInput *blas, const Tla
   ex.for_each(j.n_segments, InitSegOp{j});
   ex.zero(j.visits, j.n_slots);
   ex.zero(j.big, j.n_slots);
-  ex.zero(j.level_count, (uint32_t)kMaxLevels + 2u);  // frontier sizes + n_nodes4
+  ex.zero(j.level_count, (uint32_t)kMaxLevels + 3u);  // frontier sizes, n_nodes4, depth
   if (blas) ex.for_each(j.n_slots, TriangleBoxOp{j, *blas});
   else ex.for_each(j.n_slots, InstanceBoxOp{j, *tlas});
   ex.for_each(j.n_slots, MortonOp{j, keys_tmp, vals_tmp});
   ex.sort(keys_tmp, vals_tmp, j);
   ex.for_each(j.n_slots, RadixOp{j});
   ex.for_each(j.n_slots, FitOp{j});
+  ex.for_each(j.n_slots, DepthOp{j});
   ex.scan(j.big, j.idx2, j.n_slots);
   return ex.read(j.idx2 + (j.n_slots - 1u)) + ex.read(j.big + (j.n_slots - 1u));
 }
 
 // Phase B: node arrays (j.nodes2 / j.nodes4 sized from phase A), root references, triangles.
 // Returns the depth of the deepest 4-wide tree (0: every root is a leaf), or -1 when a tree
-// is deeper than the traversal stack allows.  *n_nodes4_out = 4-wide nodes written.
+// is deeper than the traversal stack allows.  *n_nodes4_out = 4-wide nodes written,
+// *depth2_out = interior levels of the deepest 2-wide tree.
 template <class Exec>
-inline int phase_b(Exec &ex, const Job &j, const BlasInput *blas, uint32_t *n_nodes4_out) {
+inline int phase_b(Exec &ex, const Job &j, const BlasInput *blas, uint32_t *n_nodes4_out,
+                   uint32_t *depth2_out) {
   *n_nodes4_out = 0;
+  *depth2_out = 0;
   if (j.n_slots == 0) {
     ex.for_each(j.n_segments, EmitRootOp{j});
     return 0;
@@ -589,9 +639,10 @@ inline int phase_b(Exec &ex, const Job &j, const BlasInput *blas, uint32_t *n_no
   for (uint32_t level = 0; level < (uint32_t)kMaxLevels; ++level)
     ex.for_each_counted(j.level_count + level, j.n_slots, CollapseOp{j, level});
   if (blas) ex.for_each(j.n_slots, EmitTriangleOp{j, *blas});
-  uint32_t counts[kMaxLevels + 2] = {0};
-  ex.read_n(j.level_count, (uint32_t)kMaxLevels + 2u, counts);
+  uint32_t counts[kMaxLevels + 3] = {0};
+  ex.read_n(j.level_count, (uint32_t)kMaxLevels + 3u, counts);
   *n_nodes4_out = counts[kMaxLevels + 1];
+  *depth2_out = counts[kMaxLevels + 2];
   if (counts[kMaxLevels] != 0u) return -1;
   int depth = 0;
   while (depth < kMaxLevels && counts[depth] != 0u) ++depth;

@@ -67,7 +67,7 @@ struct Workspace {
                     &visits, &big, &idx2, &vals_tmp})
       v->assign(m, 0xCDCDCDCDu);  // poison: nothing may rely on zero-initialised memory
     frontier.assign(4 * m, 0xCDCDCDCDu);
-    level_count.assign(kMaxLevels + 2, 0xCDCDCDCDu);  // + the node counter
+    level_count.assign(kMaxLevels + 3, 0xCDCDCDCDu);  // + node counter, 2-wide depth
     keys.assign(m, 0);
     keys_tmp.assign(m, 0);
     for (auto *v : {&prim_lo, &prim_hi, &leaf_lo, &leaf_hi, &node_lo, &node_hi})
@@ -95,15 +95,16 @@ struct Workspace {
 
 }  // namespace
 
-static uint32_t g_max_leaf = 4;
+static uint32_t g_max_leaf = 4, g_collapse_by_area = 0;
 
 extern "C" {
 
 void lbvh_emu_set_max_leaf(uint32_t n) { g_max_leaf = n; }
+void lbvh_emu_set_collapse_by_area(uint32_t on) { g_collapse_by_area = on; }
 
 // Builds every BLAS of a scene.  seg arrays have n_segments entries; nodes2 / nodes4 / tris
 // are caller-allocated with the given capacities (in nodes / triangles).  out[0] = 2-wide
-// nodes written, out[1] = 4-wide nodes written, out[2] = 4-wide depth.  Returns 0, or a
+// nodes written, out[1] = 4-wide nodes written, out[2] = 4-wide depth, out[3] = 2-wide depth.  Returns 0, or a
 // negative code: -1 too deep, -2 node capacity too small.
 int lbvh_emu_build_blas(const float *vertices, const uint32_t *indices, const uint32_t *counts,
                         const uint32_t *prim_base, const uint32_t *vertex_offset,
@@ -115,6 +116,7 @@ int lbvh_emu_build_blas(const float *vertices, const uint32_t *indices, const ui
   w.init(counts, prim_base, n_segments);
   Job &j = w.job;
   j.max_leaf = g_max_leaf;
+  j.collapse_by_area = g_collapse_by_area;
   j.tlas = 0;
   j.base2 = base2;
   j.base4 = base4;
@@ -131,8 +133,9 @@ int lbvh_emu_build_blas(const float *vertices, const uint32_t *indices, const ui
   HostExec ex;
   const uint32_t n_big = phase_a(ex, j, &in, nullptr, w.keys_tmp.data(), w.vals_tmp.data());
   if (base2 + n_big > cap2 || base4 + n_big > cap4) return -2;
-  uint32_t n4 = 0;
-  const int depth = phase_b(ex, j, &in, &n4);
+  uint32_t n4 = 0, depth2 = 0;
+  const int depth = phase_b(ex, j, &in, &n4, &depth2);
+  out[3] = depth2;
   for (uint32_t s = 0; s < n_segments; ++s) {
     root_box[6 * s + 0] = w.seg_lo[s].x; root_box[6 * s + 1] = w.seg_lo[s].y;
     root_box[6 * s + 2] = w.seg_lo[s].z; root_box[6 * s + 3] = w.seg_hi[s].x;
@@ -154,6 +157,7 @@ int lbvh_emu_build_tlas(const float *instances, const uint32_t *instance_blas,
   w.init(&n, nullptr, 1);
   Job &j = w.job;
   j.max_leaf = 1;
+  j.collapse_by_area = g_collapse_by_area;
   j.tlas = 1;
   j.tlas_ids = ids;
   j.base2 = j.base4 = 0;
@@ -168,8 +172,9 @@ int lbvh_emu_build_tlas(const float *instances, const uint32_t *instance_blas,
   HostExec ex;
   const uint32_t n_big = phase_a(ex, j, nullptr, &in, w.keys_tmp.data(), w.vals_tmp.data());
   if (n_big > cap2 || n_big > cap4) return -2;
-  uint32_t n4 = 0;
-  const int depth = phase_b(ex, j, nullptr, &n4);
+  uint32_t n4 = 0, depth2 = 0;
+  const int depth = phase_b(ex, j, nullptr, &n4, &depth2);
+  out[3] = depth2;
   out[0] = n_big;
   out[1] = n4;
   out[2] = depth < 0 ? 0u : (uint32_t)depth;

@@ -34,9 +34,11 @@ TRI = np.dtype([("v0", "<f4", 3), ("id", "<u4"), ("v1", "<f4", 4), ("v2", "<f4",
                 ("pad", "<f4", 4)])
 
 
-@pytest.fixture(scope="module", params=[2, 4], ids=["leaf2", "leaf4"])
+@pytest.fixture(scope="module", params=[(2, 1), (4, 0), (3, 1)],
+                ids=["leaf2-area", "leaf4-grandchildren", "leaf3-area"])
 def emu(request):
-    """The emulated builder with leaves of <= 2 (the device default) or <= 4 triangles."""
+    """The emulated builder: leaves of <= 2 triangles + largest-area-first collapse (the device
+    defaults), and the other settings of both knobs."""
     OUT.parent.mkdir(exist_ok=True)
     h = hashlib.sha256(SRC.read_bytes() + CORE.read_bytes()).hexdigest()
     stamp = OUT.with_suffix(".stamp")
@@ -47,8 +49,9 @@ def emu(request):
     lib = C.CDLL(str(OUT))
     lib.lbvh_emu_morton.restype = C.c_uint64
     lib.lbvh_emu_morton.argtypes = [C.c_float] * 3
-    lib.lbvh_emu_set_max_leaf(C.c_uint32(request.param))
-    lib.max_leaf = request.param
+    lib.lbvh_emu_set_max_leaf(C.c_uint32(request.param[0]))
+    lib.lbvh_emu_set_collapse_by_area(C.c_uint32(request.param[1]))
+    lib.max_leaf = request.param[0]
     return lib
 
 
@@ -72,7 +75,7 @@ def build_blas(emu, scene, base2=3, base4=5):
     tris = np.zeros(n_prims, TRI)
     root2, root4 = np.zeros(n_seg, np.uint32), np.zeros(n_seg, np.uint32)
     root_box = np.zeros((n_seg, 6), np.float32)
-    out = np.zeros(3, np.uint32)
+    out = np.zeros(4, np.uint32)
     rc = emu.lbvh_emu_build_blas(_p(vertices), _p(indices), _p(counts), _p(prim_base), _p(voff),
                                  _p(ioff), C.c_uint32(n_seg), C.c_uint32(base2), C.c_uint32(base4),
                                  _p(nodes2), C.c_uint32(cap), _p(nodes4), C.c_uint32(cap), _p(tris),
@@ -80,6 +83,7 @@ def build_blas(emu, scene, base2=3, base4=5):
     return dict(rc=rc, nodes2=nodes2, nodes4=nodes4, tris=tris, root2=root2, root4=root4,
                 max_leaf=emu.max_leaf,
                 root_box=root_box, n2=int(out[0]), n4=int(out[1]), depth4=int(out[2]),
+                depth2=int(out[3]),
                 entries=entries, vertices=vertices, indices=indices, base2=base2, base4=base4)
 
 
@@ -113,28 +117,30 @@ def walk4(b, ref, seen, depth=1):
     return np.min(lo, 0), np.max(hi, 0), deepest
 
 
-def walk2(b, ref, seen):
+def walk2(b, ref, seen, depth=1):
+    """(lo, hi, interior levels) of the subtree behind `ref` of the 2-wide array."""
     if ref & LEAF:
         count, first = ((ref >> 28) & 7) + 1, ref & 0x0FFFFFFF
         seen.extend(range(first, first + count))
-        return _tri_bounds(b["tris"], first, count)
+        return (*_tri_bounds(b["tris"], first, count), depth - 1)
     assert b["base2"] <= ref < b["base2"] + b["n2"], ref
     node = b["nodes2"][ref]
     q = node["q"]
     boxes = [(q[0:3], q[3:6]), (q[6:9], q[9:12])]
-    lo, hi = [], []
+    lo, hi, deepest = [], [], depth
     for s in range(2):
-        l, h = walk2(b, int(node["child"][s]), seen)
+        l, h, d = walk2(b, int(node["child"][s]), seen, depth + 1)
         assert np.array_equal(boxes[s][0], l) and np.array_equal(boxes[s][1], h)
         lo.append(l), hi.append(h)
-    return np.min(lo, 0), np.max(hi, 0)
+        deepest = max(deepest, d)
+    return np.min(lo, 0), np.max(hi, 0), deepest
 
 
 def check_blas(b):
     """`b` = the builder's outputs (emulated, or read back from the device: then root_box /
     depth4 are None and only the BLASes some instance uses have a known root)."""
     assert b["rc"] == 0
-    deepest = 0
+    deepest = deepest2 = 0
     for e, ent in enumerate(b["entries"]):
         n, base = int(ent["primitive_count"]), int(ent["primitive_offset"])
         if b.get("known_roots") is not None and e not in b["known_roots"]:
@@ -151,6 +157,8 @@ def check_blas(b):
                 assert np.array_equal(res[1], b["root_box"][e, 3:])
             if walk is walk4:
                 deepest = max(deepest, res[2])
+            else:
+                deepest2 = max(deepest2, res[2])
         # the triangle records are the BLAS's triangles, each once, with their original index
         t = b["tris"][base:base + n]
         assert sorted(t["id"].tolist()) == list(range(n))
@@ -162,6 +170,10 @@ def check_blas(b):
         assert not t["v1"][:, 3].any() and not t["v2"][:, 3].any() and not t["pad"].any()
     if b.get("depth4") is not None:
         assert deepest == b["depth4"]
+        # the reported 2-wide depth counts the radix tree's interior nodes above a primitive,
+        # including those folded into a leaf (a chain of at most max_leaf - 1): never less than
+        # the emitted tree's depth
+        assert deepest2 <= b["depth2"] <= deepest2 + b["max_leaf"] - 1
     return deepest
 
 
@@ -260,7 +272,7 @@ def test_tlas_over_instances(emu):
                    np.uint32)
     n = len(ids)
     nodes2, nodes4 = np.zeros(n + 1, NODE2), np.zeros(n + 1, NODE4)
-    root2, root4, out = np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros(3, np.uint32)
+    root2, root4, out = np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros(4, np.uint32)
     blas_of = np.ascontiguousarray(inst["blas"])
     rc = emu.lbvh_emu_build_tlas(_p(inst), _p(blas_of), _p(b["root_box"]), _p(ids), C.c_uint32(n),
                                  _p(nodes2), C.c_uint32(n + 1), _p(nodes4), C.c_uint32(n + 1),
@@ -311,7 +323,7 @@ def test_empty_scene_and_single_instance(emu):
     b = build_blas(emu, s)
     assert b["rc"] == 0 and b["n2"] == 0 and b["n4"] == 0
     assert b["root4"][0] == NONE
-    root2, root4, out = np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros(3, np.uint32)
+    root2, root4, out = np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros(4, np.uint32)
     z = np.zeros(64, np.float32)
     rc = emu.lbvh_emu_build_tlas(_p(z), _p(z), _p(z), _p(z), C.c_uint32(0), _p(z), C.c_uint32(1),
                                  _p(z), C.c_uint32(1), _p(root2), _p(root4), _p(out))
