@@ -328,6 +328,7 @@ void node_matrix(const JValue &node, float m[16]) {
 
 lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string &err) {
   Doc doc;
+  DeferredBuildScope build_scope(scene);  // the meshes' trees are built together at the end
   try {
     if (!data || size < 4) throw std::runtime_error("empty input");
     const uint8_t *json_ptr = data;
@@ -536,6 +537,7 @@ lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string 
         scene.add_instance((uint32_t)prim_entry[mi][pi], m, material);
       }
     }
+    build_scope.finish();
   } catch (const std::exception &e) {
     err = e.what();
     return LP_ERR_ACCEL_BUILD;

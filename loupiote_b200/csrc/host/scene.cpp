@@ -7,7 +7,11 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <exception>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 
 namespace lp {
 
@@ -108,11 +112,19 @@ uint32_t Scene::add_bvh(const void *positions, size_t pstride, const void *norma
   return (uint32_t)entries.size() - 1;
 }
 
-// Binned-SAH tree of every entry add_bvh left pending, in add order (node offsets are the
-// running size of `nodes`, exactly as if each tree had been built inside add_bvh).
+// Binned-SAH tree of every entry add_bvh left pending.  The trees are independent, so they are
+// built on all host cores (one entry per task, results kept per entry) and then appended in
+// add order: node offsets are the running size of `nodes`, exactly as if each tree had been
+// built inside add_bvh, whatever the thread count.
 void Scene::ensure_host_bvh() {
-  for (const uint32_t ei : pending_bvh) {
-    lp_blas_entry &e = entries[ei];
+  if (pending_bvh.empty()) return;
+  struct Built {
+    std::vector<lp_bvh_node> tree;
+    std::vector<uint32_t> perm;
+  };
+  std::vector<Built> built(pending_bvh.size());
+  auto build_one = [&](size_t k) {
+    const lp_blas_entry &e = entries[pending_bvh[k]];
     const size_t tri_count = e.primitive_count;
     std::vector<BuildBox> boxes(tri_count);
     const lp_vertex *vb = vertices.data() + e.vertex_offset;
@@ -127,23 +139,50 @@ void Scene::ensure_host_bvh() {
       }
       boxes[t] = b;
     }
-    std::vector<lp_bvh_node> tree;
-    std::vector<uint32_t> perm;
-    build_bvh2(boxes, 4, tree, perm);
+    build_bvh2(boxes, 4, built[k].tree, built[k].perm);
+  };
+  size_t work = 0;
+  for (const uint32_t ei : pending_bvh) work += entries[ei].primitive_count;
+  const size_t n_threads =
+      work < 20000 ? 1 : std::min<size_t>(pending_bvh.size(), std::max(1u, std::thread::hardware_concurrency()));
+  if (n_threads <= 1) {
+    for (size_t k = 0; k < pending_bvh.size(); ++k) build_one(k);
+  } else {
+    std::atomic<size_t> next{0};
+    std::exception_ptr failure;
+    std::mutex failure_lock;
+    auto worker = [&]() {
+      try {
+        for (size_t k = next++; k < pending_bvh.size(); k = next++) build_one(k);
+      } catch (...) {
+        std::lock_guard<std::mutex> g(failure_lock);
+        if (!failure) failure = std::current_exception();
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    if (failure) std::rethrow_exception(failure);
+  }
+  for (size_t k = 0; k < pending_bvh.size(); ++k) {
+    lp_blas_entry &e = entries[pending_bvh[k]];
+    const lp_vertex *vb = vertices.data() + e.vertex_offset;
+    const uint32_t *ib = indices.data() + e.index_offset;
     e.node_offset = (uint32_t)nodes.size();
-    e.node_count = (uint32_t)tree.size();
-    nodes.insert(nodes.end(), tree.begin(), tree.end());
-    for (size_t k = 0; k < tri_count; ++k) {
-      const uint32_t t = perm[k];
+    e.node_count = (uint32_t)built[k].tree.size();
+    nodes.insert(nodes.end(), built[k].tree.begin(), built[k].tree.end());
+    for (size_t i = 0; i < e.primitive_count; ++i) {
+      const uint32_t t = built[k].perm[i];
       lp_bvh_primitive p{};
       std::memcpy(p.v0, vb[ib[3 * t]].position, 12);
       std::memcpy(p.v1, vb[ib[3 * t + 1]].position, 12);
       std::memcpy(p.v2, vb[ib[3 * t + 2]].position, 12);
       std::memcpy(&p.v0[3], &t, 4);
-      primitives[e.primitive_offset + k] = p;
+      primitives[e.primitive_offset + i] = p;
     }
   }
-  if (!pending_bvh.empty()) derived_dirty = true;
+  derived_dirty = true;
   pending_bvh.clear();
 }
 

@@ -132,8 +132,31 @@ struct Scene {
   void add_instance(uint32_t blas, const float m[16], uint32_t material);
   void set_instance_transform(uint32_t instance, const float m[16]);
   void build_derived();  // TLAS + GPU layout (full, or TLAS-only after set_instance_transform)
-  void ensure_host_bvh();  // builds the trees add_bvh deferred
+  void ensure_host_bvh();  // builds the trees add_bvh deferred (all host cores, one per tree)
   void build_tlas();
+};
+
+// The loaders add many meshes in a row: while one of these is alive add_bvh defers its tree,
+// and the destructor builds them all at once on every core (unless the caller had asked for
+// deferred builds, which then stay deferred).
+struct DeferredBuildScope {
+  Scene &scene;
+  bool was_deferred;
+  explicit DeferredBuildScope(Scene &s) : scene(s), was_deferred(s.defer_host_bvh) {
+    s.defer_host_bvh = true;
+  }
+  void finish() {  // may throw (allocation); call on the success path
+    scene.defer_host_bvh = was_deferred;
+    if (!was_deferred) scene.ensure_host_bvh();
+  }
+  ~DeferredBuildScope() {
+    if (scene.defer_host_bvh == was_deferred) return;  // finish() ran
+    scene.defer_host_bvh = was_deferred;
+    try {
+      if (!was_deferred) scene.ensure_host_bvh();
+    } catch (...) {
+    }
+  }
 };
 
 // Binned-SAH BVH2 over boxes (16 bins, all three axes, traversal cost 1, intersection

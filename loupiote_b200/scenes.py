@@ -104,13 +104,16 @@ def cornell_box() -> dict:
     return {"scene": scene, "view": view, "env_color": (0.0, 0.0, 0.0), "name": "cornell-box"}
 
 
-def spheres_1m(grid: int = 7, subdivisions: int = 5, deferred_build: bool = False) -> dict:
+def spheres_1m(grid: int = 7, subdivisions: int = 5, deferred_build: bool = False,
+               eager_build: bool = False) -> dict:
     """BASELINE config 3: grid x grid displaced icospheres (unique BLAS each) + ground quad.
     Defaults give 49 * 20,480 + 2 = 1,003,522 triangles, 50 BLAS, 50 instances.
-    deferred_build: leave the host SAH trees unbuilt (Scene.set_deferred_build)."""
+    The host SAH trees are built together at the end, one per host core (identical to building
+    each inside add_bvh, which eager_build=True does); deferred_build=True leaves them unbuilt
+    (Scene.set_deferred_build) for a device-built SceneGPU."""
     rng = SplitMix64(SCENE_SEED)
     scene = Scene()
-    scene.set_deferred_build(deferred_build)
+    scene.set_deferred_build(not eager_build)
     base_v, base_f = icosphere(subdivisions)
     nv = base_v.shape[0]
     spacing = 2.5
@@ -133,6 +136,8 @@ def spheres_1m(grid: int = 7, subdivisions: int = 5, deferred_build: bool = Fals
             scene.blas.add_instance(blas, m, mat)
             k += 1
     _ground(scene, 30.0)
+    if not deferred_build:
+        scene.set_deferred_build(False)  # builds what is pending, on all cores
     d = np.array([0.0, -0.38, -1.0])
     view = look_at_view((0.0, 9.0, 22.0), d / np.linalg.norm(d))
     return {"scene": scene, "view": view, "env_color": ENV_COLOR, "name": "spheres-1M"}

@@ -374,12 +374,16 @@ def test_deferred_host_build_equals_the_eager_one():
     import time
     from loupiote_b200 import scenes
     t0 = time.perf_counter()
-    eager = scenes.spheres_1m(grid=3, subdivisions=4)["scene"]
+    eager = scenes.spheres_1m(grid=3, subdivisions=4, eager_build=True)["scene"]
     t_eager = time.perf_counter() - t0
     t0 = time.perf_counter()
     lazy = scenes.spheres_1m(grid=3, subdivisions=4, deferred_build=True)["scene"]
     t_lazy = time.perf_counter() - t0
     assert t_lazy < t_eager  # the SAH build is the bulk of add_bvh
+    # the default generator builds the trees together at the end, on all cores: same bytes
+    together = scenes.spheres_1m(grid=3, subdivisions=4)["scene"]
+    for which in (_ffi.SCENE_ENTRIES, _ffi.SCENE_NODES, _ffi.SCENE_PRIMITIVES):
+        assert together.array(which).tobytes() == eager.array(which).tobytes(), which
     # arrays that do not need the trees are there at once
     for which in (_ffi.SCENE_VERTICES, _ffi.SCENE_INDICES, _ffi.SCENE_INSTANCES,
                   _ffi.SCENE_MATERIALS):
