@@ -10,7 +10,9 @@
 //   lp_render --glb scene.glb [--out image.ppm] [--size 960x540] [--spp 64] [--bounces 4]
 //             [--eye x,y,z] [--dir x,y,z] [--fov degrees] [--env r,g,b]
 //             [--light cx,cy,cz,tx,ty,tz,bx,by,bz,intensity] [--denoise] [--seed n]
-//             [--checkpoint file] [--resume file]
+//             [--checkpoint file] [--resume file] [--device-build]
+//   --device-build: every BLAS and the TLAS are built on the GPU (LBVH) and the loader skips
+//   the host BVH build; the image is the same, bit for bit
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -67,7 +69,7 @@ int main(int argc, char **argv) {
   float env[3] = {0.f, 0.f, 0.f}, fov = 45.f;
   std::vector<lp_light> lights;
   uint32_t spp = 64, bounces = 4, seed = 0;
-  bool denoise = false;
+  bool denoise = false, device_build = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     const char *v = i + 1 < argc ? argv[i + 1] : nullptr;
@@ -93,6 +95,7 @@ int main(int argc, char **argv) {
     else if (a == "--checkpoint") checkpoint = need();
     else if (a == "--resume") resume = need();
     else if (a == "--denoise") denoise = true;
+    else if (a == "--device-build") device_build = true;
     else if (a == "--light") {
       float f[10];
       ok = parse_floats(need(), f, 10);
@@ -122,10 +125,12 @@ int main(int argc, char **argv) {
   CHECK(lp_device_create(0, &dev));
   lp_scene *scene = nullptr;
   CHECK(lp_scene_create(&scene));                    // Scene::default()
+  if (device_build) CHECK(lp_scene_set_deferred_build(scene, 1));
   CHECK(lp_load_gltf_path(glb.c_str(), scene));      // loaders::load_gltf_path
   for (const lp_light &l : lights) CHECK(lp_scene_push_light(scene, &l, nullptr));
   lp_scene_gpu *sg = nullptr;
-  CHECK(lp_scene_gpu_new_from_scene(scene, dev, &sg));  // SceneGPU::new_from_scene
+  if (device_build) CHECK(lp_scene_gpu_new_from_scene_lbvh(scene, dev, &sg));
+  else CHECK(lp_scene_gpu_new_from_scene(scene, dev, &sg));  // SceneGPU::new_from_scene
 
   lp_renderer *r = nullptr;
   CHECK(lp_renderer_new(dev, w, h, &r));
