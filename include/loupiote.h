@@ -257,7 +257,8 @@ typedef enum lp_scene_array {
   LP_SCENE_GPU_INSTANCES = 11, /* 128-byte instance records (host copy) */
   LP_SCENE_GPU_NODES4 = 12, /* 128-byte 4-wide collapse of the same trees (host copy) */
   LP_SCENE_ATLAS_BLOCKS = 13, /* uint32_t[4] per image: x | y << 16, w | h << 16, layer, 0 */
-  LP_SCENE_ATLAS_TEXELS = 14  /* uint8_t[4] per texel, layers * size * size texels */
+  LP_SCENE_ATLAS_TEXELS = 14, /* uint8_t[4] per texel, layers * size * size texels */
+  LP_SCENE_GPU_NODES4H = 15   /* 64-byte 4-wide nodes, binary16 boxes rounded outwards (host copy) */
 } lp_scene_array;
 LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const void **out_ptr,
                                     size_t *out_count, size_t *out_elem_size);

@@ -85,7 +85,8 @@ class RayCounters(C.Structure):
 # lp_scene_array
 (SCENE_ENTRIES, SCENE_NODES, SCENE_PRIMITIVES, SCENE_VERTICES, SCENE_INSTANCES, SCENE_MATERIALS,
  SCENE_LIGHTS, SCENE_INDICES, SCENE_EMISSION, SCENE_TLAS_NODES, SCENE_GPU_NODES,
- SCENE_GPU_INSTANCES, SCENE_GPU_NODES4, SCENE_ATLAS_BLOCKS, SCENE_ATLAS_TEXELS) = range(15)
+ SCENE_GPU_INSTANCES, SCENE_GPU_NODES4, SCENE_ATLAS_BLOCKS, SCENE_ATLAS_TEXELS,
+ SCENE_GPU_NODES4H) = range(16)
 
 _vp = C.c_void_p
 _PROTOTYPES = {

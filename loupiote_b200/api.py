@@ -141,6 +141,7 @@ _ARRAY_DTYPES = {
                                         ("root4", "<u4"), ("pad", "<u4", 2)]),
     _ffi.SCENE_GPU_NODES4: np.dtype([("lo", "<f4", (3, 4)), ("hi", "<f4", (3, 4)),
                                      ("child", "<u4", 4), ("pad", "<u4", 4)]),
+    _ffi.SCENE_GPU_NODES4H: np.dtype([("box", "<f2", (6, 4)), ("child", "<u4", 4)]),
     _ffi.SCENE_ATLAS_BLOCKS: np.dtype(("<u4", 4)),
     _ffi.SCENE_ATLAS_TEXELS: np.dtype(("u1", 4)),
 }

@@ -146,6 +146,7 @@ LP_API lp_status lp_scene_get_array(lp_scene *scene, lp_scene_array which, const
       case LP_SCENE_GPU_NODES: s.build_derived(); *out_ptr = s.gpu_nodes.data(); *out_count = s.gpu_nodes.size(); es = sizeof(GpuNode); break;
       case LP_SCENE_GPU_INSTANCES: s.build_derived(); *out_ptr = s.gpu_instances.data(); *out_count = s.gpu_instances.size(); es = sizeof(GpuInstance); break;
       case LP_SCENE_GPU_NODES4: s.build_derived(); *out_ptr = s.gpu_nodes4.data(); *out_count = s.gpu_nodes4.size(); es = sizeof(GpuNode4); break;
+      case LP_SCENE_GPU_NODES4H: s.build_derived(); *out_ptr = s.gpu_nodes4h.data(); *out_count = s.gpu_nodes4h.size(); es = sizeof(GpuNode4h); break;
       case LP_SCENE_ATLAS_BLOCKS: s.build_derived(); *out_ptr = s.atlas.gpu_blocks.data(); *out_count = s.atlas.blocks.size(); es = 16; break;
       case LP_SCENE_ATLAS_TEXELS: s.build_derived(); *out_ptr = s.atlas.texels.data(); *out_count = s.atlas.texels.size() / 4; es = 4; break;
       default: return fail(LP_ERR_INVALID_ARG, "unknown scene array");

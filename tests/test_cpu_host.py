@@ -413,3 +413,30 @@ def test_ingest_survives_mutated_inputs():
                           "--seed", "3"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "'rejected'" in out.stdout
+
+
+def test_fp16_node_boxes_are_the_fp32_boxes_rounded_outwards():
+    """The production traversal reads 4-wide nodes whose child boxes are binary16: every lower
+    bound is the largest half <= the fp32 value, every upper bound the smallest half >= it
+    (conservative and tight), children unchanged -- checked against numpy's float16 on every
+    node of a scene with coordinates from 1e-3 to 40 (halves from subnormal-ish to coarse)."""
+    rng = np.random.default_rng(9)
+    s = lb.Scene()
+    for scale in (1e-3, 0.3, 40.0):
+        c = rng.uniform(-1, 1, (1500, 1, 3)) * scale
+        pos = (c + rng.normal(scale=0.02 * scale, size=(1500, 3, 3))).reshape(-1, 3)
+        b = s.blas.add_bvh(pos.astype(np.float32))
+        s.blas.add_instance(b, np.eye(4, dtype=np.float32), 0)
+    n4, h4 = s.array(_ffi.SCENE_GPU_NODES4), s.array(_ffi.SCENE_GPU_NODES4H)
+    assert len(n4) == len(h4) and s.fp16_node_boxes
+    assert np.array_equal(n4["child"], h4["child"])
+    live = (n4["child"] != 0x7FFFFFFF)[:, None, :].repeat(3, 1)
+    lo32, hi32 = n4["lo"], n4["hi"]
+    lo16, hi16 = h4["box"][:, :3].astype(np.float32), h4["box"][:, 3:].astype(np.float32)
+    assert (lo16 <= lo32)[live].all() and (hi16 >= hi32)[live].all()
+    up = np.nextafter(h4["box"][:, :3], np.float16(np.inf)).astype(np.float32)
+    dn = np.nextafter(h4["box"][:, 3:], np.float16(-np.inf)).astype(np.float32)
+    assert (up > lo32)[live].all() and (dn < hi32)[live].all()
+    # empty slots: inverted infinite boxes in both
+    assert np.isposinf(lo16[~live]).all() and np.isneginf(hi16[~live]).all()
+    assert live.sum() > 3000
