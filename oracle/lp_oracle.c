@@ -420,6 +420,24 @@ int lpo_any_hit_bvh(const lpo_scene *s, const float o[3], const float d[3], floa
   return tlas_traverse(s, o, d, tmin, tmax, &h, 1, stats);
 }
 
+/* Batch of closest hits (OpenMP over rays) for the large known-answer tests: mode 0 = brute
+ * force, 1 = BVH.  origins / directions: 3 floats per ray; outputs one entry per ray. */
+void lpo_closest_hit_batch(const lpo_scene *s, size_t n, const float *origins,
+                           const float *directions, int mode, uint32_t *instance,
+                           uint32_t *primitive, float *t, float *u, float *v) {
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (long long i = 0; i < (long long)n; ++i) {
+    lpo_hit h;
+    if (mode == 0) lpo_closest_hit_brute(s, origins + 3 * i, directions + 3 * i, 0.0f, INFINITY, &h);
+    else lpo_closest_hit_bvh(s, origins + 3 * i, directions + 3 * i, 0.0f, INFINITY, &h, NULL);
+    instance[i] = h.instance;
+    primitive[i] = h.primitive;
+    t[i] = h.t;
+    u[i] = h.u;
+    v[i] = h.v;
+  }
+}
+
 /* ------------------------------------------------------------------ camera */
 void lpo_camera_from_view(const float view[16], uint32_t w, uint32_t h, float v_fov,
                           lp_camera *cam) {

@@ -87,6 +87,11 @@ void lpo_two_nearest_brute(const lpo_scene *s, const float o[3], const float d[3
 /* closest hit through the canonical TLAS/BLAS BVH2 (near-child-first, t_max culling) */
 void lpo_closest_hit_bvh(const lpo_scene *s, const float o[3], const float d[3], float tmin,
                          float tmax, lpo_hit *hit, lpo_stats *stats);
+/* closest hits of n rays (3 floats per origin / direction), OpenMP over rays; mode 0 = brute
+ * force, 1 = BVH */
+void lpo_closest_hit_batch(const lpo_scene *s, size_t n, const float *origins,
+                           const float *directions, int mode, uint32_t *instance,
+                           uint32_t *primitive, float *t, float *u, float *v);
 /* any hit (shadow rays): 1 if occluded */
 int lpo_any_hit_bvh(const lpo_scene *s, const float o[3], const float d[3], float tmin, float tmax,
                     lpo_stats *stats);

@@ -234,6 +234,19 @@ def closest_hit(oscene: OracleScene, o, d, mode: int = 1, tmin=0.0, tmax=np.inf)
     return hit
 
 
+def closest_hit_batch(oscene: OracleScene, origins, directions, mode: int = 1):
+    """(instance, primitive, t, u, v) arrays for n rays; mode 0 = brute force, 1 = BVH."""
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+    n = len(o)
+    inst, prim = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    t, u, v = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().lpo_closest_hit_batch(C.byref(oscene.c), C.c_size_t(n), p(o), p(d), C.c_int(mode),
+                                p(inst), p(prim), p(t), p(u), p(v))
+    return inst, prim, t, u, v
+
+
 def any_hit(oscene: OracleScene, o, d, tmin, tmax, mode: int = 1) -> bool:
     oo = (C.c_float * 3)(*o)
     dd = (C.c_float * 3)(*d)
