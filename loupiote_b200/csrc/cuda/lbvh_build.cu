@@ -231,6 +231,9 @@ struct Workspace {
       j.big = (uint32_t *)take(m * 4);
       j.idx2 = (uint32_t *)take(m * 4);
       tlas_ids = (uint32_t *)take(m * 4);
+      j.prims = (uint32_t *)take(m * 4);
+      j.visits2 = (uint32_t *)take(m * 4);
+      j.cost = (float *)take(m * 4);
       j.frontier = (uint32_t *)take(4 * m * 4);
       j.level_count = (uint32_t *)take((kMaxLevels + 3) * 4);
       root2 = (uint32_t *)take(ns * 4);
@@ -458,6 +461,13 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
   // the grandchildren rule.
   const char *cb = std::getenv("LP_LBVH_COLLAPSE");
   j.collapse_by_area = cb ? (uint32_t)(std::atoi(cb) != 0) : 1u;
+  // LP_LBVH_TREELETS=<passes> (default 0 = off): treelet restructuring of the binary trees
+  // (Karras & Aila 2013, lbvh_core.h section 4b).  Validated on the host only so far (optimal
+  // against exhaustive search, -5 % surface-area cost after two passes); off until it has run
+  // and been measured on a GPU.
+  const char *tp = std::getenv("LP_LBVH_TREELETS");
+  j.treelet_passes = tp ? (uint32_t)std::min(8, std::max(0, std::atoi(tp))) : 0u;
+  j.treelet_gamma = 7;
   BlasInput in;
   in.vertices = g->vertices.ptr;
   in.indices = g->indices.ptr;

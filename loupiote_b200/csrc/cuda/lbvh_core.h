@@ -60,6 +60,11 @@ struct Job {
   uint32_t max_leaf = 4;  // 4 for a BLAS, 1 for the TLAS
   uint32_t tlas = 0;      // leaf reference = instance id instead of a triangle range
   uint32_t collapse_by_area = 0;  // 4-wide collapse: 0 = grandchildren, 1 = largest area first
+  uint32_t treelet_passes = 0;    // > 0: treelet restructuring of the binary tree (section 4b)
+  uint32_t treelet_gamma = 7;     // smallest subtree (primitives) that roots a treelet
+  float *cost = nullptr;          // treelet pass: surface-area cost of every interior node
+  uint32_t *prims = nullptr;      //               primitives below it
+  uint32_t *visits2 = nullptr;    //               arrival counters, zeroed before every pass
   const Segment *segs = nullptr;
   const uint32_t *slot_seg = nullptr;  // segment of every slot
   float4 *seg_lo = nullptr, *seg_hi = nullptr;    // bounds of every segment
@@ -131,8 +136,12 @@ __device__ __forceinline__ int clz32(uint32_t x) { return __clz((int)x); }
 // boxes written by OTHER threads of the same launch (bottom-up fit) are read through L2: an
 // L1 line fetched earlier for a neighbouring node may hold the stale value
 __device__ __forceinline__ float4 ld_box(const float4 *p) { return __ldcg(p); }
+__device__ __forceinline__ uint32_t ld_u32(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ float ld_f32(const float *p) { return __ldcg(p); }
 #else
 inline float4 ld_box(const float4 *p) { return *p; }
+inline uint32_t ld_u32(const uint32_t *p) { return *p; }
+inline float ld_f32(const float *p) { return *p; }
 inline void atomic_min_f(float *a, float v) { if (v < *a) *a = v; }
 inline void atomic_max_f(float *a, float v) { if (v > *a) *a = v; }
 inline void grow_segment(float4 *seg_lo, float4 *seg_hi, uint32_t s, const float4 &lo,
@@ -320,6 +329,203 @@ LBVH_HD void fit_from_leaf(const Job &j, uint32_t pos) {
     j.node_lo[cur] = lo;
     j.node_hi[cur] = hi;
     cur = j.parent[cur];
+  }
+}
+
+// ------------------------------------------------------------------ 4b. treelet restructuring
+// Karras & Aila 2013, "Fast Parallel Construction of High-Quality Bounding Volume
+// Hierarchies": bottom-up (like the fit), every interior node of >= gamma primitives roots a
+// treelet of up to 7 leaves -- grown from its two children by always opening the leaf with
+// the largest area -- whose best topology under the surface-area cost is found by dynamic
+// programming over the 2^7 subsets of its leaves and written back into the treelet's own
+// interior node slots.  Only nodes that stay interior in the output (big) are opened or
+// rewritten, so the leaves of the output tree keep their contiguous triangle ranges; a
+// rewritten node stays interior whatever it holds.  Lower treelets are finished before the
+// thread that completes a node moves up, so concurrent threads work on disjoint subtrees; all
+// reads of what other threads wrote in the same launch go through L2 (ld_u32 / ld_f32 / ld_box).
+LBVH_HD bool link_is_leaf(const Job &j, uint32_t link);  // section 5
+
+constexpr float kTreeletCi = 1.2f;  // cost of visiting an interior node (the paper's C_i)
+constexpr float kTreeletCt = 1.0f;  // cost of testing a triangle        (the paper's C_t)
+constexpr int kTreeletLeaves = 7;
+
+LBVH_HD int popcount7(int x) {
+  int n = 0;
+  for (int k = 0; k < kTreeletLeaves; ++k) n += x >> k & 1;
+  return n;
+}
+LBVH_HD float half_area(const float4 &lo, const float4 &hi) {
+  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+LBVH_HD uint32_t link_prims(const Job &j, uint32_t link) {
+  return (link & kLinkLeaf) ? 1u : ld_u32(j.prims + link);
+}
+LBVH_HD float link_cost(const Job &j, uint32_t link) {
+  if (!(link & kLinkLeaf)) return ld_f32(j.cost + link);
+  float4 lo, hi;
+  link_box(j, link, lo, hi);
+  return kTreeletCt * half_area(lo, hi);
+}
+LBVH_HD void set_parent(const Job &j, uint32_t link, uint32_t parent) {
+  if (link & kLinkLeaf) j.leaf_parent[link & ~kLinkLeaf] = parent;
+  else j.parent[link] = parent;
+}
+
+// best topology of the treelet rooted at `root` (whose subtrees are complete); sets cost[root]
+LBVH_HD void restructure_treelet(const Job &j, uint32_t root) {
+  uint32_t leaves[kTreeletLeaves], nodes[kTreeletLeaves - 1];
+  int n = 2, n_nodes = 1;
+  nodes[0] = root;
+  leaves[0] = ld_u32(j.left + root);
+  leaves[1] = ld_u32(j.right + root);
+  while (n < kTreeletLeaves) {
+    int best = -1;
+    float best_area = -1.0f;
+    for (int k = 0; k < n; ++k) {
+      if (link_is_leaf(j, leaves[k])) continue;  // an output leaf is never opened
+      float4 lo, hi;
+      link_box(j, leaves[k], lo, hi);
+      const float a = half_area(lo, hi);
+      if (a > best_area) {
+        best_area = a;
+        best = k;
+      }
+    }
+    if (best < 0) break;
+    const uint32_t open = leaves[best];
+    nodes[n_nodes++] = open;
+    leaves[best] = ld_u32(j.left + open);
+    leaves[n++] = ld_u32(j.right + open);
+  }
+  float4 leaf_lo[kTreeletLeaves], leaf_hi[kTreeletLeaves];
+  float c_opt[1 << kTreeletLeaves];
+  uint8_t p_opt[1 << kTreeletLeaves];
+  for (int k = 0; k < n; ++k) {
+    link_box(j, leaves[k], leaf_lo[k], leaf_hi[k]);
+    c_opt[1 << k] = link_cost(j, leaves[k]);
+    p_opt[1 << k] = 0;
+  }
+  const int full = (1 << n) - 1;
+  // subsets in increasing numeric order: every proper subset of s is smaller than s
+  for (int s = 3; s <= full; ++s) {
+    if ((s & (s - 1)) == 0) continue;  // singleton
+    float4 lo = leaf_lo[0], hi = leaf_hi[0];
+    bool first = true;
+    for (int k = 0; k < n; ++k) {
+      if (!(s >> k & 1)) continue;
+      if (first) {
+        lo = leaf_lo[k];
+        hi = leaf_hi[k];
+        first = false;
+      } else {
+        lo.x = fmin_(lo.x, leaf_lo[k].x); lo.y = fmin_(lo.y, leaf_lo[k].y); lo.z = fmin_(lo.z, leaf_lo[k].z);
+        hi.x = fmax_(hi.x, leaf_hi[k].x); hi.y = fmax_(hi.y, leaf_hi[k].y); hi.z = fmax_(hi.z, leaf_hi[k].z);
+      }
+    }
+    // every unordered partition {p, s ^ p} once: p runs over the subsets that hold s's lowest bit
+    const int delta = (s - 1) & s;
+    int p = (-delta) & s, best_p = 0, best_skew = 99;
+    float best = 3.402823466e38f;
+    do {
+      // equal costs (coincident boxes: every topology costs the same) go to the more balanced
+      // split, or duplicates would be chained into a list as deep as the treelet
+      const float c = c_opt[p] + c_opt[s ^ p];
+      int skew = popcount7(p) - popcount7(s ^ p);
+      skew = skew < 0 ? -skew : skew;
+      if (c < best || (c == best && skew < best_skew)) {
+        best = c;
+        best_p = p;
+        best_skew = skew;
+      }
+      p = (p - delta) & s;
+    } while (p != 0);
+    c_opt[s] = kTreeletCi * half_area(lo, hi) + best;
+    p_opt[s] = (uint8_t)best_p;
+  }
+  // keep the topology unless the optimum is strictly cheaper: with coincident boxes every
+  // topology costs the same, and the radix tree's position-balanced one is the shallowest
+  {
+    float4 lo = ld_box(j.node_lo + root), hi = ld_box(j.node_hi + root);
+    const float current = kTreeletCi * half_area(lo, hi) + link_cost(j, ld_u32(j.left + root)) +
+                          link_cost(j, ld_u32(j.right + root));
+    if (!(c_opt[full] < current * (1.0f - 1e-6f))) {
+      j.cost[root] = current;
+      return;
+    }
+  }
+  // write the optimum back into the treelet's interior slots, top-down
+  int stack_set[kTreeletLeaves], stack_node[kTreeletLeaves], top = 0, used = 1;
+  stack_set[0] = full;
+  stack_node[0] = (int)nodes[0];
+  top = 1;
+  while (top > 0) {
+    --top;
+    const int s = stack_set[top];
+    const uint32_t at = (uint32_t)stack_node[top];
+    const int halves[2] = {(int)p_opt[s], s ^ (int)p_opt[s]};
+    uint32_t links[2];
+    for (int c = 0; c < 2; ++c) {
+      const int h = halves[c];
+      if ((h & (h - 1)) == 0) {
+        int k = 0;
+        while (!(h >> k & 1)) ++k;
+        links[c] = leaves[k];
+      } else {
+        links[c] = nodes[used++];
+        stack_set[top] = h;
+        stack_node[top] = (int)links[c];
+        ++top;
+      }
+      set_parent(j, links[c], at);
+    }
+    j.left[at] = links[0];
+    j.right[at] = links[1];
+    float4 lo = leaf_lo[0], hi = leaf_hi[0];
+    uint32_t count = 0;
+    bool first = true;
+    for (int k = 0; k < n; ++k) {
+      if (!(s >> k & 1)) continue;
+      count += link_prims(j, leaves[k]);
+      if (first) {
+        lo = leaf_lo[k];
+        hi = leaf_hi[k];
+        first = false;
+      } else {
+        lo.x = fmin_(lo.x, leaf_lo[k].x); lo.y = fmin_(lo.y, leaf_lo[k].y); lo.z = fmin_(lo.z, leaf_lo[k].z);
+        hi.x = fmax_(hi.x, leaf_hi[k].x); hi.y = fmax_(hi.y, leaf_hi[k].y); hi.z = fmax_(hi.z, leaf_hi[k].z);
+      }
+    }
+    lo.w = hi.w = 0.0f;
+    j.node_lo[at] = lo;
+    j.node_hi[at] = hi;
+    j.cost[at] = c_opt[s];
+    j.prims[at] = count;
+  }
+}
+
+// one thread per SORTED position, after the fit: climbs like it (own arrival counters)
+LBVH_HD void treelets_from_leaf(const Job &j, uint32_t pos) {
+  if (j.segs[j.slot_seg[pos]].count < 2) return;
+  uint32_t cur = j.leaf_parent[pos];
+  while (cur != kNone) {
+    fence();
+    if (atomic_inc_u32(&j.visits2[cur], 1u) == 0u) return;
+    fence();
+    const uint32_t l = ld_u32(j.left + cur), r = ld_u32(j.right + cur);
+    const uint32_t count = link_prims(j, l) + link_prims(j, r);
+    float4 lo, hi;
+    lo = ld_box(j.node_lo + cur);
+    hi = ld_box(j.node_hi + cur);
+    j.prims[cur] = count;
+    if (!j.big[cur]) {
+      j.cost[cur] = kTreeletCt * half_area(lo, hi) * (float)count;  // (inside) an output leaf
+    } else if (count >= j.treelet_gamma) {
+      restructure_treelet(j, cur);
+    } else {
+      j.cost[cur] = kTreeletCi * half_area(lo, hi) + link_cost(j, l) + link_cost(j, r);
+    }
+    cur = ld_u32(j.parent + cur);
   }
 }
 
@@ -573,6 +779,10 @@ struct FitOp {
   Job j;
   LBVH_HD void operator()(uint32_t i) const { fit_from_leaf(j, i); }
 };
+struct TreeletOp {
+  Job j;
+  LBVH_HD void operator()(uint32_t i) const { treelets_from_leaf(j, i); }
+};
 struct DepthOp {
   Job j;
   LBVH_HD void operator()(uint32_t i) const { depth_from_leaf(j, i); }
@@ -616,6 +826,10 @@ inline uint32_t phase_a(Exec &ex, const Job &j, const BlasInput *blas, const Tla
   ex.sort(keys_tmp, vals_tmp, j);
   ex.for_each(j.n_slots, RadixOp{j});
   ex.for_each(j.n_slots, FitOp{j});
+  for (uint32_t pass = 0; pass < j.treelet_passes; ++pass) {
+    ex.zero(j.visits2, j.n_slots);
+    ex.for_each(j.n_slots, TreeletOp{j});
+  }
   ex.for_each(j.n_slots, DepthOp{j});
   ex.scan(j.big, j.idx2, j.n_slots);
   return ex.read(j.idx2 + (j.n_slots - 1u)) + ex.read(j.big + (j.n_slots - 1u));

@@ -51,7 +51,8 @@ struct HostExec {
 struct Workspace {
   std::vector<Segment> segs;
   std::vector<uint32_t> slot_seg, vals, left, right, parent, leaf_parent, range_first, range_last,
-      visits, big, idx2, frontier, level_count, vals_tmp;
+      visits, big, idx2, frontier, level_count, vals_tmp, prims, visits2;
+  std::vector<float> cost;
   std::vector<uint64_t> keys, keys_tmp;
   std::vector<float4> seg_lo, seg_hi, prim_lo, prim_hi, leaf_lo, leaf_hi, node_lo, node_hi;
   Job job;
@@ -63,8 +64,9 @@ struct Workspace {
       n += counts[s];
     }
     const size_t m = std::max<uint32_t>(n, 1u);
+    cost.assign(m, -1.0f);
     for (auto *v : {&vals, &left, &right, &parent, &leaf_parent, &range_first, &range_last,
-                    &visits, &big, &idx2, &vals_tmp})
+                    &visits, &big, &idx2, &vals_tmp, &prims, &visits2})
       v->assign(m, 0xCDCDCDCDu);  // poison: nothing may rely on zero-initialised memory
     frontier.assign(4 * m, 0xCDCDCDCDu);
     level_count.assign(kMaxLevels + 3, 0xCDCDCDCDu);  // + node counter, 2-wide depth
@@ -90,17 +92,24 @@ struct Workspace {
     j.visits = visits.data(); j.big = big.data(); j.idx2 = idx2.data();
     j.frontier = frontier.data(); j.level_count = level_count.data();
     j.n_nodes4 = level_count.data() + kMaxLevels + 1;
+    j.cost = cost.data();
+    j.prims = prims.data();
+    j.visits2 = visits2.data();
   }
 };
 
 }  // namespace
 
-static uint32_t g_max_leaf = 4, g_collapse_by_area = 0;
+static uint32_t g_max_leaf = 4, g_collapse_by_area = 0, g_treelet_passes = 0, g_treelet_gamma = 7;
 
 extern "C" {
 
 void lbvh_emu_set_max_leaf(uint32_t n) { g_max_leaf = n; }
 void lbvh_emu_set_collapse_by_area(uint32_t on) { g_collapse_by_area = on; }
+void lbvh_emu_set_treelets(uint32_t passes, uint32_t gamma) {
+  g_treelet_passes = passes;
+  g_treelet_gamma = gamma;
+}
 
 // Builds every BLAS of a scene.  seg arrays have n_segments entries; nodes2 / nodes4 / tris
 // are caller-allocated with the given capacities (in nodes / triangles).  out[0] = 2-wide
@@ -117,6 +126,8 @@ int lbvh_emu_build_blas(const float *vertices, const uint32_t *indices, const ui
   Job &j = w.job;
   j.max_leaf = g_max_leaf;
   j.collapse_by_area = g_collapse_by_area;
+  j.treelet_passes = g_treelet_passes;
+  j.treelet_gamma = g_treelet_gamma;
   j.tlas = 0;
   j.base2 = base2;
   j.base4 = base4;

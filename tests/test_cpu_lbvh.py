@@ -34,8 +34,8 @@ TRI = np.dtype([("v0", "<f4", 3), ("id", "<u4"), ("v1", "<f4", 4), ("v2", "<f4",
                 ("pad", "<f4", 4)])
 
 
-@pytest.fixture(scope="module", params=[(2, 1), (4, 0), (3, 1)],
-                ids=["leaf2-area", "leaf4-grandchildren", "leaf3-area"])
+@pytest.fixture(scope="module", params=[(2, 1, 0), (4, 0, 0), (3, 1, 0), (2, 1, 2)],
+                ids=["leaf2-area", "leaf4-grandchildren", "leaf3-area", "leaf2-area-treelets"])
 def emu(request):
     """The emulated builder: leaves of <= 2 triangles + largest-area-first collapse (the device
     defaults), and the other settings of both knobs."""
@@ -51,7 +51,9 @@ def emu(request):
     lib.lbvh_emu_morton.argtypes = [C.c_float] * 3
     lib.lbvh_emu_set_max_leaf(C.c_uint32(request.param[0]))
     lib.lbvh_emu_set_collapse_by_area(C.c_uint32(request.param[1]))
+    lib.lbvh_emu_set_treelets(C.c_uint32(request.param[2]), C.c_uint32(7))
     lib.max_leaf = request.param[0]
+    lib.treelets = request.param[2]
     return lib
 
 
@@ -328,3 +330,88 @@ def test_empty_scene_and_single_instance(emu):
     rc = emu.lbvh_emu_build_tlas(_p(z), _p(z), _p(z), _p(z), C.c_uint32(0), _p(z), C.c_uint32(1),
                                  _p(z), C.c_uint32(1), _p(root2), _p(root4), _p(out))
     assert rc == 0 and root4[0] == NONE and root2[0] == NONE
+
+
+def _sah2(b, ref, ci=1.2, ct=1.0):
+    """Surface-area cost of the 2-wide tree behind `ref` (C_i per interior node, C_t per
+    triangle, both weighted by the half area of the node's box)."""
+    def area(lo, hi):
+        d = np.maximum(hi.astype(np.float64) - lo, 0)
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0]
+
+    def rec(ref, lo, hi):
+        if ref & LEAF:
+            return ct * area(lo, hi) * (((ref >> 28) & 7) + 1)
+        q = b["nodes2"][ref]["q"]
+        ch = b["nodes2"][ref]["child"]
+        return ci * area(lo, hi) + rec(int(ch[0]), q[0:3], q[3:6]) + rec(int(ch[1]), q[6:9], q[9:12])
+
+    q = b["nodes2"][ref]["q"]
+    lo, hi = np.minimum(q[0:3], q[6:9]), np.maximum(q[3:6], q[9:12])
+    return rec(ref, lo, hi)
+
+
+@pytest.mark.parametrize("n_tris,seed", [(5, 0), (6, 1), (7, 2), (7, 3)])
+def test_treelet_restructuring_finds_the_optimal_small_tree(emu, n_tris, seed):
+    """A BLAS of <= 7 triangles with single-triangle leaves IS one treelet: after one pass its
+    surface-area cost must equal the minimum over ALL binary trees on those leaves, computed
+    here by an independent exhaustive search (checks the subset DP and its partition walk)."""
+    from itertools import combinations
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n_tris, 1, 3)) * 4 + rng.normal(0, 0.3, (n_tris, 3, 3))).astype(np.float32)
+    s = lb.Scene()
+    s.blas.add_bvh(pos.reshape(-1, 3))
+    emu.lbvh_emu_set_max_leaf(C.c_uint32(1))
+    emu.lbvh_emu_set_treelets(C.c_uint32(1), C.c_uint32(2))
+    try:
+        b = build_blas(emu, s, base2=0, base4=0)
+        b["max_leaf"] = 1
+        check_blas(b)
+        emu.lbvh_emu_set_treelets(C.c_uint32(0), C.c_uint32(7))
+        plain = build_blas(emu, s, base2=0, base4=0)
+    finally:
+        emu.lbvh_emu_set_max_leaf(C.c_uint32(emu.max_leaf))
+        emu.lbvh_emu_set_treelets(C.c_uint32(emu.treelets), C.c_uint32(7))
+    got, before = _sah2(b, int(b["root2"][1])), _sah2(plain, int(plain["root2"][1]))
+
+    lo, hi = pos.min(1).astype(np.float64), pos.max(1).astype(np.float64)
+
+    def area(idx):
+        d = hi[list(idx)].max(0) - lo[list(idx)].min(0)
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0]
+
+    best = {}
+
+    def opt(sub):
+        if len(sub) == 1:
+            return area(sub)
+        if sub not in best:
+            items = sorted(sub)
+            rest = items[1:]
+            cands = []
+            for k in range(len(rest)):
+                for pick in combinations(rest, k):
+                    left = frozenset([items[0], *pick])
+                    cands.append(opt(left) + opt(sub - left))
+            best[sub] = 1.2 * area(sub) + min(cands)
+        return best[sub]
+
+    want = opt(frozenset(range(n_tris)))
+    assert got == pytest.approx(want, rel=1e-5)
+    assert got <= before * (1 + 1e-6)
+
+
+def test_treelet_passes_lower_the_cost_of_a_real_mesh(emu):
+    """Two passes over a displaced icosphere: the 2-wide surface-area cost falls by > 3 % and
+    the tree stays valid (check_blas) -- the quantity the trace rate follows."""
+    c = scenes.spheres_1m(grid=1, subdivisions=4)
+    costs = []
+    try:
+        for passes in (0, 2):
+            emu.lbvh_emu_set_treelets(C.c_uint32(passes), C.c_uint32(7))
+            b = build_blas(emu, c["scene"], base2=0, base4=0)
+            check_blas(b)
+            costs.append(_sah2(b, int(b["root2"][1])))
+    finally:
+        emu.lbvh_emu_set_treelets(C.c_uint32(emu.treelets), C.c_uint32(7))
+    assert costs[1] < 0.97 * costs[0], costs
