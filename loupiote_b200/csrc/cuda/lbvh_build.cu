@@ -103,6 +103,110 @@ __global__ void __launch_bounds__(256) fill_empty_nodes(float4 *nodes2, float4 *
 
 inline uint32_t blocks_for(uint32_t n) { return (n + 255u) / 256u; }
 
+// ---- one-block executor: a job of <= kBlockJobMax primitives (the TLAS of every BASELINE
+// scene) runs its whole build sequence inside ONE kernel launch: every op is a strided loop of
+// the block's threads between __syncthreads, the sort a rank sort, the scan serial.  All
+// threads call every method together; control flow in phase_a / phase_b only depends on job
+// constants and on values every thread reads identically after a barrier.  Counters that
+// other threads bump with atomics are read through L2 (ld_u32).
+constexpr uint32_t kBlockJobMax = 1024;
+struct BlockExec {
+  template <class Op>
+  __device__ void for_each(uint32_t n, Op op) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) op(i);
+    __threadfence();  // some results are read back through L2 (ld_u32 / ld_box)
+    __syncthreads();
+  }
+  template <class Op>
+  __device__ void for_each_counted(const uint32_t *count, uint32_t, Op op) {
+    for_each(ld_u32(count), op);
+  }
+  __device__ void zero(uint32_t *p, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0u;
+    __syncthreads();
+  }
+  // single segment: position = number of smaller (key, input index) pairs
+  __device__ void sort(const uint64_t *keys_in, const uint32_t *vals_in, const Job &j) {
+    for (uint32_t i = threadIdx.x; i < j.n_slots; i += blockDim.x) {
+      const uint64_t k = keys_in[i];
+      uint32_t rank = 0;
+      for (uint32_t o = 0; o < j.n_slots; ++o) {
+        const uint64_t ko = keys_in[o];
+        rank += (ko < k || (ko == k && o < i)) ? 1u : 0u;
+      }
+      j.keys[rank] = k;
+      j.vals[rank] = vals_in[i];
+    }
+    __syncthreads();
+  }
+  __device__ void scan(const uint32_t *in, uint32_t *out, uint32_t n) {
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      for (uint32_t i = 0; i < n; ++i) {
+        out[i] = acc;
+        acc += in[i];
+      }
+      __threadfence();  // read() looks at the result through L2
+    }
+    __syncthreads();
+  }
+  __device__ uint32_t read(const uint32_t *p) { return ld_u32(p); }
+  __device__ void read_n(const uint32_t *p, uint32_t n, uint32_t *out) {
+    for (uint32_t k = 0; k < n; ++k) out[k] = ld_u32(p + k);
+  }
+};
+
+__device__ __forceinline__ void write_empty_node(float4 *nodes2, float4 *nodes4, uint32_t i) {
+  const float inf = __uint_as_float(0x7F800000u), none = __uint_as_float(kRefNone);
+  float4 *a = nodes2 + 4ull * i;
+  a[0] = make_float4(inf, inf, inf, -inf);
+  a[1] = make_float4(-inf, -inf, inf, inf);
+  a[2] = make_float4(inf, -inf, -inf, -inf);
+  a[3] = make_float4(none, none, 0.f, 0.f);
+  float4 *b = nodes4 + 8ull * i;
+  for (int k = 0; k < 3; ++k) b[k] = make_float4(inf, inf, inf, inf);
+  for (int k = 3; k < 6; ++k) b[k] = make_float4(-inf, -inf, -inf, -inf);
+  b[6] = make_float4(none, none, none, none);
+  b[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void write_half_node(const float4 *nodes4, uint4 *nodes4h, uint32_t i) {
+  const float4 *in = nodes4 + 8ull * i;
+  uint4 *out = nodes4h + 4ull * i;
+  const float4 lx = in[0], ly = in[1], lz = in[2], hx = in[3], hy = in[4], hz = in[5];
+  const float4 ch = in[6];
+  out[0] = make_uint4(pack_half2(lx.x, lx.y, false), pack_half2(lx.z, lx.w, false),
+                      pack_half2(ly.x, ly.y, false), pack_half2(ly.z, ly.w, false));
+  out[1] = make_uint4(pack_half2(lz.x, lz.y, false), pack_half2(lz.z, lz.w, false),
+                      pack_half2(hx.x, hx.y, true), pack_half2(hx.z, hx.w, true));
+  out[2] = make_uint4(pack_half2(hy.x, hy.y, true), pack_half2(hy.z, hy.w, true),
+                      pack_half2(hz.x, hz.y, true), pack_half2(hz.z, hz.w, true));
+  out[3] = make_uint4(__float_as_uint(ch.x), __float_as_uint(ch.y), __float_as_uint(ch.z),
+                      __float_as_uint(ch.w));
+}
+
+// The whole TLAS build in one launch of one block: empty the TLAS region, build into it, fp16
+// copy.  result: n_big, n4, depth4 (0xFFFFFFFF = too deep), depth2.
+__global__ void __launch_bounds__(1024)
+    tlas_block_kernel(Job j, TlasInput in, uint64_t *keys_tmp, uint32_t *vals_tmp,
+                      uint4 *nodes4h, uint32_t tlas_capacity, uint32_t *result) {
+  for (uint32_t i = threadIdx.x; i < tlas_capacity; i += blockDim.x)
+    write_empty_node(j.nodes2, j.nodes4, i);
+  __syncthreads();
+  BlockExec ex;
+  const uint32_t n_big = phase_a(ex, j, (const BlasInput *)nullptr, &in, keys_tmp, vals_tmp);
+  uint32_t n4 = 0, depth2 = 0;
+  const int depth4 = phase_b(ex, j, (const BlasInput *)nullptr, &n4, &depth2);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < tlas_capacity; i += blockDim.x)
+    write_half_node(j.nodes4, nodes4h, i);
+  if (threadIdx.x == 0) {
+    result[0] = n_big;
+    result[1] = n4;
+    result[2] = depth4 < 0 ? 0xFFFFFFFFu : (uint32_t)depth4;
+    result[3] = depth2;
+  }
+}
+
 // Device executor of lbvh_core.h's build sequence.  The first CUDA error sticks; the caller
 // checks `err` once at the end (every later launch on a failed stream is harmless).
 struct DeviceExec {
@@ -235,7 +339,7 @@ struct Workspace {
       j.visits2 = (uint32_t *)take(m * 4);
       j.cost = (float *)take(m * 4);
       j.frontier = (uint32_t *)take(4 * m * 4);
-      j.level_count = (uint32_t *)take((kMaxLevels + 3) * 4);
+      j.level_count = (uint32_t *)take((kMaxLevels + 3 + 4) * 4);  // + 4 result words
       root2 = (uint32_t *)take(ns * 4);
       root4 = (uint32_t *)take(ns * 4);
       j.keys = (uint64_t *)take(m * 8);
@@ -350,16 +454,34 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
   in.instances = sg->instances.ptr;
   in.instance_blas = d_blas_of.ptr;
   in.blas_root_box = d_root_box.ptr;
-  fill_empty_nodes<<<blocks_for(sg->tlas_capacity), 256, 0, st>>>(sg->nodes.ptr, sg->nodes4.ptr,
-                                                                  sg->tlas_capacity);
   DeviceExec ex{st, dev->sm_count};
-  const uint32_t n_big = phase_a(ex, j, nullptr, &in, w.keys_tmp, w.vals_tmp);
-  if (ex.err != cudaSuccess) return cuda_fail(ex.err, "TLAS build");
-  if (n_big > sg->tlas_capacity) return fail(LP_ERR_ACCEL_BUILD, "TLAS larger than its node region");
   uint32_t n4 = 0, tlas_depth2 = 0;
-  const int depth4 = phase_b(ex, j, nullptr, &n4, &tlas_depth2);
-  to_half_nodes_kernel<<<blocks_for(sg->tlas_capacity), 256, 0, st>>>(
-      sg->nodes4.ptr, (uint4 *)sg->nodes4h.ptr, 0u, sg->tlas_capacity);
+  int depth4 = 0;
+  // LP_LBVH_BLOCK_TLAS=1 (opt-in until it has run on a GPU): a TLAS of <= 1024 instances is
+  // built by ONE launch of one block (BlockExec) instead of ~70 launches and 4 read-backs
+  const char *bt = std::getenv("LP_LBVH_BLOCK_TLAS");
+  const bool block_tlas = bt && std::atoi(bt) != 0;
+  if (block_tlas && ids.size() <= kBlockJobMax && sg->tlas_capacity <= 4 * kBlockJobMax) {
+    uint32_t *result = j.level_count + kMaxLevels + 3;  // 4 spare words of the counter block
+    tlas_block_kernel<<<1, 1024, 0, st>>>(j, in, w.keys_tmp, w.vals_tmp, (uint4 *)sg->nodes4h.ptr,
+                                          sg->tlas_capacity, result);
+    ex.note(cudaGetLastError());
+    uint32_t host_result[4] = {0, 0, 0, 0};
+    ex.read_n(result, 4, host_result);
+    n4 = host_result[1];
+    depth4 = host_result[2] == 0xFFFFFFFFu ? -1 : (int)host_result[2];
+    tlas_depth2 = host_result[3];
+  } else {
+    fill_empty_nodes<<<blocks_for(sg->tlas_capacity), 256, 0, st>>>(sg->nodes.ptr, sg->nodes4.ptr,
+                                                                    sg->tlas_capacity);
+    const uint32_t n_big = phase_a(ex, j, nullptr, &in, w.keys_tmp, w.vals_tmp);
+    if (ex.err != cudaSuccess) return cuda_fail(ex.err, "TLAS build");
+    if (n_big > sg->tlas_capacity)
+      return fail(LP_ERR_ACCEL_BUILD, "TLAS larger than its node region");
+    depth4 = phase_b(ex, j, nullptr, &n4, &tlas_depth2);
+    to_half_nodes_kernel<<<blocks_for(sg->tlas_capacity), 256, 0, st>>>(
+        sg->nodes4.ptr, (uint4 *)sg->nodes4h.ptr, 0u, sg->tlas_capacity);
+  }
   uint32_t roots[2] = {kRefNone, kRefNone};
   float box[8] = {0};
   ex.note(cudaMemcpyAsync(&roots[0], w.root2, 4, cudaMemcpyDeviceToHost, st));

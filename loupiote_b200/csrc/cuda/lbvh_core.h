@@ -726,7 +726,9 @@ LBVH_HD void emit_triangle(const Job &j, uint32_t pos, const float4 *vertices,
 //   zero(ptr, n_u32)                      32-bit words to 0
 //   sort(keys_in, vals_in, job)           (segment, key)-ordered into job.keys / job.vals
 //   scan(in, out, n)                      exclusive prefix sum
-//   read(ptr) / read_n(ptr, n, out)       u32s back to the host (synchronises)
+//   read(ptr) / read_n(ptr, n, out)       u32s back to the caller (synchronises)
+// A third executor runs a small job inside ONE thread block (lbvh_build.cu: BlockExec, every
+// op a strided loop between __syncthreads); the sequences are host/device for its sake.
 struct BlasInput {
   const float4 *vertices = nullptr;  // 2 x float4 per lp_vertex
   const uint32_t *indices = nullptr;
@@ -812,8 +814,11 @@ struct EmitTriangleOp {
 // Phase A: boxes -> codes -> sort -> radix tree -> fit -> which interior nodes stay.
 // Returns the number of interior nodes of the output trees (2-wide node count, and an upper
 // bound of the 4-wide node count) so that the caller can size the node arrays.
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable  // instantiated with host executors AND a device one
+#endif
 template <class Exec>
-inline uint32_t phase_a(Exec &ex, const Job &j, const BlasInput *blas, const TlasInput *tlas,
+LBVH_HD uint32_t phase_a(Exec &ex, const Job &j, const BlasInput *blas, const TlasInput *tlas,
                         uint64_t *keys_tmp, uint32_t *vals_tmp) {
   if (j.n_slots == 0) return 0;
   ex.for_each(j.n_segments, InitSegOp{j});
@@ -839,8 +844,11 @@ inline uint32_t phase_a(Exec &ex, const Job &j, const BlasInput *blas, const Tla
 // Returns the depth of the deepest 4-wide tree (0: every root is a leaf), or -1 when a tree
 // is deeper than the traversal stack allows.  *n_nodes4_out = 4-wide nodes written,
 // *depth2_out = interior levels of the deepest 2-wide tree.
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
 template <class Exec>
-inline int phase_b(Exec &ex, const Job &j, const BlasInput *blas, uint32_t *n_nodes4_out,
+LBVH_HD int phase_b(Exec &ex, const Job &j, const BlasInput *blas, uint32_t *n_nodes4_out,
                    uint32_t *depth2_out) {
   *n_nodes4_out = 0;
   *depth2_out = 0;

@@ -204,3 +204,19 @@ def test_lbvh_treelet_restructuring_keeps_hits_and_arrays_valid(device, monkeypa
     first_hit_equals_oracle(device, scene, view, (192, 128))
     test_lbvh_device_arrays_are_valid_trees(device)
     test_lbvh_path_traced_image_is_bit_identical_to_host_built_tree(device)
+
+
+@pytest.mark.skipif(os.environ.get("LP_TEST_LBVH_BLOCK_TLAS", "0") != "1",
+                    reason="the one-block TLAS build is opt-in and not yet confirmed on "
+                           "hardware: set LP_TEST_LBVH_BLOCK_TLAS=1")
+def test_lbvh_one_block_tlas_build(device, monkeypatch):
+    """LP_LBVH_BLOCK_TLAS=1: the TLAS built by one launch of one block (the same build sequence
+    under BlockExec) gives the oracle's hits, valid arrays, and survives instance updates."""
+    monkeypatch.setenv("LP_LBVH_BLOCK_TLAS", "1")
+    c = scenes.spheres_1m(grid=3, subdivisions=3)
+    first_hit_equals_oracle(device, c["scene"], c["view"], (256, 144))
+    scene, view = soup_scene()
+    first_hit_equals_oracle(device, scene, view, (192, 128))
+    test_lbvh_device_arrays_are_valid_trees(device)
+    test_lbvh_update_instances_rebuilds_the_tlas_on_the_device(device)
+    test_lbvh_degenerate_and_empty_scenes(device)
