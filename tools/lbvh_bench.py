@@ -33,12 +33,15 @@ def main() -> None:
     ap.add_argument("--build-repeats", type=int, default=5)
     ap.add_argument("--max-leaf", type=int, default=0, help="LP_LBVH_MAX_LEAF for the device build")
     ap.add_argument("--treelets", type=int, default=-1, help="LP_LBVH_TREELETS (passes)")
+    ap.add_argument("--block-tlas", action="store_true", help="LP_LBVH_BLOCK_TLAS=1")
     args = ap.parse_args()
     import os
     if args.max_leaf:
         os.environ["LP_LBVH_MAX_LEAF"] = str(args.max_leaf)
     if args.treelets >= 0:
         os.environ["LP_LBVH_TREELETS"] = str(args.treelets)
+    if args.block_tlas:
+        os.environ["LP_LBVH_BLOCK_TLAS"] = "1"
 
     def make(deferred):
         t0 = time.perf_counter()
@@ -126,6 +129,7 @@ def main() -> None:
                                           else "deferred build: no host tree"),
                       "max_leaf": args.max_leaf or "default",
                       "treelet_passes": os.environ.get("LP_LBVH_TREELETS", "0"),
+                      "block_tlas": os.environ.get("LP_LBVH_BLOCK_TLAS", "0"),
                       "mrays_per_s": round(rays / sec / 1e6, 1), "rays": int(rays),
                       "ms_per_step": round(sec / args.steps * 1e3, 2), "spp_per_step": args.spp,
                       "node_bytes": sg.stats()["node_bytes"], "timing": "wall clock + synchronize"})
