@@ -11,11 +11,16 @@
 // Algorithm (LBVH): 63-bit Morton code of every primitive's box centre inside its tree's
 // bounds; radix sort; binary radix tree over the sorted codes (Karras 2012, one thread per
 // interior node, ties broken by sorted position); bottom-up box fit (one thread per leaf,
-// the second thread to arrive at a node carries on); subtrees of <= max_leaf primitives become
+// the second thread to arrive at a node carries on); optionally treelet restructuring of the
+// binary tree (Karras & Aila 2013, section 4b); subtrees of <= max_leaf primitives become
 // leaves (a subtree is a contiguous range of the sorted order); 4-wide collapse level by
-// level from the roots (a node's slots are its grandchildren, or a child that is a leaf).
+// level from the roots (largest-area slot opened first, or plain grandchildren).
 // Many trees are built at once: a SEGMENT is one tree (one BLAS, or the TLAS), its
 // primitives a contiguous slice of every per-primitive array.
+//
+// The launch ORDER is here too (phase_a / phase_b over an executor interface): lbvh_build.cu
+// has the device executor (one kernel per op, cub sort / scan) and a one-block executor for
+// small jobs, tests/lbvh_emu.cpp the serial host executor.
 //
 // The tree differs from the host's binned-SAH tree; results do not: closest hit is the
 // lexicographic minimum of (t, instance, primitive) over the triangles a conservative
