@@ -46,6 +46,14 @@ struct Task {
   uint32_t node, first, count;
 };
 
+// bin of a scaled centroid coordinate, clamped BEFORE the conversion: boxes that overflowed to
+// infinity (an instance transform of 1e38) give NaN here, and converting NaN or an
+// out-of-range float to int is undefined
+inline int bin_of(float f) {
+  if (!(f > 0.0f)) return 0;
+  return f < (float)kBins ? (int)f : kBins - 1;
+}
+
 }  // namespace
 
 void build_bvh2(const std::vector<BuildBox> &boxes, uint32_t max_leaf,
@@ -111,8 +119,7 @@ void build_bvh2(const std::vector<BuildBox> &boxes, uint32_t max_leaf,
       }
       for (uint32_t i = t.first; i < t.first + t.count; ++i) {
         const uint32_t p = perm[i];
-        int b = (int)((cen[3 * (size_t)p + axis] - cmin) * scale);
-        b = std::min(std::max(b, 0), kBins - 1);
+        const int b = bin_of((cen[3 * (size_t)p + axis] - cmin) * scale);
         bin_cnt[b]++;
         bin_box[b].grow(boxes[p].lo, boxes[p].hi);
       }
@@ -154,9 +161,7 @@ void build_bvh2(const std::vector<BuildBox> &boxes, uint32_t max_leaf,
         const float scale = (float)kBins / (cmax - cmin);
         auto first = perm.begin() + t.first, last = first + t.count;
         auto it = std::stable_partition(first, last, [&](uint32_t p) {
-          int b = (int)((cen[3 * (size_t)p + best_axis] - cmin) * scale);
-          b = std::min(std::max(b, 0), kBins - 1);
-          return b <= best_split;
+          return bin_of((cen[3 * (size_t)p + best_axis] - cmin) * scale) <= best_split;
         });
         mid = (uint32_t)(it - perm.begin());
       }

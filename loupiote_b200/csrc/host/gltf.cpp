@@ -37,7 +37,14 @@ struct JValue {
     const JValue *v = get(key);
     return (v && v->kind == Num) ? v->num : dflt;
   }
-  long integer(const char *key, long dflt) const { return (long)number(key, (double)dflt); }
+  // integers arrive as JSON numbers: anything that is not a finite value of at most 2^53 in
+  // magnitude (NaN, 1e308, ...) cannot be converted without undefined behaviour and is
+  // mapped to -1, which every caller rejects as an index, an offset or a count
+  long integer(const char *key, long dflt) const {
+    const double v = number(key, (double)dflt);
+    if (!(v >= -9007199254740992.0 && v <= 9007199254740992.0)) return -1;
+    return (long)v;
+  }
   std::string string(const char *key, const char *dflt = "") const {
     const JValue *v = get(key);
     return (v && v->kind == Str) ? v->str : std::string(dflt);
@@ -224,6 +231,49 @@ int component_size(long ct) {
   return 0;
 }
 
+// [offset, offset + length) lies inside a buffer of `size` bytes (no overflow, no negatives)
+bool span_ok(long offset, long length, size_t size) {
+  return offset >= 0 && length >= 0 && (size_t)offset <= size &&
+         (size_t)length <= size - (size_t)offset;
+}
+
+// Where accessor `a` reads: validates bufferView / buffer indices and that `count` elements
+// of `elem` bytes, `stride` apart, lie inside the buffer -- with every quantity taken from
+// the file checked for sign and overflow BEFORE anything is allocated or read.  Returns false
+// for an invalid accessor; *bytes == nullptr (with true) for an accessor without a bufferView
+// (all zeros; sparse accessors are not expanded).
+constexpr size_t kMaxAccessorCount = (size_t)1 << 30;
+bool accessor_view(const Doc &d, const JValue &a, size_t elem, size_t &count,
+                   const uint8_t *&bytes, size_t &stride) {
+  bytes = nullptr;
+  stride = elem;
+  const long n = a.integer("count", 0);
+  if (n < 0 || (size_t)n > kMaxAccessorCount) return false;
+  count = (size_t)n;
+  const JValue *bvp = a.get("bufferView");
+  if (!bvp) return true;
+  const long bv_index = a.integer("bufferView", -1);
+  const JValue *bvs = d.root.get("bufferViews");
+  if (!bvs || bv_index < 0 || (size_t)bv_index >= bvs->size()) return false;
+  const JValue &bv = bvs->arr[bv_index];
+  const long buf = bv.integer("buffer", 0);
+  if (buf < 0 || (size_t)buf >= d.buffers.size()) return false;
+  const std::vector<uint8_t> &buffer = d.buffers[buf];
+  const long bv_off = bv.integer("byteOffset", 0), acc_off = a.integer("byteOffset", 0);
+  const long bv_stride = bv.integer("byteStride", 0);
+  if (bv_off < 0 || acc_off < 0 || bv_stride < 0) return false;
+  if (bv_stride) stride = (size_t)bv_stride;
+  if (!span_ok(bv_off, acc_off, buffer.size())) return false;  // base = bv_off + acc_off
+  const size_t base = (size_t)bv_off + (size_t)acc_off;
+  if (count) {
+    if (elem > buffer.size() - base) return false;
+    const size_t room = buffer.size() - base - elem;  // bytes left for count - 1 strides
+    if (stride == 0 || (count - 1) > room / stride) return false;
+  }
+  bytes = buffer.data() + base;
+  return true;
+}
+
 // Reads accessor `index` as floats (out_comp components per element), following the
 // `gltf` crate's `into_f32` normalisation rules for integer texcoords.
 bool read_accessor_f32(const Doc &d, long index, int want_comp, std::vector<float> &out,
@@ -234,24 +284,16 @@ bool read_accessor_f32(const Doc &d, long index, int want_comp, std::vector<floa
   const int comps = type_components(a.string("type"));
   const long ct = a.integer("componentType", 0);
   const int csz = component_size(ct);
-  count = (size_t)a.integer("count", 0);
+  count = 0;
   if (comps != want_comp || !csz) return false;
+  const uint8_t *bytes = nullptr;
+  size_t stride = 0;
+  if (!accessor_view(d, a, (size_t)comps * csz, count, bytes, stride)) return false;
   out.assign(count * comps, 0.f);
-  const long bv_index = a.integer("bufferView", -1);
-  if (bv_index < 0) return true;  // all zeros (sparse accessors are not expanded)
-  const JValue *bvs = d.root.get("bufferViews");
-  if (!bvs || (size_t)bv_index >= bvs->size()) return false;
-  const JValue &bv = bvs->arr[bv_index];
-  const long buf = bv.integer("buffer", 0);
-  if (buf < 0 || (size_t)buf >= d.buffers.size()) return false;
-  const std::vector<uint8_t> &bytes = d.buffers[buf];
-  const size_t base = (size_t)bv.integer("byteOffset", 0) + (size_t)a.integer("byteOffset", 0);
-  size_t stride = (size_t)bv.integer("byteStride", 0);
-  if (!stride) stride = (size_t)comps * csz;
-  if (count && base + (count - 1) * stride + (size_t)comps * csz > bytes.size()) return false;
+  if (!bytes) return true;  // all zeros (sparse accessors are not expanded)
   const bool normalized = a.get("normalized") && a.get("normalized")->b;
   for (size_t i = 0; i < count; ++i) {
-    const uint8_t *src = bytes.data() + base + i * stride;
+    const uint8_t *src = bytes + i * stride;
     for (int c = 0; c < comps; ++c) {
       float v = 0.f;
       switch (ct) {
@@ -274,23 +316,14 @@ bool read_accessor_u32(const Doc &d, long index, std::vector<uint32_t> &out) {
   const JValue &a = accs->arr[index];
   const long ct = a.integer("componentType", 0);
   const int csz = component_size(ct);
-  const size_t count = (size_t)a.integer("count", 0);
   if (type_components(a.string("type")) != 1 || !csz || ct == 5126) return false;
+  size_t count = 0, stride = 0;
+  const uint8_t *bytes = nullptr;
+  if (!accessor_view(d, a, (size_t)csz, count, bytes, stride)) return false;
   out.assign(count, 0u);
-  const long bv_index = a.integer("bufferView", -1);
-  if (bv_index < 0) return true;
-  const JValue *bvs = d.root.get("bufferViews");
-  if (!bvs || (size_t)bv_index >= bvs->size()) return false;
-  const JValue &bv = bvs->arr[bv_index];
-  const long buf = bv.integer("buffer", 0);
-  if (buf < 0 || (size_t)buf >= d.buffers.size()) return false;
-  const std::vector<uint8_t> &bytes = d.buffers[buf];
-  const size_t base = (size_t)bv.integer("byteOffset", 0) + (size_t)a.integer("byteOffset", 0);
-  size_t stride = (size_t)bv.integer("byteStride", 0);
-  if (!stride) stride = (size_t)csz;
-  if (count && base + (count - 1) * stride + (size_t)csz > bytes.size()) return false;
+  if (!bytes) return true;
   for (size_t i = 0; i < count; ++i) {
-    const uint8_t *src = bytes.data() + base + i * stride;
+    const uint8_t *src = bytes + i * stride;
     switch (csz) {
       case 1: out[i] = src[0]; break;
       case 2: { uint16_t u; std::memcpy(&u, src, 2); out[i] = u; break; }
@@ -460,10 +493,10 @@ lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string 
         if (bvs && (size_t)bv_index < bvs->size()) {
           const JValue &bv = bvs->arr[bv_index];
           const long buf = bv.integer("buffer", 0);
-          const size_t boff = (size_t)bv.integer("byteOffset", 0);
-          const size_t blen = (size_t)bv.integer("byteLength", 0);
-          if (buf >= 0 && (size_t)buf < doc.buffers.size() && boff + blen <= doc.buffers[buf].size())
-            ok = decode_image(doc.buffers[buf].data() + boff, blen, decoded, ierr);
+          const long boff = bv.integer("byteOffset", 0), blen = bv.integer("byteLength", 0);
+          if (buf >= 0 && (size_t)buf < doc.buffers.size() &&
+              span_ok(boff, blen, doc.buffers[buf].size()))
+            ok = decode_image(doc.buffers[buf].data() + boff, (size_t)blen, decoded, ierr);
         }
       } else if (uri.rfind("data:", 0) == 0) {
         const size_t comma = uri.find(',');
@@ -519,19 +552,18 @@ lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string 
     const JValue *nodes = doc.root.get("nodes");
     for (size_t ni = 0; nodes && ni < nodes->size(); ++ni) {
       const JValue &node = nodes->arr[ni];
-      const JValue *mesh = node.get("mesh");
-      if (!mesh || mesh->kind != JValue::Num) continue;
-      const size_t mi = (size_t)mesh->num;
-      if (mi >= prim_entry.size()) continue;
+      const long mesh_index = node.integer("mesh", -1);
+      if (mesh_index < 0 || (size_t)mesh_index >= prim_entry.size()) continue;
+      const size_t mi = (size_t)mesh_index;
       float m[16];
       node_matrix(node, m);
       const JValue *prims = meshes->arr[mi].get("primitives");
       for (size_t pi = 0; pi < prim_entry[mi].size(); ++pi) {
         if (prim_entry[mi][pi] < 0) continue;
-        const JValue *mat = prims->arr[pi].get("material");
-        // missing material -> mat_offset + u32::MAX, wrapping [ref gltf.rs:137-144]
+        // missing (or unusable) material -> mat_offset + u32::MAX, wrapping [ref gltf.rs:137-144]
+        const long mat_i = prims->arr[pi].integer("material", -1);
         const uint32_t material_index =
-            (mat && mat->kind == JValue::Num) ? (uint32_t)mat->num : 0xFFFFFFFFu;
+            (mat_i >= 0 && mat_i < 0xFFFFFFFFL) ? (uint32_t)mat_i : 0xFFFFFFFFu;
         uint32_t material = mat_offset + material_index;
         if (material >= scene.materials.size()) material = 0;
         scene.add_instance((uint32_t)prim_entry[mi][pi], m, material);

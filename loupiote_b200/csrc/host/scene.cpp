@@ -186,7 +186,13 @@ void Scene::ensure_host_bvh() {
   pending_bvh.clear();
 }
 
+static void require_finite(const float m[16]) {
+  for (int i = 0; i < 16; ++i)
+    if (!std::isfinite(m[i])) throw std::invalid_argument("non-finite instance transform");
+}
+
 void Scene::add_instance(uint32_t blas, const float m[16], uint32_t material) {
+  require_finite(m);
   lp_instance inst{};
   std::memcpy(inst.model_to_world, m, 64);
   invert_affine(m, inst.world_to_model);
@@ -197,6 +203,7 @@ void Scene::add_instance(uint32_t blas, const float m[16], uint32_t material) {
 }
 
 void Scene::set_instance_transform(uint32_t i, const float m[16]) {
+  require_finite(m);
   std::memcpy(instances[i].model_to_world, m, 64);
   invert_affine(m, instances[i].world_to_model);
   instances_dirty = true;  // TLAS + instance records only; the BLAS layout stays valid

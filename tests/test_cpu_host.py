@@ -409,10 +409,11 @@ def test_ingest_survives_mutated_inputs():
     down; the --asan mode of the tool rebuilds the host sources with ASan + UBSan)."""
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, str(ROOT / "tools" / "fuzz_ingest.py"), "--n", "600",
-                          "--seed", "3"], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert "'rejected'" in out.stdout
+    for extra in ([], ["--structured"]):
+        out = subprocess.run([sys.executable, str(ROOT / "tools" / "fuzz_ingest.py"), "--n", "500",
+                              "--seed", "3", *extra], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "'rejected'" in out.stdout
 
 
 def test_fp16_node_boxes_are_the_fp32_boxes_rounded_outwards():
@@ -440,3 +441,65 @@ def test_fp16_node_boxes_are_the_fp32_boxes_rounded_outwards():
     # empty slots: inverted infinite boxes in both
     assert np.isposinf(lo16[~live]).all() and np.isneginf(hi16[~live]).all()
     assert live.sum() > 3000
+
+
+def test_gltf_accessor_arithmetic_is_overflow_safe():
+    """Found by tools/fuzz_ingest.py --structured --asan: a negative byteOffset wrapped the
+    bounds check of an accessor and read in front of the buffer.  Offsets, strides, counts and
+    indices from the file are now checked for sign and overflow before anything is allocated
+    or read; hostile values are rejected (the primitive is skipped) or reported, never
+    dereferenced."""
+    import copy
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    from fuzz_ingest import join_glb, split_glb
+    doc, blob = split_glb(GLB.read_bytes())
+    n_tris = 34
+
+    def load(mutate):
+        d = copy.deepcopy(doc)
+        mutate(d)
+        s = lb.Scene()
+        try:
+            lb.loaders.load_gltf(join_glb(d, blob), s)
+        except lb.Error as e:
+            return None, e
+        return s, None
+
+    def tris(scene):
+        return int(scene.array(_ffi.SCENE_ENTRIES)["primitive_count"].sum())
+
+    s, _ = load(lambda d: None)
+    assert tris(s) == n_tris
+    pos_acc = doc["meshes"][0]["primitives"][0]["attributes"]["POSITION"]
+    view = doc["accessors"][pos_acc]["bufferView"]
+    hostile = [
+        lambda d: d["accessors"][pos_acc].__setitem__("byteOffset", -1),
+        lambda d: d["bufferViews"][view].__setitem__("byteOffset", -4),
+        lambda d: d["bufferViews"][view].__setitem__("byteOffset", 2 ** 63),
+        lambda d: d["bufferViews"][view].__setitem__("byteStride", -12),
+        lambda d: d["bufferViews"][view].__setitem__("byteStride", 2 ** 62),
+        lambda d: d["accessors"][pos_acc].__setitem__("count", -3),
+        lambda d: d["accessors"][pos_acc].__setitem__("count", 2 ** 40),
+        lambda d: d["accessors"][pos_acc].__setitem__("count", 1e308),
+        lambda d: d["accessors"][pos_acc].__setitem__("bufferView", -7),
+        lambda d: d["bufferViews"][view].__setitem__("buffer", 2 ** 33),
+    ]
+    for mutate in hostile:
+        s, err = load(mutate)
+        assert err is not None or tris(s) < n_tris   # the broken primitive never loads
+    # indices that are not integers in range
+    for bad in (-6, 2 ** 40, 1e300, 0.5):
+        s, err = load(lambda d, bad=bad: d["nodes"][0].__setitem__("mesh", bad))
+        assert err is not None or s is not None
+        s, err = load(lambda d, bad=bad: d["meshes"][0]["primitives"][0].__setitem__("material", bad))
+        assert err is not None or s is not None
+    # a transform that overflows float is an error, not a NaN in the TLAS builder
+    s, err = load(lambda d: d["nodes"][0].__setitem__("translation", [1e300, 0, 0]))
+    assert err is not None and "non-finite" in str(err)
+    with pytest.raises(lb.Error):
+        sc = lb.Scene()
+        b = sc.blas.add_bvh(np.eye(3, dtype=np.float32))
+        m = np.eye(4, dtype=np.float32)
+        m[0, 3] = np.nan
+        sc.blas.add_instance(b, m, 0)

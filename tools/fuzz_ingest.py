@@ -11,11 +11,15 @@ the mutation reaches the decoder proper.
     python tools/fuzz_ingest.py --n 3000 --seed 1            # the product library
     python tools/fuzz_ingest.py --n 3000 --seed 1 --asan     # host sources rebuilt with
                                                              # -fsanitize=address,undefined
+    python tools/fuzz_ingest.py --n 3000 --structured [--asan]   # well-formed JSON, mutated
+                                                             # meaning (offsets, counts, types)
 (--asan re-executes itself with libasan preloaded; the sanitized library holds the host
 sources only, which is all the ingest path needs.)
 """
 import argparse
+import copy
 import ctypes as C
+import json
 import os
 import random
 import struct
@@ -63,6 +67,90 @@ def mutate(rng: random.Random, data: bytes) -> bytes:
     return bytes(b)
 
 
+def split_glb(glb: bytes):
+    jl = struct.unpack_from("<I", glb, 12)[0]
+    doc = json.loads(glb[20:20 + jl])
+    rest = glb[20 + jl:]
+    blob = rest[8:8 + struct.unpack_from("<I", rest, 0)[0]] if len(rest) >= 8 else b""
+    return doc, blob
+
+
+def join_glb(doc, blob: bytes) -> bytes:
+    js = json.dumps(doc).encode()
+    js += b" " * (-len(js) % 4)
+    total = 12 + 8 + len(js) + 8 + len(blob)
+    return (b"glTF" + struct.pack("<II", 2, total) + struct.pack("<I", len(js)) + b"JSON" + js +
+            struct.pack("<I", len(blob)) + b"BIN\x00" + blob)
+
+
+def mutate_json(rng: random.Random, node):
+    """Structure-aware mutation: walks to a random place of the glTF document and replaces a
+    value with an extreme of the same or another type, drops a key, or duplicates an item --
+    the JSON stays well formed, its meaning does not (offsets past the buffer, negative or
+    huge counts and indices, wrong component types, cyclic / missing references)."""
+    path = []
+    cur = node
+    while isinstance(cur, (dict, list)) and cur and (not path or rng.random() < 0.85):
+        key = rng.choice(list(cur.keys())) if isinstance(cur, dict) else rng.randrange(len(cur))
+        if not path and rng.random() < 0.9:  # mostly where the loader follows references
+            hot = [k for k in ("accessors", "bufferViews", "meshes", "nodes", "materials",
+                               "textures", "images", "buffers") if k in cur]
+            key = rng.choice(hot) if hot else key
+        path.append((cur, key))
+        cur = cur[key]
+    if not path:
+        return
+    parent, key = path[-1]
+    extremes = [-1, 0, 1, 2, 255, 65535, 65536, 2 ** 31 - 1, 2 ** 32 - 1, 2 ** 32, 10 ** 12, -2 ** 31,
+                0.5, -0.0, 1e38, 1e308, None, "", "VEC3", "MAT4", "SCALAR", [], {}, True,
+                5120, 5121, 5123, 5125, 5126, 34962]
+    mode = rng.randrange(4)
+    if mode == 0 or not isinstance(parent, (dict, list)):
+        parent[key] = rng.choice(extremes)
+    elif mode == 1 and isinstance(parent, dict):
+        del parent[key]
+    elif mode == 2 and isinstance(parent, list):
+        parent.append(parent[key])
+    elif isinstance(parent[key], (int, float)) and not isinstance(parent[key], bool):
+        parent[key] = parent[key] + rng.choice([-1, 1, 3, -7, 1000, 0.25])
+    else:
+        parent[key] = rng.choice(extremes)
+
+
+def run_structured(lib: C.CDLL, n: int, seed: int) -> dict:
+    """Well-formed GLBs whose JSON has been mutated structurally (mutate_json), from two seeds:
+    the reference's cornell box and a textured two-material GLB with embedded PNG images."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from _glb import textured_quad_glb
+    z = np.load(ROOT / "tests" / "golden" / "image_fixtures.npz")
+    png = bytes(z["file_png_rgb8"].tobytes())
+    seeds = [(ROOT / "tests" / "golden" / "cornell-box.glb").read_bytes(),
+             textured_quad_glb([png, png], [0, 1], [{"base": 0, "mr": 1}, {"base": 1}])]
+    parts = [split_glb(g) for g in seeds]
+    lib.lp_load_gltf.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    lib.lp_scene_get_array.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    rng = random.Random(seed)
+    counts = {"ok": 0, "rejected": 0}
+    for _ in range(n):
+        doc, blob = parts[rng.randrange(len(parts))]
+        doc = copy.deepcopy(doc)
+        for _ in range(rng.randrange(1, 4)):
+            mutate_json(rng, doc)
+        if rng.random() < 0.1:
+            blob = blob[:rng.randrange(len(blob) + 1)]
+        b = join_glb(doc, blob)
+        h = C.c_void_p()
+        assert lib.lp_scene_create(C.byref(h)) == 0
+        st = lib.lp_load_gltf(b, len(b), h)
+        if st == 0:  # what was accepted must also survive the derived builds (TLAS, layouts)
+            ptr, cnt, es = C.c_void_p(), C.c_size_t(), C.c_size_t()
+            lib.lp_scene_get_array(h, 12, C.byref(ptr), C.byref(cnt), C.byref(es))
+        counts["ok" if st == 0 else "rejected"] += 1
+        lib.lp_scene_destroy(h)
+    return counts
+
+
 def run(lib: C.CDLL, n: int, seed: int) -> dict:
     z = np.load(ROOT / "tests" / "golden" / "image_fixtures.npz")
     images = [bytes(z[k].tobytes()) for k in sorted(z.keys()) if k.startswith("file_")]
@@ -94,11 +182,13 @@ def main() -> None:
     ap.add_argument("--n", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--asan", action="store_true")
+    ap.add_argument("--structured", action="store_true",
+                    help="structure-aware mutations of the glTF JSON instead of byte mutations")
     args = ap.parse_args()
     if args.asan and os.environ.get("LP_FUZZ_CHILD") != "1":
         ASAN_LIB.parent.mkdir(exist_ok=True)
         srcs = sorted(str(p) for p in (ROOT / "loupiote_b200" / "csrc" / "host").glob("*.cpp"))
-        subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+        subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined,float-cast-overflow", "-fno-sanitize-recover=undefined,float-cast-overflow", "-fno-omit-frame-pointer",
                         "-std=c++17", "-shared", "-fPIC", f"-I{ROOT / 'include'}", *srcs, "-o",
                         str(ASAN_LIB)], check=True)
         asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True,
@@ -114,7 +204,9 @@ def main() -> None:
         sys.path.insert(0, str(ROOT))
         from loupiote_b200 import _ffi
         lib = _ffi.lib()
-    print({"n": args.n, "seed": args.seed, "sanitized": bool(args.asan), **run(lib, args.n, args.seed)})
+    counts = (run_structured if args.structured else run)(lib, args.n, args.seed)
+    print({"n": args.n, "seed": args.seed, "sanitized": bool(args.asan),
+           "structured": bool(args.structured), **counts})
 
 
 if __name__ == "__main__":
