@@ -447,7 +447,7 @@ __global__ void gather_sample_kernel(const float4 *__restrict__ rad, float4 *__r
 extern "C" {
 
 // ------------------------------------------------------------------ Device
-LP_API lp_status lp_device_create(int cuda_ordinal, lp_device **out) {
+LP_API lp_status lp_device_create(int cuda_ordinal, lp_device **out) try {
   if (!out) return fail(LP_ERR_INVALID_ARG, "out is NULL");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -477,9 +477,9 @@ LP_API lp_status lp_device_create(int cuda_ordinal, lp_device **out) {
   }
   *out = d;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_device_destroy(lp_device *dev) {
+LP_API lp_status lp_device_destroy(lp_device *dev) try {
   if (!dev) return LP_OK;
   cudaSetDevice(dev->ordinal);
   if (dev->stream2) {
@@ -492,23 +492,23 @@ LP_API lp_status lp_device_destroy(lp_device *dev) {
   }
   delete dev;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_device_stream(lp_device *dev, void **out_cuda_stream) {
+LP_API lp_status lp_device_stream(lp_device *dev, void **out_cuda_stream) try {
   if (!dev || !out_cuda_stream) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   *out_cuda_stream = (void *)dev->stream;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_device_synchronize(lp_device *dev) {
+LP_API lp_status lp_device_synchronize(lp_device *dev) try {
   if (!dev) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   CUDA_CHECK(cudaSetDevice(dev->ordinal));
   CUDA_CHECK(cudaStreamSynchronize(dev->stream));
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_device_info(lp_device *dev, char *name, size_t name_cap, int *sm_count,
-                                int *cc_major, int *cc_minor, size_t *total_mem) {
+                                int *cc_major, int *cc_minor, size_t *total_mem) try {
   if (!dev) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (name && name_cap) {
     std::strncpy(name, dev->prop.name, name_cap - 1);
@@ -519,7 +519,7 @@ LP_API lp_status lp_device_info(lp_device *dev, char *name, size_t name_cap, int
   if (cc_minor) *cc_minor = dev->prop.minor;
   if (total_mem) *total_mem = dev->prop.totalGlobalMem;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 // ------------------------------------------------------------------ SceneGPU / ProbeGPU
 }  // extern "C"
@@ -614,7 +614,7 @@ lp_status lp::refresh_small_tables(lp_scene_gpu *sg, Scene &s, cudaStream_t st) 
 
 extern "C" {
 
-LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp_scene_gpu **out) {
+LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp_scene_gpu **out) try {
   if (!scene || !dev || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   Scene &s = scene_of(scene);
   try {
@@ -657,13 +657,13 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   g->layout_version = s.layout_version;
   *out = g;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 // Instance::set_transform after the upload [ref standalone/src/lib.rs:118-121, where the
 // reference moves an instance BEFORE its one upload]: the TLAS region of the node arrays, the
 // instance records and the (small) material / emission / light tables are refreshed; the
 // BLAS nodes, triangles, vertices and the atlas stay where they are.
-LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene) {
+LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene) try {
   if (!sg || !scene) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   Scene &s = scene_of(scene);
   if (sg->lbvh) return lbvh_update_instances(sg, s);  // TLAS rebuilt on the device
@@ -700,10 +700,10 @@ LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene
   sg->max_depth = s.gpu_max_depth;
   sg->half_boxes_ok = s.half_boxes_ok;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_scene_gpu_read_array(lp_scene_gpu *sg, int which, void *dst, size_t cap_bytes,
-                                         size_t *out_bytes) {
+                                         size_t *out_bytes) try {
   if (!sg || !out_bytes) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   const DevBuf<float4> *buf = nullptr;
   switch (which) {
@@ -721,34 +721,34 @@ LP_API lp_status lp_scene_gpu_read_array(lp_scene_gpu *sg, int which, void *dst,
   CUDA_CHECK(cudaStreamSynchronize(sg->dev->stream));
   CUDA_CHECK(cudaMemcpy(dst, buf->ptr, *out_bytes, cudaMemcpyDeviceToHost));
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_scene_gpu_roots(const lp_scene_gpu *sg, uint32_t *tlas_root,
-                                    uint32_t *tlas_root4) {
+                                    uint32_t *tlas_root4) try {
   if (!sg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (tlas_root) *tlas_root = sg->sc.tlas_root;
   if (tlas_root4) *tlas_root4 = sg->sc.tlas_root4;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_scene_gpu_destroy(lp_scene_gpu *sg) {
+LP_API lp_status lp_scene_gpu_destroy(lp_scene_gpu *sg) try {
   if (sg) cudaSetDevice(sg->dev->ordinal);
   delete sg;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_scene_gpu_stats(const lp_scene_gpu *sg, size_t *node_bytes, size_t *tri_bytes,
-                                    size_t *total_bytes, uint32_t *max_depth) {
+                                    size_t *total_bytes, uint32_t *max_depth) try {
   if (!sg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (node_bytes) *node_bytes = sg->node_bytes;
   if (tri_bytes) *tri_bytes = sg->tri_bytes;
   if (total_bytes) *total_bytes = sg->total_bytes;
   if (max_depth) *max_depth = sg->max_depth;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_probe_new(lp_device *dev, const uint8_t *rgbe8, uint32_t width, uint32_t height,
-                              lp_probe **out) {
+                              lp_probe **out) try {
   if (!dev || !rgbe8 || !out || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
   CUDA_CHECK(cudaSetDevice(dev->ordinal));
   lp_probe *p = new (std::nothrow) lp_probe();
@@ -774,13 +774,13 @@ LP_API lp_status lp_probe_new(lp_device *dev, const uint8_t *rgbe8, uint32_t wid
   }
   *out = p;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_probe_destroy(lp_probe *probe) {
+LP_API lp_status lp_probe_destroy(lp_probe *probe) try {
   if (probe) cudaSetDevice(probe->dev->ordinal);
   delete probe;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 // ------------------------------------------------------------------ Renderer
 LP_API void lp_render_config_default(lp_render_config *cfg) {
@@ -799,7 +799,7 @@ LP_API void lp_render_config_default(lp_render_config *cfg) {
 }
 
 LP_API lp_status lp_renderer_new(lp_device *dev, uint32_t width, uint32_t height,
-                                 lp_renderer **out) {
+                                 lp_renderer **out) try {
   if (!dev || !out || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
   CUDA_CHECK(cudaSetDevice(dev->ordinal));
   lp_renderer *r = new (std::nothrow) lp_renderer();
@@ -827,9 +827,9 @@ LP_API lp_status lp_renderer_new(lp_device *dev, uint32_t width, uint32_t height
   }
   *out = r;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_destroy(lp_renderer *r) {
+LP_API lp_status lp_renderer_destroy(lp_renderer *r) try {
   if (!r) return LP_OK;
   cudaSetDevice(r->dev->ordinal);
   cudaStreamSynchronize(r->dev->stream);
@@ -842,19 +842,19 @@ LP_API lp_status lp_renderer_destroy(lp_renderer *r) {
   if (r->ev_connected) cudaEventDestroy(r->ev_connected);
   delete r;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_set_resources(lp_renderer *r, lp_scene_gpu *sg,
-                                           lp_probe *probe_or_null) {
+                                           lp_probe *probe_or_null) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   r->sg = sg;
   r->probe = probe_or_null;
   r->samples_accumulated = 0;  // frame_count = 1 [ref renderer.rs:724]
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_resize(lp_renderer *r, lp_scene_gpu *sg, lp_probe *probe_or_null,
-                                    uint32_t width, uint32_t height) {
+                                    uint32_t width, uint32_t height) try {
   if (!r || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
   CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
   CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
@@ -863,9 +863,9 @@ LP_API lp_status lp_renderer_resize(lp_renderer *r, lp_scene_gpu *sg, lp_probe *
   lp_status st = allocate_targets(r);
   if (st != LP_OK) return st;
   return lp_renderer_set_resources(r, sg, probe_or_null);
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_set_config(lp_renderer *r, const lp_render_config *cfg) {
+LP_API lp_status lp_renderer_set_config(lp_renderer *r, const lp_render_config *cfg) try {
   if (!r || !cfg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (cfg->max_bounces < 1 || cfg->max_bounces > kMaxBounces)
     return fail(LP_ERR_INVALID_ARG, "max_bounces must be in [1, 32]");
@@ -881,15 +881,15 @@ LP_API lp_status lp_renderer_set_config(lp_renderer *r, const lp_render_config *
     return allocate_targets(r);
   }
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_get_config(const lp_renderer *r, lp_render_config *cfg) {
+LP_API lp_status lp_renderer_get_config(const lp_renderer *r, lp_render_config *cfg) try {
   if (!r || !cfg) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   *cfg = r->cfg;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform[16]) {
+LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform[16]) try {
   if (!r || !view_transform) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   r->frame_back = !r->frame_back;  // [ref renderer.rs:401]
   if (!r->sg) return LP_OK;        // silently returns without resources [ref renderer.rs:403-422]
@@ -1080,32 +1080,32 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
   world_to_screen(r->camera, view_transform, 0.01f, 100.0f, r->prev_w2s);
   CUDA_CHECK(cudaGetLastError());
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_reset_accumulation(lp_renderer *r) {
+LP_API lp_status lp_renderer_reset_accumulation(lp_renderer *r) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   r->samples_accumulated = 0;  // frame_count = 1 [ref renderer.rs:610]
   r->accumulate = false;       // [ref renderer.rs:611]
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_set_blit_mode(lp_renderer *r, lp_blit_mode mode) {
+LP_API lp_status lp_renderer_set_blit_mode(lp_renderer *r, lp_blit_mode mode) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if ((int)mode < 0 || (int)mode > LP_BLIT_MOTION_VECTOR)
     return fail(LP_ERR_INVALID_ARG, "unknown blit mode");
   r->mode = mode;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_use_noise_texture(lp_renderer *r, int flag) {
+LP_API lp_status lp_renderer_use_noise_texture(lp_renderer *r, int flag) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   r->use_noise = flag != 0;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_upload_noise_texture(lp_renderer *r, const uint8_t *data,
                                                   uint32_t width, uint32_t height,
-                                                  uint32_t bytes_per_row) {
+                                                  uint32_t bytes_per_row) try {
   if (!r || !data || !width || !height || bytes_per_row < width * 4u)
     return fail(LP_ERR_INVALID_ARG, "bad argument");
   CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
@@ -1116,39 +1116,39 @@ LP_API lp_status lp_renderer_upload_noise_texture(lp_renderer *r, const uint8_t 
   r->noise_w = width;
   r->noise_h = height;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_get_size(const lp_renderer *r, uint32_t *width, uint32_t *height) {
+LP_API lp_status lp_renderer_get_size(const lp_renderer *r, uint32_t *width, uint32_t *height) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (width) *width = r->width;
   if (height) *height = r->height;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_set_accumulate(lp_renderer *r, int flag) {
+LP_API lp_status lp_renderer_set_accumulate(lp_renderer *r, int flag) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   r->accumulate = flag != 0;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_get_accumulate(const lp_renderer *r, int *flag) {
+LP_API lp_status lp_renderer_get_accumulate(const lp_renderer *r, int *flag) try {
   if (!r || !flag) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   *flag = r->accumulate ? 1 : 0;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_set_downsample_factor(lp_renderer *r, float factor) {
+LP_API lp_status lp_renderer_set_downsample_factor(lp_renderer *r, float factor) try {
   if (!r || !(factor > 0.0f) || factor > 4.0f) return fail(LP_ERR_INVALID_ARG, "bad factor");
   r->downsample = factor;  // takes effect at the next resize [ref renderer.rs:203,333]
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API uint32_t lp_renderer_max_ssbo_element_in_bytes(void) {
   // max(Ray = 2 x float4 + throughput/radiance 2 x float4, Intersection, Camera, PerDraw)
   return 64u;
 }
 
-LP_API lp_status lp_renderer_read_pixels(lp_renderer *r, uint8_t *out, size_t cap) {
+LP_API lp_status lp_renderer_read_pixels(lp_renderer *r, uint8_t *out, size_t cap) try {
   if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   const size_t n = (size_t)r->width * r->height;
   if (cap < n * 4) return fail(LP_ERR_READBACK, "output buffer too small");
@@ -1162,10 +1162,10 @@ LP_API lp_status lp_renderer_read_pixels(lp_renderer *r, uint8_t *out, size_t ca
   if (e == cudaSuccess) e = cudaStreamSynchronize(r->dev->stream);
   if (e != cudaSuccess) return fail(LP_ERR_READBACK, cudaGetErrorString(e));
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_queries(lp_renderer *r, const char *const **labels, const double **ms,
-                                     size_t *count) {
+                                     size_t *count) try {
   if (!r || !count) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
   CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
@@ -1180,9 +1180,9 @@ LP_API lp_status lp_renderer_queries(lp_renderer *r, const char *const **labels,
   if (ms) *ms = r->q_ms.data();
   *count = r->q_labels.size();
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_read_accum_f32(lp_renderer *r, float *out, size_t cap_floats) {
+LP_API lp_status lp_renderer_read_accum_f32(lp_renderer *r, float *out, size_t cap_floats) try {
   if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   const size_t n = (size_t)r->width * r->height;
   if (cap_floats < n * 4) return fail(LP_ERR_READBACK, "output buffer too small");
@@ -1193,12 +1193,12 @@ LP_API lp_status lp_renderer_read_accum_f32(lp_renderer *r, float *out, size_t c
                              r->dev->stream));
   CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 // Checkpoint / resume of a long accumulation ("resumable accumulators"): the
 // raw FP32 SUM target (alpha = sample count) and the number of samples in it.
 LP_API lp_status lp_renderer_read_accum_sum(lp_renderer *r, float *out, size_t cap_floats,
-                                            uint32_t *samples) {
+                                            uint32_t *samples) try {
   if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   const size_t n = (size_t)r->width * r->height;
   if (cap_floats < n * 4) return fail(LP_ERR_READBACK, "output buffer too small");
@@ -1208,10 +1208,10 @@ LP_API lp_status lp_renderer_read_accum_sum(lp_renderer *r, float *out, size_t c
   CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
   if (samples) *samples = r->samples_accumulated;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_write_accum_sum(lp_renderer *r, const float *in, size_t count_floats,
-                                             uint32_t samples) {
+                                             uint32_t samples) try {
   if (!r || !in) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   const size_t n = (size_t)r->width * r->height;
   if (count_floats != n * 4) return fail(LP_ERR_INVALID_ARG, "accumulator size mismatch");
@@ -1222,10 +1222,10 @@ LP_API lp_status lp_renderer_write_accum_sum(lp_renderer *r, const float *in, si
   r->samples_accumulated = samples;
   r->accumulate = samples > 0;  // the next raytrace adds to the restored sum
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_read_first_hit(lp_renderer *r, uint32_t *instance, uint32_t *primitive,
-                                            float *t, size_t cap_pixels) {
+                                            float *t, size_t cap_pixels) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   const size_t n = (size_t)r->width * r->height;
   if (cap_pixels < n) return fail(LP_ERR_READBACK, "output buffer too small");
@@ -1236,9 +1236,9 @@ LP_API lp_status lp_renderer_read_first_hit(lp_renderer *r, uint32_t *instance, 
   if (t) CUDA_CHECK(cudaMemcpyAsync(t, r->fh_t.ptr, n * 4, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_ray_counters(lp_renderer *r, lp_ray_counters *out, int reset) {
+LP_API lp_status lp_renderer_ray_counters(lp_renderer *r, lp_ray_counters *out, int reset) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
   cudaStream_t st = r->dev->stream;
@@ -1257,32 +1257,32 @@ LP_API lp_status lp_renderer_ray_counters(lp_renderer *r, lp_ray_counters *out, 
   }
   if (reset) CUDA_CHECK(cudaMemsetAsync(r->counters.ptr, 0, sizeof(Counters), st));
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_accum_device_ptr(lp_renderer *r, void **dev_ptr, size_t *count_floats,
-                                              uint32_t *samples) {
+                                              uint32_t *samples) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (dev_ptr) *dev_ptr = r->accum.ptr;
   if (count_floats) *count_floats = (size_t)r->width * r->height * 4;
   if (samples) *samples = r->samples_accumulated;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_set_sample_count(lp_renderer *r, uint32_t samples) {
+LP_API lp_status lp_renderer_set_sample_count(lp_renderer *r, uint32_t samples) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   r->samples_accumulated = samples;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_camera(const lp_renderer *r, lp_camera *out,
-                                    float prev_world_to_screen[16]) {
+                                    float prev_world_to_screen[16]) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (out) *out = r->camera;
   if (prev_world_to_screen) std::memcpy(prev_world_to_screen, r->prev_w2s, 64);
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_read_aux(lp_renderer *r, int which, void *out, size_t cap_bytes) {
+LP_API lp_status lp_renderer_read_aux(lp_renderer *r, int which, void *out, size_t cap_bytes) try {
   if (!r || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   const size_t n = (size_t)r->width * r->height;
   const int cur = r->svgf_back ? 1 : 0;
@@ -1307,18 +1307,18 @@ LP_API lp_status lp_renderer_read_aux(lp_renderer *r, int which, void *out, size
   CUDA_CHECK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, r->dev->stream));
   CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_renderer_set_kernel_timing(lp_renderer *r, int flag) {
+LP_API lp_status lp_renderer_set_kernel_timing(lp_renderer *r, int flag) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
   if (!flag) kt_drain(r);
   r->kt_enabled = flag != 0;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 LP_API lp_status lp_renderer_kernel_times(lp_renderer *r, double ms[4], uint64_t launches[4],
-                                          int reset) {
+                                          int reset) try {
   if (!r) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
   kt_drain(r);
@@ -1331,9 +1331,9 @@ LP_API lp_status lp_renderer_kernel_times(lp_renderer *r, double ms[4], uint64_t
     }
   }
   return LP_OK;
-}
+} LP_ABI_CATCH
 
-LP_API lp_status lp_device_fp32_peak(lp_device *dev, int repeats, double *tflops) {
+LP_API lp_status lp_device_fp32_peak(lp_device *dev, int repeats, double *tflops) try {
   if (!dev || !tflops) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   CUDA_CHECK(cudaSetDevice(dev->ordinal));
   const int blocks = dev->sm_count * 8, threads = 256, iters = 1 << 15;
@@ -1358,6 +1358,6 @@ LP_API lp_status lp_device_fp32_peak(lp_device *dev, int repeats, double *tflops
   CUDA_CHECK(cudaGetLastError());
   *tflops = best;
   return LP_OK;
-}
+} LP_ABI_CATCH
 
 }  // extern "C"

@@ -527,7 +527,7 @@ lp_status lp::lbvh_update_instances(lp_scene_gpu *sg, Scene &s) {
 }
 
 extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp_device *dev,
-                                                  lp_scene_gpu **out) {
+                                                  lp_scene_gpu **out) try {
   if (!scene || !dev || !out) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   Scene &s = scene_of(scene);
   if (s.primitives.size() >= (1u << 28))
@@ -640,4 +640,4 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
   if (ts != LP_OK) return bail(ts);
   *out = g;
   return LP_OK;
-}
+} LP_ABI_CATCH

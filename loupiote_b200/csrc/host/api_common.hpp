@@ -22,3 +22,15 @@ Scene &scene_of(lp_scene *s);
   } catch (const std::exception &e) {                        \
     return lp::fail(LP_ERR_INVALID_ARG, e.what());           \
   }
+
+// Function-try-block tail for the C ABI entry points of the CUDA translation units:
+//   LP_API lp_status f(...) try { ... } LP_ABI_CATCH
+// std::bad_alloc and friends from std::vector / std::string inside an entry point become status
+// codes like everywhere else.
+#define LP_ABI_CATCH                                         \
+  catch (const std::bad_alloc &) {                           \
+    return lp::fail(LP_ERR_OOM, "out of host memory");       \
+  }                                                          \
+  catch (const std::exception &e) {                          \
+    return lp::fail(LP_ERR_INVALID_ARG, e.what());           \
+  }

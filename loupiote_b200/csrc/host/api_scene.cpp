@@ -213,9 +213,8 @@ LP_API lp_status lp_probe_tables(const uint8_t *rgbe8, uint32_t width, uint32_t 
 
 LP_API lp_status lp_load_gltf(const uint8_t *data, size_t size, lp_scene *scene) {
   if (!scene) return fail(LP_ERR_INVALID_ARG, "scene is NULL");
-  std::string err;
-  const lp_status st = load_gltf(data, size, scene->s, err);
-  return st == LP_OK ? LP_OK : fail(st, err);
+  LP_TRY(std::string err; const lp_status st = load_gltf(data, size, scene->s, err);
+         return st == LP_OK ? LP_OK : fail(st, err);)
 }
 
 LP_API lp_status lp_load_gltf_path(const char *path, lp_scene *scene) {
@@ -223,15 +222,15 @@ LP_API lp_status lp_load_gltf_path(const char *path, lp_scene *scene) {
   // the reference unwrap()s the read [ref gltf.rs:159]; we report FileNotFound instead
   std::ifstream f(path, std::ios::binary);
   if (!f) return fail(LP_ERR_FILE_NOT_FOUND, path);
-  std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-  return lp_load_gltf(bytes.data(), bytes.size(), scene);
+  LP_TRY(std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)),
+                                    std::istreambuf_iterator<char>());
+         return lp_load_gltf(bytes.data(), bytes.size(), scene);)
 }
 
 LP_API lp_status lp_load_binary_from_path(const char *path, lp_scene *scene) {
   if (!scene || !path) return fail(LP_ERR_INVALID_ARG, "NULL argument");
-  std::string err;
-  const lp_status st = load_binary(path, scene->s, err);
-  return st == LP_OK ? LP_OK : fail(st, err);
+  LP_TRY(std::string err; const lp_status st = load_binary(path, scene->s, err);
+         return st == LP_OK ? LP_OK : fail(st, err);)
 }
 
 }  // extern "C"

@@ -591,14 +591,29 @@ lp_status load_binary(const char *path, Scene &scene, std::string &err) {
     return LP_ERR_FILE_NOT_FOUND;
   }
   const size_t vcount = (size_t)tri_count * 3;
-  std::vector<float> raw(vcount * 4);
+  // the count comes from the file: compare it with what the file holds BEFORE allocating
+  const std::streampos here = f.tellg();
+  f.seekg(0, std::ios::end);
+  const std::streampos end = f.tellg();
+  f.seekg(here);
+  if (!f || end < here || (uint64_t)(end - here) < (uint64_t)vcount * 16u) {
+    err = std::string(path) + ": truncated";
+    return LP_ERR_FILE_NOT_FOUND;
+  }
+  std::vector<float> raw, nrm;
+  try {
+    raw.resize(vcount * 4);
+    nrm.resize(vcount * 3);
+  } catch (const std::exception &e) {
+    err = e.what();
+    return LP_ERR_ACCEL_BUILD;
+  }
   f.read((char *)raw.data(), (std::streamsize)(raw.size() * 4));
   if (!f) {
     err = std::string(path) + ": truncated";
     return LP_ERR_FILE_NOT_FOUND;
   }
   // flat normals: cross(normalize(v0-v1), normalize(v0-v2)) [ref binary.rs:33-47]
-  std::vector<float> nrm(vcount * 3);
   for (size_t i = 0; i < vcount; i += 3) {
     const float *a = &raw[4 * i], *b = &raw[4 * (i + 1)], *c = &raw[4 * (i + 2)];
     float e0[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};

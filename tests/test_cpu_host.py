@@ -503,3 +503,21 @@ def test_gltf_accessor_arithmetic_is_overflow_safe():
         m = np.eye(4, dtype=np.float32)
         m[0, 3] = np.nan
         sc.blas.add_instance(b, m, 0)
+
+
+def test_binary_loader_checks_the_count_against_the_file(tmp_path):
+    """load_binary_from_path [ref binary.rs:6-31] reads a u32 triangle count and then that
+    many triangles: a count larger than the file can hold is a truncated file (an error
+    status), not a multi-gigabyte allocation that aborts the process across the C ABI."""
+    for count in (0xFFFFFFFF, 0x10000000, 3):
+        f = tmp_path / f"hostile_{count}.bin"
+        f.write_bytes(struct.pack("<I", count) + b"\0" * 100)
+        with pytest.raises(lb.Error) as e:
+            lb.loaders.load_binary_from_path(f, lb.Scene())
+        assert e.value.code == lb.Error.FileNotFound and "truncated" in str(e.value)
+    ok = tmp_path / "two.bin"
+    tri = np.array([[0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1]] * 2, np.float32)
+    ok.write_bytes(struct.pack("<I", 2) + tri.tobytes())
+    s = lb.Scene()
+    lb.loaders.load_binary_from_path(ok, s)
+    assert s.array(_ffi.SCENE_ENTRIES)["primitive_count"][-1] == 2
