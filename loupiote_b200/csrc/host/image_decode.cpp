@@ -235,7 +235,9 @@ bool decode_png(const uint8_t *d, size_t n, Image &out) {
     }
     off += 12 + (size_t)len;
   }
-  if (!have_ihdr || !w || !h || w > 32768 || h > 32768) throw std::runtime_error("png: bad size");
+  // 16384 = the atlas layer limit (textures.cpp): a larger image could never be used, and the
+  // header alone must not be able to ask for gigabytes
+  if (!have_ihdr || !w || !h || w > 16384 || h > 16384) throw std::runtime_error("png: bad size");
   int channels;
   switch (ctype) {
     case 0: channels = 1; break;
@@ -486,7 +488,7 @@ bool decode_jpeg(const uint8_t *d, size_t n, Image &out) {
       const int nc = s[5];
       if ((nc != 1 && nc != 3) || sl < 6 + 3 * (size_t)nc)
         throw std::runtime_error("jpeg: unsupported component count");
-      if (!W || !H) throw std::runtime_error("jpeg: bad size");
+      if (!W || !H || W > 16384 || H > 16384) throw std::runtime_error("jpeg: bad size");
       comps.resize(nc);
       for (int c = 0; c < nc; ++c) {
         comps[c].id = s[6 + 3 * c];
