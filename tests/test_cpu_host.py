@@ -409,7 +409,7 @@ def test_ingest_survives_mutated_inputs():
     down; the --asan mode of the tool rebuilds the host sources with ASan + UBSan)."""
     import subprocess
     import sys
-    for extra in ([], ["--structured"]):
+    for extra in ([], ["--structured"], ["--api"]):
         out = subprocess.run([sys.executable, str(ROOT / "tools" / "fuzz_ingest.py"), "--n", "500",
                               "--seed", "3", *extra], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]

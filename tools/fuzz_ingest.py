@@ -151,6 +151,72 @@ def run_structured(lib: C.CDLL, n: int, seed: int) -> dict:
     return counts
 
 
+def run_api(lib: C.CDLL, n: int, seed: int) -> dict:
+    """The scene-building entry points with extreme but well-typed arguments: vertex positions
+    and instance matrices drawn from {0, -0, denormals, +-1e19, +-3e38, NaN, inf, ...}, empty
+    and out-of-range index lists; every accepted scene then goes through the TLAS build and
+    the GPU re-layouts (lp_scene_get_array of the derived arrays)."""
+    void_p, size_t, u32p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)
+    lib.lp_scene_add_bvh.argtypes = [void_p, void_p, size_t, void_p, size_t, void_p, size_t, size_t, u32p]
+    lib.lp_scene_add_bvh_indexed.argtypes = [void_p, void_p, size_t, void_p, size_t, void_p, size_t,
+                                             size_t, void_p, size_t, u32p]
+    lib.lp_scene_add_instance.argtypes = [void_p, C.c_uint32, void_p, C.c_uint32]
+    lib.lp_scene_get_array.argtypes = [void_p, C.c_int, C.POINTER(void_p), C.POINTER(size_t),
+                                       C.POINTER(size_t)]
+    rng = np.random.default_rng(seed)
+    vals = np.array([0, -0.0, 1e-45, -1e-38, 1, -1, 1e19, -1e19, 3e38, -3e38, 65504, 1e-3, 7.5],
+                    np.float32)
+    counts = {"ok": 0, "rejected": 0}
+    for _ in range(n):
+        h = void_p()
+        assert lib.lp_scene_create(C.byref(h)) == 0
+        for _b in range(int(rng.integers(1, 4))):
+            nv = int(rng.integers(0, 40)) * 3
+            mode = int(rng.integers(0, 4))
+            if mode == 0:
+                pos = rng.normal(size=(nv, 3)).astype(np.float32)
+            elif mode == 1:
+                pos = rng.choice(vals, size=(nv, 3)).astype(np.float32)
+            elif mode == 2:
+                with np.errstate(over="ignore"):
+                    pos = (rng.normal(size=(nv, 3)) * 10.0 ** int(rng.integers(-30, 38))).astype(np.float32)
+            else:
+                pos = rng.normal(size=(nv, 3)).astype(np.float32)
+                if nv:
+                    pos[rng.integers(0, nv), rng.integers(0, 3)] = rng.choice([np.nan, np.inf, -np.inf])
+            idx = C.c_uint32()
+            if rng.random() < 0.5 and nv:
+                hi = nv + (2 if rng.random() < 0.2 else 0)
+                ind = rng.integers(0, hi, size=int(rng.integers(0, 30)) * 3).astype(np.uint32)
+                st = lib.lp_scene_add_bvh_indexed(h, pos.ctypes.data, 12, None, 0, None, 0, nv,
+                                                  ind.ctypes.data, len(ind), C.byref(idx))
+            else:
+                st = lib.lp_scene_add_bvh(h, pos.ctypes.data if nv else None, 12, None, 0, None, 0,
+                                          nv, C.byref(idx))
+            if st != 0:
+                continue
+            for _k in range(int(rng.integers(0, 4))):
+                m = np.eye(4, dtype=np.float32)
+                mm = int(rng.integers(0, 4))
+                if mm == 0:
+                    m[:3, :3] = rng.normal(size=(3, 3))
+                elif mm == 1:
+                    m = rng.choice(vals, size=(4, 4)).astype(np.float32)
+                elif mm == 2:
+                    m[:3, :3] *= np.float32(10.0 ** int(rng.integers(-30, 30)))
+                else:
+                    m[rng.integers(0, 4), rng.integers(0, 4)] = rng.choice([np.nan, np.inf])
+                m = np.ascontiguousarray(m)
+                lib.lp_scene_add_instance(h, idx.value, m.ctypes.data, 0)
+        ptr, cnt, es = void_p(), size_t(), size_t()
+        st = 0
+        for which in (12, 15, 10, 9, 11):
+            st |= lib.lp_scene_get_array(h, which, C.byref(ptr), C.byref(cnt), C.byref(es))
+        counts["ok" if st == 0 else "rejected"] += 1
+        lib.lp_scene_destroy(h)
+    return counts
+
+
 def run(lib: C.CDLL, n: int, seed: int) -> dict:
     z = np.load(ROOT / "tests" / "golden" / "image_fixtures.npz")
     images = [bytes(z[k].tobytes()) for k in sorted(z.keys()) if k.startswith("file_")]
@@ -182,6 +248,8 @@ def main() -> None:
     ap.add_argument("--n", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--asan", action="store_true")
+    ap.add_argument("--api", action="store_true",
+                    help="scene-building entry points with extreme float arguments")
     ap.add_argument("--structured", action="store_true",
                     help="structure-aware mutations of the glTF JSON instead of byte mutations")
     args = ap.parse_args()
@@ -204,9 +272,10 @@ def main() -> None:
         sys.path.insert(0, str(ROOT))
         from loupiote_b200 import _ffi
         lib = _ffi.lib()
-    counts = (run_structured if args.structured else run)(lib, args.n, args.seed)
+    counts = (run_api if args.api else run_structured if args.structured else run)(
+        lib, args.n, args.seed)
     print({"n": args.n, "seed": args.seed, "sanitized": bool(args.asan),
-           "structured": bool(args.structured), **counts})
+           "structured": bool(args.structured), "api": bool(args.api), **counts})
 
 
 if __name__ == "__main__":
