@@ -4,18 +4,22 @@ Mrays/s, primary+bounce+shadow rays actually traced, 1080p).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one Renderer::raytrace call tracing --spp-per-step samples per pixel of the
-workload (default: the procedural 1,003,522-triangle scene of BASELINE config 3 at
-1920x1080, 8 bounces) followed by the accumulation-buffer reduce across ranks.  Multi-GPU =
-one process per GPU (torchrun), scene replicated, sample indices interleaved across ranks
-(rank, rank+N, ...), FP32 sum accumulators reduced to rank 0 with NCCL (weak scaling: every
-rank traces spp-per-step samples per step).
+One "step" = one batch of the workload (default: the procedural 1,003,522-triangle scene of
+BASELINE config 3 at 1920x1080, 8 bounces): every GPU traces --spp-per-step samples per pixel
+(weak scaling, the headline) and the FP32 SUM accumulators are summed to rank 0, where the
+frame is tone-mapped.  Everything goes through the C ABI of libloupiote_b200 (lp_multi_*:
+replicated scene, interleaved sample split, NCCL reduce inside the library); torch is the
+launcher's plumbing (rendezvous, barrier, max-over-ranks of the timings).
 
 Prints ONE JSON line on rank 0 (contract in the task brief): value = device-timed Mrays/s
 with everything resident in HBM; e2e = same metric through the public API including the
-per-step host->device uniform upload and the device->host read_pixels; roofline for the
-dominant kernel (extend = closest-hit traversal) against the fetch roofline of SURVEY 8(d);
-cpu_baseline = the CPU restatement (oracle) timed on a bounded sample of the same workload.
+per-step host->device uniform upload and the device->host read of the frame; roofline for the
+dominant kernels (closest-hit traversal) against the fetch roofline of SURVEY 8(d);
+cpu_baseline = the CPU restatement (oracle) timed on a bounded sample of the same workload,
+and parity_check = the GPU image of exactly that sample set against the oracle's.  Extra
+blocks: strong scaling (a FIXED --spp-per-step split over the ranks), multi_check (the reduced
+N-GPU image against one GPU tracing the same sample set), config5 (1 spp + SVGF frame
+latency, N = 1), config4 (10M-triangle lattice at 4K, N = 8).
 """
 from __future__ import annotations
 
@@ -43,6 +47,9 @@ WORKLOADS = {
     "spheres-small-540p-4b": ("spheres_1m", {"grid": 3, "subdivisions": 3}, 960, 540, 4),
 }
 V_FOV = 0.78539816339
+METRIC = "path-tracing throughput (primary+bounce+shadow rays)"
+# radiance bar of the same-sample comparison
+PARITY_REL, PARITY_ABS, PARITY_MAX_BAD, PARITY_MAX_MEAN = 1e-3, 1e-5, 2e-3, 1e-3
 
 
 def algorithmic_bytes_flops(c: dict) -> dict:
@@ -58,15 +65,16 @@ def algorithmic_bytes_flops(c: dict) -> dict:
     return out
 
 
-def ncu_traffic(workload: str, spp_per_step: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the extend kernels, from the
-    committed ncu --set full capture of this workload (profiles/ncu_traffic.json); None when
-    no capture matches what is being run."""
+def committed_capture(workload: str, spp_per_step: int):
+    """Numbers that only a profiler gives, from the COMMITTED ncu --set full capture of this
+    workload (profiles/ncu_traffic.json; never measured in this run): DRAM bytes per launch of
+    the closest-hit kernels and the physical per-ray counters (instructions, L2 bytes, issue
+    utilisation).  None when no capture matches what is being run."""
     p = ROOT / "profiles" / "ncu_traffic.json"
     try:
         t = json.loads(p.read_text())
         if t["workload"] == workload and t["spp_per_step"] == spp_per_step:
-            return t["extend"]["dram_bytes_per_launch"]
+            return t
     except (OSError, KeyError, ValueError):
         pass
     return None
@@ -141,8 +149,19 @@ def build_workload(name: str):
     return c, w, h, bounces
 
 
+def workload_config(args, c, w, h, bounces) -> dict:
+    """The `config` object: identical in both arms (ours / reference) of the same command."""
+    return {"workload": args.workload, "width": w, "height": h, "bounces": bounces,
+            "spp_per_step": args.spp_per_step,
+            "triangles": int(len(c["scene"].blas.primitives) - 1),
+            "parallelism": f"spp-split x{args.gpus}, scene replicated, sum-reduce to rank 0",
+            "l2": "path state per step exceeds L2 (no flush needed); the BVH is L2-resident "
+                  "by design"}
+
+
 def cpu_reference_sample(c, w, h, bounces, spp, pixel_step, sample_offset=0):
-    """Times the CPU restatement (oracle) on a bounded sample of the workload."""
+    """Times the CPU restatement (oracle) on a bounded sample of the workload; returns
+    (rays, seconds, stats, SUM accumulator (h, w, 4): alpha 0 on the pixels not sampled)."""
     from loupiote_b200 import _ffi
     from oracle import oracle as O
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all host threads
@@ -155,10 +174,29 @@ def cpu_reference_sample(c, w, h, bounces, spp, pixel_step, sample_offset=0):
     cfg.env_color = (_ffi.C.c_float * 3)(*c["env_color"])
     cfg.sample_offset = sample_offset
     t0 = time.perf_counter()
-    _, st = O.render(osc, cam, cfg, spp, pixel_step=pixel_step)
+    acc, st = O.render(osc, cam, cfg, spp, pixel_step=pixel_step)
     dt = time.perf_counter() - t0
     rays = st["primary"] + st["bounce"] + st["shadow"]
-    return rays, dt, st
+    return rays, dt, st, acc
+
+
+def parity_check(gpu_sum: np.ndarray, cpu_sum: np.ndarray) -> dict:
+    """Same sample set on both sides: per pixel |gpu - cpu| <= 1e-3 max(cpu) + 1e-5 on >= 99.8 %
+    of the sampled pixels and the image mean within 0.1 % (the bar of tests/test_gpu_parity.py)."""
+    mask = cpu_sum[..., 3] > 0
+    n = int(mask.sum())
+    same_alpha = bool(np.array_equal(gpu_sum[..., 3][mask], cpu_sum[..., 3][mask]))
+    cpu = cpu_sum[mask][:, :3] / cpu_sum[mask][:, 3:4]
+    gpu = gpu_sum[mask][:, :3] / np.maximum(gpu_sum[mask][:, 3:4], 1.0)
+    err = np.abs(gpu - cpu).max(axis=-1)
+    tol = PARITY_REL * np.maximum(cpu.max(axis=-1), 1e-3) + PARITY_ABS
+    bad = float((err > tol).mean())
+    mean_rel = abs(float(gpu.mean()) - float(cpu.mean())) / float(cpu.mean())
+    return {"pixels": n, "samples_per_pixel": float(cpu_sum[..., 3].max()),
+            "same_sample_count": same_alpha, "mean_rel": mean_rel, "frac_outside_tol": bad,
+            "tol": f"|gpu-cpu| <= {PARITY_REL} max(cpu) + {PARITY_ABS} per pixel; "
+                   f"frac <= {PARITY_MAX_BAD}; mean_rel <= {PARITY_MAX_MEAN}",
+            "pass": bool(same_alpha and bad <= PARITY_MAX_BAD and mean_rel <= PARITY_MAX_MEAN)}
 
 
 def run_reference(args) -> None:
@@ -171,7 +209,7 @@ def run_reference(args) -> None:
     c, w, h, bounces = build_workload(args.workload)
     cores = os.cpu_count() or 1
     # calibrate the pixel subsample so one step is ~5 s of CPU work
-    rays, dt, _ = cpu_reference_sample(c, w, h, bounces, 1, 64)
+    rays, dt, _, _ = cpu_reference_sample(c, w, h, bounces, 1, 64)
     frame_s = dt * 64  # estimated CPU time of one full 1-spp frame
     # bounded sample: the whole run (warm-up + K steps) stays near two minutes of CPU time
     target = min(10.0, 120.0 / max(args.steps + min(args.warmup, 1), 1))
@@ -181,24 +219,60 @@ def run_reference(args) -> None:
         cpu_reference_sample(c, w, h, bounces, spp, pixel_step)
     total_rays, total_t = 0, 0.0
     for k in range(args.steps):
-        rays, dt, _ = cpu_reference_sample(c, w, h, bounces, spp, pixel_step,
-                                           sample_offset=k * spp)
+        rays, dt, _, _ = cpu_reference_sample(c, w, h, bounces, spp, pixel_step,
+                                              sample_offset=k * spp)
         total_rays += rays
         total_t += dt
     value = total_rays / total_t / 1e6
     sample = f"{spp} spp of every {pixel_step}th pixel of {args.workload} per step"
-    line = {"impl": "reference", "metric": "path-tracing throughput (primary+bounce+shadow rays)",
+    line = {"impl": "reference", "metric": METRIC,
             "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "width": w, "height": h, "bounces": bounces,
-                       "note": "CPU restatement (not wgpu/lavapipe)"},
+            "config": workload_config(args, c, w, h, bounces),
+            "note": "CPU restatement of the path (oracle/lp_oracle.c) on the host cores, not "
+                    "wgpu/lavapipe: the reference cannot be built in this image",
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+def config5_frames(dev, c, w, h, frames=200, warm=20) -> dict:
+    """BASELINE config 5: 1 spp per frame + SVGF (temporal + 5 a-trous + composite), camera
+    orbiting 0.5 degrees per frame; frame latency = raytrace call to completion on the host
+    clock, denoise = the device-timed "asvgf" span."""
+    import loupiote_b200 as lb
+    from loupiote_b200 import scenes
+    sg = lb.SceneGPU.new_from_scene(c["scene"], dev)
+    r = lb.Renderer(dev, (w, h), downsample_factor=1.0)
+    r.set_resources(sg, None)
+    r.set_config(max_bounces=4, spp_per_call=1, jitter=1, seed=0, env_color=c["env_color"],
+                 atrous_iterations=5)
+    r.set_blit_mode(lb.BlitMode.DenoisedPathrace)
+    lat, denoise = [], []
+    for k in range(frames + warm):
+        view = scenes.orbit_view(c["view"], 0.5 * k)
+        t0 = time.perf_counter()
+        r.raytrace(view)
+        dev.synchronize()
+        lat.append(1e3 * (time.perf_counter() - t0))
+        denoise.append(r.queries.get("asvgf", 0.0))
+    lat, denoise = np.array(lat[warm:]), np.array(denoise[warm:])
+    hist = r.read_aux("history")
+    bound_ms = 400.0 * w * h / (measured_peaks()["hbm_gbs"] * 1e9) * 1e3
+    out = {"workload": "interactive 1080p, 1 spp/frame, 4 bounces + SVGF (temporal + 5 a-trous + "
+                       "composite), camera orbiting 0.5 deg/frame",
+           "frames": int(len(lat)), "frame_ms_median": float(np.median(lat)),
+           "frame_ms_p99": float(np.percentile(lat, 99)),
+           "denoise_ms_median": float(np.median(denoise)), "denoise_hbm_bound_ms": bound_ms,
+           "denoise_fraction_of_bound": bound_ms / float(np.median(denoise)),
+           "median_history_length": float(np.median(hist))}
+    r.close()
+    sg.close()
+    return out
 
 
 def run_ours(args) -> None:
@@ -217,74 +291,83 @@ def run_ours(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # ---- the product: one lp_multi rank per process; the NCCL id travels through the launcher
+    uid = [lb.MultiRenderer.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    m = lb.MultiRenderer.create_rank(local_rank, uid[0], world, rank)
+    m.set_reduce_mode(lb.ReduceMode.NCCL)
     c, w, h, bounces = build_workload(args.workload)
-    dev = lb.Device(local_rank)
-    sg = lb.SceneGPU.new_from_scene(c["scene"], dev)
-    r = lb.Renderer(dev, (w, h), downsample_factor=1.0)
-    r.set_resources(sg, None)
-    from loupiote_b200 import multi
-    base_cfg = dict(max_bounces=bounces, spp_per_call=args.spp_per_step, jitter=1, seed=0,
-                    env_color=c["env_color"], traversal_variant=args.variant,
-                    **multi.sample_partition(rank, world))
+    m.set_scene(c["scene"])
+    m.resize((w, h))
+    dev, r = m.device(0), m.renderer(0)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
-
-    # the accumulator as a torch tensor (zero copy) for the NCCL reduce; looked up again
-    # whenever the renderer may have re-allocated its targets (set_config / resize)
-    accum_ref = {"ptr": None, "t": None}
-
-    def accum_tensor():
-        ptr = r.accum_device_ptr()[0]
-        if ptr != accum_ref["ptr"]:
-            accum_ref["ptr"], accum_ref["t"] = ptr, multi.accum_tensor(r, local_rank)
-        return accum_ref["t"]
+    view = c["view"]
+    spp = args.spp_per_step
+    common = dict(max_bounces=bounces, jitter=1, seed=0, env_color=c["env_color"],
+                  traversal_variant=args.variant, sample_offset=0, sample_stride=1)
+    weak_total = world * spp  # every GPU traces spp samples per step
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def reduce_accum():
-        if world > 1:
-            with torch.cuda.stream(stream):
-                multi.reduce_sum_(accum_tensor(), dst=0)
+    def timed_steps(n_steps: int) -> float:
+        """n_steps x (render + reduce), device-timed on the tracing stream; the reduce of step k
+        overlaps the tracing of step k+1 (only its accumulation waits), the final join puts the
+        last reduce in front of the closing event."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(n_steps):
+                m.render(view)
+                m.reduce()
+            m.join()
+            e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def max_over_ranks(*vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def total_rays(reset=True) -> float:
+        cc = m.ray_counters(reset=reset)  # summed over the ranks by the last reduce (rank 0)
+        return float(cc["primary"] + cc["bounce"] + cc["shadow"])
 
     # ---- canonical traversal statistics (untimed, one step, count_stats on): gives the
-    # algorithmic bytes per ray that the roofline is defined on
-    r.set_config(**base_cfg, count_stats=1)
+    # algorithmic bytes per ray that the roofline is defined on (SURVEY 8(d)); this rank's share
+    m.set_config(**common, spp_per_call=weak_total, count_stats=1)
     r.ray_counters(reset=True)
-    r.raytrace(c["view"])
+    m.render(view)
+    m.synchronize()
     stats = algorithmic_bytes_flops(r.ray_counters(reset=True))
-    r.set_config(**base_cfg, count_stats=0)
-    # every step is an independent batch: `accumulate` stays off, so each raytrace call
-    # overwrites the SUM accumulator with its own spp_per_step samples and the reduce that
-    # follows sums exactly one batch per rank (one reduce per batch)
-    r.reset_accumulation()
+    m.set_config(**common, spp_per_call=weak_total, count_stats=0)
+    # every step is an independent batch: `accumulate` stays off, so each render overwrites the
+    # SUM accumulator with its own samples and the reduce that follows sums exactly one batch
+    # per rank (one reduce per batch, SURVEY 8(e))
 
     # ---- warm-up
     for _ in range(max(args.warmup, 0)):
-        r.raytrace(c["view"])
-        reduce_accum()
+        m.render(view)
+        m.reduce()
+    m.synchronize()
     barrier()
-    r.ray_counters(reset=True)
+    m.ray_counters(reset=True)
     r.kernel_times(reset=True)
 
     # ---- timed region: K steps, CUDA events on the stream the kernels are launched on
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(args.steps):
-            r.raytrace(c["view"])
-            reduce_accum()
-        e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed_steps(args.steps)
     launches = sum(v[1] for v in r.kernel_times(reset=True).values())
-    counters = r.ray_counters(reset=True)
-    rays = counters["primary"] + counters["bounce"] + counters["shadow"]
+    rays = total_rays()
 
     # ---- per-kernel durations: the same K steps again with an event pair around every launch.
     # Per-launch timing serialises the frame (the production frame overlaps the shadow-ray
@@ -292,111 +375,235 @@ def run_ours(args) -> None:
     # bracketed duration would be the duration of the pair), so this pass is a little slower
     # than the timed region; `kernel_ms` and `roofline` come from it, `value` does not.
     r.set_kernel_timing(True)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        k0.record(stream)
-        for _ in range(args.steps):
-            r.raytrace(c["view"])
-            reduce_accum()
-        k1.record(stream)
-    barrier()
+    serial_ms = timed_steps(args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    serial_ms = k0.elapsed_time(k1)
     kt = r.kernel_times(reset=True)
     r.set_kernel_timing(False)
-    r.ray_counters(reset=True)
+    m.ray_counters(reset=True)
 
     # ---- e2e: same steps through the public API with HOST buffers: per step the view
-    # matrix + uniforms go host->device and the tone-mapped frame comes back (read_pixels)
+    # matrix + uniforms go host->device and the tone-mapped frame of the batch comes back
+    # (rank 0 reads the reduced frame, which makes every exchange step of this pass timed)
+    m.reduce_time(reset=True)
     barrier()
     t0 = time.perf_counter()
-    e2e_rays = 0
+    img = None
     for _ in range(args.steps):
-        r.raytrace(c["view"])
-        reduce_accum()
-        img = r.read_pixels()
+        m.render(view)
+        m.reduce()
+        if rank == 0:
+            img = m.read_pixels()
+        else:
+            m.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
-    cc = r.ray_counters(reset=True)
-    e2e_rays = cc["primary"] + cc["bounce"] + cc["shadow"]
+    e2e_rays = total_rays()
+    reduce_ms_total, reduce_n = m.reduce_time(reset=True)
+    ms, e2e_s, serial_ms = max_over_ranks(ms, e2e_s, serial_ms)
 
-    # ---- aggregate over ranks: max time, sum of rays
+    # ---- strong scaling: the SAME total work per step (spp samples per pixel) split over the
+    # ranks; at N = 1 it is the headline itself
+    strong = None
     if world > 1:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        n = torch.tensor([rays, e2e_rays], dtype=torch.float64, device="cuda")
-        dist.all_reduce(n, op=dist.ReduceOp.SUM)
-        ms, e2e_s = t.tolist()
-        rays, e2e_rays = n.tolist()
+        m.set_config(**common, spp_per_call=spp, count_stats=0)
+        k_strong = max(3, min(args.steps, 10))
+        timed_steps(2)
+        m.ray_counters(reset=True)
+        s_ms = timed_steps(k_strong)
+        s_rays = total_rays()
+        m.reduce_time(reset=True)
+        for _ in range(3):
+            m.render(view)
+            m.reduce()
+            m.synchronize()
+        s_red, s_n = m.reduce_time(reset=True)
+        (s_ms,) = max_over_ranks(s_ms)
+        strong = {"spp_total_per_step": spp, "spp_per_gpu": spp / world, "steps": k_strong,
+                  "ms_per_step": s_ms / k_strong, "mrays_s": s_rays / (s_ms * 1e-3) / 1e6,
+                  "nccl_ms": s_red / max(s_n, 1) if rank == 0 else None}
 
+    # ---- the reduced N-GPU image against ONE GPU tracing the same sample set
+    multi_check = None
+    if world > 1:
+        m.set_config(**common, spp_per_call=weak_total, count_stats=0)
+        m.render(view)
+        m.reduce()
+        m.synchronize()
+        if rank == 0:
+            acc_n = m.read_accum_sum()
+        barrier()
+        if rank == 0:
+            r.set_config(**common, spp_per_call=weak_total, count_stats=0)
+            r.reset_accumulation()
+            r.raytrace(view)
+            acc_1, _ = r.read_accum_sum()
+            alpha_ok = bool(np.all(acc_n[..., 3] == float(weak_total)))
+            rel = np.abs(acc_n - acc_1) / (np.abs(acc_1) + 1e-3 * weak_total)
+            multi_check = {"samples_per_pixel": weak_total, "alpha_is_n_times_spp": alpha_ok,
+                           "max_rel_diff_vs_one_gpu": float(rel.max()),
+                           "mean_rel_diff": abs(float(acc_n.mean()) - float(acc_1.mean()))
+                           / float(acc_1.mean()),
+                           "tol": "rtol 1e-5 (FP32 summation order)",
+                           "pass": bool(alpha_ok and float(rel.max()) <= 1e-5)}
+        barrier()
+
+    line = None
     if rank == 0:
         peaks = measured_peaks()
         fp32 = dev.fp32_peak_tflops()
-        # dominant kernel: extend (closest hit).  Algorithmic bytes of its launches in the
-        # timed region = (primary + bounce ray bytes per step from the stats pass) x steps.
+        # dominant kernels: closest hit.  Algorithmic bytes of their launches in the timed
+        # region = (primary + bounce ray bytes per step from the stats pass) x steps.
         ext_ms, ext_launches = kt["extend"]
         ext_bytes = (stats["bytes"][0] + stats["bytes"][1]) * args.steps
         ext_flops = (stats["flops"][0] + stats["flops"][1]) * args.steps
         achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         total_bytes = sum(stats["bytes"])
         total_flops = sum(stats["flops"])
-        total_rays = sum(stats["rays"])
-        roof_mrays = min(peaks["hbm_gbs"] * 1e9 / (total_bytes / total_rays),
-                         fp32 * 1e12 / (total_flops / total_rays)) / 1e6
+        n_rays = sum(stats["rays"])
+        roof_mrays = min(peaks["hbm_gbs"] * 1e9 / (total_bytes / n_rays),
+                         fp32 * 1e12 / (total_flops / n_rays)) / 1e6
         value = rays / (ms * 1e-3) / 1e6
+        cap = committed_capture(args.workload, spp)
+        kernel_names = ("extend4_kernel<fp16 boxes, fused ray generation> (primary rays) + "
+                        "trace_pool_kernel<closest hit> (bounce rays)"
+                        if args.variant in (0, 14) else f"traversal variant {args.variant}")
         line = {
-            "metric": "path-tracing throughput (primary+bounce+shadow rays)",
+            "metric": METRIC,
             "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": w, "height": h, "bounces": bounces,
-                       "spp_per_step": args.spp_per_step,
-                       "triangles": int(len(c["scene"].blas.primitives) - 1),
-                       "parallelism": f"spp-split x{world}, scene replicated, NCCL sum-reduce",
-                       "l2": "path state per step exceeds L2 (no flush needed); the BVH is "
-                             "L2-resident by design",
-                       "scene_bytes": sg.stats()["total_bytes"]},
-            "spp_per_s": world * args.spp_per_step * args.steps / (ms * 1e-3),
+            "config": workload_config(args, c, w, h, bounces),
+            "api": "lp_multi_* (C ABI): lp_multi_create_rank + lp_multi_render + lp_multi_reduce "
+                   "(ncclReduce inside libloupiote_b200.so)",
+            "scene_bytes": 0,
+            "spp_per_s": world * spp * args.steps / (ms * 1e-3),
             "rays_per_step": rays / args.steps,
             "roofline_fraction_of_path": value / (world * roof_mrays),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": ncu_traffic(args.workload, args.spp_per_step),
+                         "traffic": cap["extend"]["dram_bytes_per_launch"] if cap else None,
+                         "traffic_source": (f"committed ncu capture {cap.get('source', '')} "
+                                            "(profiles/ncu_traffic.json), not measured in this "
+                                            "run") if cap else None,
                          "algorithmic_bytes_per_launch": achieved * 1e9 * ext_ms * 1e-3
                          / max(ext_launches, 1),
-                         "kernel": "extend_kernel", "launch_ms": ext_ms / max(ext_launches, 1),
+                         "kernel": kernel_names, "launch_ms": ext_ms / max(ext_launches, 1),
                          "launches": ext_launches, "peak_source": peaks["source"],
                          "fp32_peak_tflops": fp32,
                          "fp32_achieved_tflops": ext_flops / (ext_ms * 1e-3) / 1e12 if ext_ms else 0,
                          "mean_bytes_per_ray": [stats["bytes"][k] / max(stats["rays"][k], 1)
                                                 for k in range(3)],
-                         "path_roofline_mrays": roof_mrays},
+                         "path_roofline_mrays": roof_mrays,
+                         "physical": cap.get("physical") if cap else None},
             "kernel_ms": {k: v[0] for k, v in kt.items()},
             "kernel_timing_pass": {"ms_per_step": serial_ms / args.steps,
                                    "note": "separate pass of the same K steps, one stream, an "
                                            "event pair around every launch"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "nccl_ms": reduce_ms_total / max(reduce_n, 1),
+            "nccl_ms_note": "device time of one exchange step on rank 0's communication stream "
+                            "(inputs ready -> reduced sRGB8 frame), mean over the e2e pass",
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",
                     "h2d_bytes_per_step": 64 + 256, "d2h_bytes_per_step": int(img.nbytes),
                     "ms_per_step": 1e3 * e2e_s / args.steps},
+            "strong": strong if strong else {
+                "spp_total_per_step": spp, "spp_per_gpu": spp, "steps": args.steps,
+                "ms_per_step": ms / args.steps, "mrays_s": value,
+                "nccl_ms": reduce_ms_total / max(reduce_n, 1)},
+            "multi_check": multi_check,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            crays, cdt, _ = cpu_reference_sample(c, w, h, bounces, 1, 64)
-            frame_s = cdt * 64  # estimated CPU time of one full 1-spp frame
-            target = 15.0       # seconds of CPU work for the baseline sample
-            step = min(max(int(frame_s / target), 1), 64)
-            cspp = max(1, int(target / frame_s)) if step == 1 else 1
-            crays, cdt, _ = cpu_reference_sample(c, w, h, bounces, cspp, step)
-            line["cpu_baseline"] = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": cores,
-                                    "kind": "port",
-                                    "sample": f"{cspp} spp of every {step}th pixel of "
-                                              f"{args.workload} ({crays} rays, {cdt:.1f} s)"}
+
+    # ---- BASELINE config 4 inside the N-GPU record (default at N = 8): 10,240,002 instanced
+    # triangles at 3840x2160, weak split, 133 MB reduce per batch; then rank 0 alone on the same
+    # per-GPU load, which gives north_star's ">= 7x at 8 GPUs on a 10M-triangle scene"
+    if args.config4 == "on" or (args.config4 == "auto" and world == 8):
+        c4, w4, h4, b4 = build_workload("lattice-10M-4k-8b")
+        m.set_scene(c4["scene"])
+        m.resize((w4, h4))
+        spp4, k4 = 15, 3
+        cfg4 = dict(max_bounces=b4, jitter=1, seed=0, env_color=c4["env_color"], sample_offset=0,
+                    sample_stride=1, count_stats=0, traversal_variant=args.variant)
+        m.set_config(**cfg4, spp_per_call=spp4 * world)
+        v4 = c4["view"]
+        view, keep = v4, view
+        timed_steps(1)
+        m.ray_counters(reset=True)
+        ms4 = timed_steps(k4)
+        rays4 = total_rays()
+        m.reduce_time(reset=True)
+        for _ in range(2):
+            m.render(v4)
+            m.reduce()
+            m.synchronize()
+        red4, n4 = m.reduce_time(reset=True)
+        (ms4,) = max_over_ranks(ms4)
+        barrier()
+        one = None
+        if rank == 0:  # the same per-GPU load on ONE GPU
+            r.set_config(**cfg4, spp_per_call=spp4)
+            r.reset_accumulation()
+            r.raytrace(v4)
+            dev.synchronize()
+            r.ray_counters(reset=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for _ in range(k4):
+                    r.raytrace(v4)
+                e1.record(stream)
+            torch.cuda.synchronize()
+            cc = r.ray_counters(reset=True)
+            one = (cc["primary"] + cc["bounce"] + cc["shadow"]) / (e0.elapsed_time(e1) * 1e-3) / 1e6
+        barrier()
+        view = keep
+        if rank == 0:
+            mr4 = rays4 / (ms4 * 1e-3) / 1e6
+            line["config4"] = {
+                "workload": "lattice-10M-4k-8b", "triangles": 125 * 81920 + 2, "width": w4,
+                "height": h4, "bounces": b4, "spp_per_gpu_per_step": spp4, "steps": k4,
+                "ms_per_step": ms4 / k4, "mrays_s": mr4, "one_gpu_mrays_s": one,
+                "speedup_vs_one_gpu": mr4 / one if one else None,
+                "reduce_bytes": w4 * h4 * 16, "nccl_ms": red4 / max(n4, 1)}
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- BASELINE config 5 (interactive frame + SVGF) beside the headline
+        try:
+            line["config5"] = config5_frames(lb.Device(local_rank), c, w, h)
+        except lb.Error as e:  # an extra must not take the headline down
+            line["config5"] = {"error": str(e)}
+
+    parity_failed = False
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        crays, cdt, _, _ = cpu_reference_sample(c, w, h, bounces, 1, 64)
+        frame_s = cdt * 64  # estimated CPU time of one full 1-spp frame
+        target = 15.0       # seconds of CPU work for the baseline sample
+        step = min(max(int(frame_s / target), 1), 64)
+        cspp = max(1, int(target / frame_s)) if step == 1 else 1
+        crays, cdt, _, cpu_sum = cpu_reference_sample(c, w, h, bounces, cspp, step)
+        line["cpu_baseline"] = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": cores,
+                                "kind": "port",
+                                "sample": f"{cspp} spp of every {step}th pixel of "
+                                          f"{args.workload} ({crays} rays, {cdt:.1f} s)"}
+        # the GPU traces exactly the samples the CPU just traced; compared, not thrown away
+        r.set_config(**common, spp_per_call=cspp, count_stats=0)
+        r.reset_accumulation()
+        r.raytrace(view)
+        gpu_sum, _ = r.read_accum_sum()
+        line["parity_check"] = parity_check(gpu_sum, cpu_sum)
+        parity_failed = not line["parity_check"]["pass"]
+    if rank == 0:
         print(json.dumps(line), file=_JSON_OUT, flush=True)
+        _JSON_OUT.flush()
+    m.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    bad_multi = rank == 0 and multi_check is not None and not multi_check["pass"]
+    if parity_failed or bad_multi:
+        raise SystemExit("bench.py: result check FAILED (parity_check / multi_check in the JSON "
+                         "line): the numbers above describe a wrong image")
 
 
 def main() -> None:
@@ -407,8 +614,13 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="spheres-1M-1080p-8b", choices=sorted(WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=64,
-                    help="samples per pixel traced by one step (one raytrace call = one batch)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+                    help="samples per pixel every GPU traces per step (weak scaling); the "
+                         "`strong` block splits this same number over the GPUs")
+    ap.add_argument("--no-cpu-baseline", action="store_true",
+                    help="skip the cpu_baseline + parity_check leg (N = 1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-5 block (N = 1)")
+    ap.add_argument("--config4", default="auto", choices=["auto", "on", "off"],
+                    help="BASELINE config 4 block (10M-triangle lattice at 4K): auto = at N = 8")
     ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (tuning)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there while the bench

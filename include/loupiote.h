@@ -153,7 +153,8 @@ typedef enum lp_blit_mode {
  * the measurement contract needs.  Zero-initialise then call lp_render_config_default. */
 typedef struct lp_render_config {
   uint32_t max_bounces;      /* path segments per sample incl. the primary one; ref = 3 */
-  uint32_t spp_per_call;     /* samples per pixel traced by ONE raytrace call; ref = 1 */
+  uint32_t spp_per_call;     /* samples per pixel traced by ONE raytrace call; ref = 1.  The SVGF
+                              * blit modes (DenoisedPathrace, Temporal) always trace 1 */
   uint32_t seed;             /* global RNG offset (PerDrawUniforms.seed start value) */
   uint32_t atrous_iterations;/* ref uses an even count [ref asvgf.rs:286]; default 4 */
   uint32_t jitter;           /* 1: sub-pixel jitter; 0: pixel-centre rays (ID parity) */
@@ -226,9 +227,16 @@ LP_API lp_status lp_scene_push_material(lp_scene *scene, const lp_material *mate
  * emissive field [ref binary.rs:63-69]). */
 LP_API lp_status lp_scene_set_material_emission(lp_scene *scene, uint32_t material_index,
                                                 const float rgb[3]);
+/* scene.materials[i] = .. / scene.lights[i] = .. (pub fields [ref scene.rs:30-35]): edits of
+ * EXISTING entries.  Like lp_scene_set_material_emission they are small-table edits: no
+ * re-layout; lp_scene_gpu_update_instances carries them to an existing SceneGPU. */
+LP_API lp_status lp_scene_set_material(lp_scene *scene, uint32_t material_index,
+                                       const lp_material *material);
+LP_API lp_status lp_scene_set_light(lp_scene *scene, uint32_t light_index, const lp_light *light);
 /* scene.lights.push(..) [ref scene.rs:33]. */
 LP_API lp_status lp_scene_push_light(lp_scene *scene, const lp_light *light, uint32_t *out_index);
-/* scene.images.push(ImageData::new(rgba8, w, h)) [ref scene.rs:5-28, gltf.rs:150-153]. */
+/* scene.images.push(ImageData::new(rgba8, w, h)) [ref scene.rs:5-28, gltf.rs:150-153].
+ * LP_ERR_INVALID_ARG unless 1 <= width, height <= 16384 (the atlas layer limit). */
 LP_API lp_status lp_scene_push_image(lp_scene *scene, const uint8_t *rgba8, uint32_t width,
                                      uint32_t height, uint32_t *out_index);
 
@@ -367,7 +375,10 @@ LP_API lp_status lp_renderer_upload_noise_texture(lp_renderer *r, const uint8_t 
                                                   uint32_t bytes_per_row);
 /* Renderer::get_size [ref renderer.rs:683-685]. */
 LP_API lp_status lp_renderer_get_size(const lp_renderer *r, uint32_t *width, uint32_t *height);
-/* pub fields Renderer.accumulate / .downsample_factor [ref renderer.rs:203-204]. */
+/* pub fields Renderer.accumulate / .downsample_factor [ref renderer.rs:203-204].  With
+ * accumulate off a frame OVERWRITES the target and the sample count returns to 0 (the reference
+ * leaves frame_count where it was until reset_accumulation; its app only clears the flag
+ * through reset_accumulation, where both agree [ref renderer.rs:609-618, app.rs:308-318]). */
 LP_API lp_status lp_renderer_set_accumulate(lp_renderer *r, int flag);
 LP_API lp_status lp_renderer_get_accumulate(const lp_renderer *r, int *flag);
 LP_API lp_status lp_renderer_set_downsample_factor(lp_renderer *r, float factor);
@@ -427,6 +438,78 @@ LP_API lp_status lp_renderer_kernel_times(lp_renderer *r, double ms[4], uint64_t
 /* FP32 FMA throughput microbenchmark (TFLOP/s, best of `repeats`), the second roofline
  * denominator of SURVEY 8(d). */
 LP_API lp_status lp_device_fp32_peak(lp_device *dev, int repeats, double *tflops);
+
+/* ------------------------------------------------------------------ multi-GPU (extension)
+ *
+ * The reference renders on ONE device [ref crates/standalone/src/lib.rs:220-231]; the
+ * measurement contract splits a frame's samples over the GPUs of one box: the
+ * scene is replicated (SceneGPU::new_from_scene per device [ref scene.rs:151-187]), global rank
+ * g of W traces sample indices g, g+W, ... of the sequence ONE GPU would trace, and the FP32 SUM
+ * accumulators are summed to rank 0 (NCCL over NVLink, or one fused peer-memory kernel), where
+ * the x 1/count -> tone map -> sRGB8 of BlitPass [ref renderer.rs:756-770] follows on the same
+ * stream.  An lp_multi owns one lp_device / lp_scene_gpu / lp_renderer per local GPU; handles
+ * returned by lp_multi_device / lp_multi_renderer are BORROWED.  One caller thread per
+ * lp_multi.  NCCL failures surface as LP_ERR_NCCL (ncclCommGetAsyncError is polled). */
+typedef struct lp_multi lp_multi;
+#define LP_MULTI_ID_BYTES 128 /* == NCCL_UNIQUE_ID_BYTES */
+
+typedef enum lp_multi_reduce_mode {
+  LP_REDUCE_AUTO = 0, /* PEER when one process drives GPUs that all map each other, else NCCL */
+  LP_REDUCE_NCCL = 1, /* ncclReduce(sum, fp32, root 0) + tone map on rank 0's comm stream */
+  LP_REDUCE_PEER = 2  /* one kernel per GPU over NVLink peer memory: reduce-scatter of the
+                         accumulators + tone map + gather into rank 0's targets */
+} lp_multi_reduce_mode;
+
+/* ONE process drives n GPUs (ncclCommInitAll, one host worker thread per device);
+ * cuda_ordinals == NULL means devices 0..n-1.  n == 1 is valid (no NCCL communicator). */
+LP_API lp_status lp_multi_create(const int *cuda_ordinals, int n_devices, lp_multi **out);
+/* One process per GPU (torchrun / MPI): rank 0 calls lp_multi_unique_id and carries the bytes to
+ * the other ranks by its own means; then EVERY rank calls lp_multi_create_rank (collective:
+ * ncclCommInitRank). */
+LP_API lp_status lp_multi_unique_id(uint8_t id[LP_MULTI_ID_BYTES]);
+LP_API lp_status lp_multi_create_rank(int cuda_ordinal, const uint8_t id[LP_MULTI_ID_BYTES],
+                                      int n_ranks, int rank, lp_multi **out);
+LP_API lp_status lp_multi_destroy(lp_multi *m);
+LP_API lp_status lp_multi_info(const lp_multi *m, int *world, int *first_rank, int *local_devices,
+                               int *peer_access);
+LP_API lp_status lp_multi_device(lp_multi *m, int local_index, lp_device **out);
+LP_API lp_status lp_multi_renderer(lp_multi *m, int local_index, lp_renderer **out);
+/* Replicated SceneGPU::new_from_scene (device_build != 0: lp_scene_gpu_new_from_scene_lbvh) +
+ * Renderer::set_resources on every local device. */
+LP_API lp_status lp_multi_set_scene(lp_multi *m, lp_scene *scene, int device_build);
+/* lp_scene_gpu_update_instances on every copy. */
+LP_API lp_status lp_multi_update_instances(lp_multi *m, lp_scene *scene);
+/* Replicated ProbeGPU::new [ref scene.rs:71-121]; rgbe8 == NULL unbinds the probe. */
+LP_API lp_status lp_multi_set_probe(lp_multi *m, const uint8_t *rgbe8, uint32_t width,
+                                    uint32_t height);
+/* Renderer::resize on every local device with the given downsample factor. */
+LP_API lp_status lp_multi_resize(lp_multi *m, uint32_t width, uint32_t height,
+                                 float downsample_factor);
+/* cfg describes the frame ONE GPU would trace: spp_per_call = TOTAL samples per pixel of one
+ * lp_multi_render over all ranks; rank g gets sample_offset + g * sample_stride, stride
+ * sample_stride * W and ceil((spp_per_call - g) / W) samples, so the reduced image is the 1-GPU
+ * image of the same cfg up to FP32 summation order. */
+LP_API lp_status lp_multi_set_config(lp_multi *m, const lp_render_config *cfg);
+LP_API lp_status lp_multi_set_accumulate(lp_multi *m, int flag);
+LP_API lp_status lp_multi_set_reduce_mode(lp_multi *m, lp_multi_reduce_mode mode);
+/* Renderer::raytrace on every local device (asynchronous). */
+LP_API lp_status lp_multi_render(lp_multi *m, const float view_transform[16]);
+/* The exchange step (asynchronous, on the communication streams; the next lp_multi_render may
+ * trace beside it, only its accumulation waits).  Collective over all ranks. */
+LP_API lp_status lp_multi_reduce(lp_multi *m);
+LP_API lp_status lp_multi_synchronize(lp_multi *m);
+/* Device-side join: every local tracing stream (lp_device_stream) waits for the exchange step
+ * enqueued so far; the host does not block.  An event recorded on that stream afterwards
+ * covers render + reduce. */
+LP_API lp_status lp_multi_join(lp_multi *m);
+/* Rank 0 only: the reduced frame as sRGB8 (Renderer::read_pixels [ref renderer.rs:727-811]), the
+ * reduced FP32 SUM target (alpha = total sample count), the ray counters summed over ranks. */
+LP_API lp_status lp_multi_read_pixels(lp_multi *m, uint8_t *out, size_t cap);
+LP_API lp_status lp_multi_read_accum_sum(lp_multi *m, float *out, size_t cap_floats);
+LP_API lp_status lp_multi_ray_counters(lp_multi *m, lp_ray_counters *out, int reset);
+/* Device time of the exchange step on rank 0 (inputs ready -> sRGB8 frame complete), summed over
+ * the lp_multi_reduce calls so far, and their number. */
+LP_API lp_status lp_multi_reduce_time(lp_multi *m, double *total_ms, uint64_t *count, int reset);
 
 #ifdef __cplusplus
 }

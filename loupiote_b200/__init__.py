@@ -4,9 +4,10 @@ hot path of DavidPeicho/loupiote behind the reference's `loupiote-core` renderer
 The product is the C-ABI library (include/loupiote.h, loupiote_b200/csrc); this package is
 the thin host-side mirror of the reference interface used by tests and bench.py.
 """
-from .api import (BlitMode, BLASArray, Camera, Device, Error, Light, Material, ProbeGPU,  # noqa: F401
-                  RayCounters, RenderConfig, Renderer, Scene, SceneGPU, loaders, look_at_view)
+from .api import (BlitMode, BLASArray, Camera, Device, Error, Light, Material,  # noqa: F401
+                  MultiRenderer, ProbeGPU, RayCounters, ReduceMode, RenderConfig, Renderer, Scene,
+                  SceneGPU, loaders, look_at_view)
 
-__all__ = ["BlitMode", "BLASArray", "Camera", "Device", "Error", "Light", "Material", "ProbeGPU",
-           "RayCounters", "RenderConfig", "Renderer", "Scene", "SceneGPU", "loaders",
+__all__ = ["BlitMode", "BLASArray", "Camera", "Device", "Error", "Light", "Material", "MultiRenderer", "ProbeGPU",
+           "RayCounters", "ReduceMode", "RenderConfig", "Renderer", "Scene", "SceneGPU", "loaders",
            "look_at_view"]

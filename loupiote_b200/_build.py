@@ -26,6 +26,7 @@ SOURCES = [
     CSRC / "host" / "textures.cpp",
     CSRC / "host" / "api_scene.cpp",
     CSRC / "cuda" / "api_render.cu",
+    CSRC / "cuda" / "api_multi.cu",
     CSRC / "cuda" / "lbvh_build.cu",
 ]
 # translation units whose arithmetic never decides a hit: FMA contraction on
@@ -96,7 +97,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "",
     if failed:
         raise RuntimeError("nvcc failed building libloupiote_b200.so")
     link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(lib_path),
-            *[str(o) for o in objs]]
+            *[str(o) for o in objs], "-lnccl"]  # lp_multi_*: NCCL over NVLink
     proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -108,6 +108,8 @@ _PROTOTYPES = {
     "lp_scene_set_instance_transform": (C.c_int, [_vp, C.c_uint32, c_float_p]),
     "lp_scene_push_material": (C.c_int, [_vp, C.POINTER(Material), c_u32_p]),
     "lp_scene_set_material_emission": (C.c_int, [_vp, C.c_uint32, c_float_p]),
+    "lp_scene_set_material": (C.c_int, [_vp, C.c_uint32, C.POINTER(Material)]),
+    "lp_scene_set_light": (C.c_int, [_vp, C.c_uint32, C.POINTER(Light)]),
     "lp_scene_push_light": (C.c_int, [_vp, C.POINTER(Light), c_u32_p]),
     "lp_scene_push_image": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, c_u32_p]),
     "lp_scene_get_array": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t),
@@ -165,7 +167,33 @@ _PROTOTYPES = {
     "lp_renderer_kernel_times": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
                                            C.c_int]),
     "lp_device_fp32_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
+    "lp_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "lp_multi_unique_id": (C.c_int, [_vp]),
+    "lp_multi_create_rank": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lp_multi_destroy": (C.c_int, [_vp]),
+    "lp_multi_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int)]),
+    "lp_multi_device": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "lp_multi_renderer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "lp_multi_set_scene": (C.c_int, [_vp, _vp, C.c_int]),
+    "lp_multi_update_instances": (C.c_int, [_vp, _vp]),
+    "lp_multi_set_probe": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32]),
+    "lp_multi_resize": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_float]),
+    "lp_multi_set_config": (C.c_int, [_vp, C.POINTER(RenderConfig)]),
+    "lp_multi_set_accumulate": (C.c_int, [_vp, C.c_int]),
+    "lp_multi_set_reduce_mode": (C.c_int, [_vp, C.c_int]),
+    "lp_multi_render": (C.c_int, [_vp, c_float_p]),
+    "lp_multi_reduce": (C.c_int, [_vp]),
+    "lp_multi_synchronize": (C.c_int, [_vp]),
+    "lp_multi_join": (C.c_int, [_vp]),
+    "lp_multi_read_pixels": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "lp_multi_read_accum_sum": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "lp_multi_ray_counters": (C.c_int, [_vp, C.POINTER(RayCounters), C.c_int]),
+    "lp_multi_reduce_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                       C.c_int]),
 }
+LP_MULTI_ID_BYTES = 128
+REDUCE_AUTO, REDUCE_NCCL, REDUCE_PEER = 0, 1, 2
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

@@ -73,15 +73,19 @@ class BlitMode(enum.IntEnum):
 class Device:
     """loupiote_core::Device (device.rs:71-141): owns the CUDA context + stream."""
 
-    def __init__(self, cuda_ordinal: int = 0):
+    def __init__(self, cuda_ordinal: int = 0, _borrowed=None):
         self._h = C.c_void_p()
-        _check(_ffi.lib().lp_device_create(cuda_ordinal, C.byref(self._h)))
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a handle owned by a MultiRenderer
+            self._h = _borrowed
+        else:
+            _check(_ffi.lib().lp_device_create(cuda_ordinal, C.byref(self._h)))
         self.ordinal = cuda_ordinal
 
     def close(self) -> None:
-        if self._h:
+        if self._h and self._owned:
             _ffi.lib().lp_device_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -288,13 +292,36 @@ class Scene:
         _check(_ffi.lib().lp_scene_set_material_emission(self._h, material_index,
                                                          e.ctypes.data_as(_ffi.c_float_p)))
 
-    def push_light(self, center, tangent, bitangent, intensity, color=(1, 1, 1)) -> int:
+    def set_material(self, material_index: int, color=(1, 1, 1, 1), roughness=1.0,
+                     reflectivity=0.0, albedo_texture=_ffi.LP_INVALID_INDEX,
+                     mra_texture=_ffi.LP_INVALID_INDEX) -> None:
+        """scene.materials[i] = Material{..}: edit of an existing entry (no re-layout;
+        SceneGPU.update_instances carries it to the device)."""
+        m = Material()
+        c = list(color) + [1.0] * (4 - len(color))
+        m.color = (C.c_float * 4)(*c)
+        m.roughness, m.reflectivity = roughness, reflectivity
+        m.albedo_texture, m.mra_texture = albedo_texture, mra_texture
+        _check(_ffi.lib().lp_scene_set_material(self._h, material_index, C.byref(m)))
+
+    @staticmethod
+    def _light(center, tangent, bitangent, intensity, color):
         l = Light()
         l.center = (C.c_float * 3)(*center)
         l.tangent = (C.c_float * 3)(*tangent)
         l.bitangent = (C.c_float * 3)(*bitangent)
         l.color = (C.c_float * 3)(*color)
         l.intensity = intensity
+        return l
+
+    def set_light(self, light_index: int, center, tangent, bitangent, intensity,
+                  color=(1, 1, 1)) -> None:
+        """scene.lights[i] = ..: edit of an existing light (small-table edit, see set_material)."""
+        l = self._light(center, tangent, bitangent, intensity, color)
+        _check(_ffi.lib().lp_scene_set_light(self._h, light_index, C.byref(l)))
+
+    def push_light(self, center, tangent, bitangent, intensity, color=(1, 1, 1)) -> int:
+        l = self._light(center, tangent, bitangent, intensity, color)
         out = C.c_uint32()
         _check(_ffi.lib().lp_scene_push_light(self._h, C.byref(l), C.byref(out)))
         return out.value
@@ -439,11 +466,16 @@ class ProbeGPU:
 class Renderer:
     """loupiote_core::Renderer (renderer.rs:169-811)."""
 
-    def __init__(self, device: Device, original_size: Sequence[int], downsample_factor=None):
+    def __init__(self, device: Device, original_size: Sequence[int] = (2, 2),
+                 downsample_factor=None, _borrowed=None):
         self.device = device
         self._h = C.c_void_p()
+        self._owned = _borrowed is None
         self._scene_gpu: Optional[SceneGPU] = None
         self._probe: Optional[ProbeGPU] = None
+        if _borrowed is not None:  # a handle owned by a MultiRenderer
+            self._h = _borrowed
+            return
         w, h = int(original_size[0]), int(original_size[1])
         _check(_ffi.lib().lp_renderer_new(device._h, w, h, C.byref(self._h)))
         if downsample_factor is not None:
@@ -453,9 +485,9 @@ class Renderer:
             self.resize(None, None, (w, h))
 
     def close(self) -> None:
-        if self._h:
+        if self._h and self._owned:
             _ffi.lib().lp_renderer_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -626,6 +658,164 @@ class Renderer:
         out = np.empty((h, w, ch), dtype=dt)
         _check(_ffi.lib().lp_renderer_read_aux(self._h, which, out.ctypes.data, out.nbytes))
         return out
+
+
+class ReduceMode(enum.IntEnum):
+    """lp_multi_reduce_mode: how the FP32 SUM accumulators are summed to rank 0."""
+    AUTO = _ffi.REDUCE_AUTO
+    NCCL = _ffi.REDUCE_NCCL
+    PEER = _ffi.REDUCE_PEER
+
+
+class MultiRenderer:
+    """lp_multi (include/loupiote.h): the Renderer on several GPUs of one box.  The scene is
+    replicated, the samples of a frame are split (global rank g of W traces indices g, g+W, ...
+    of the sequence one GPU would trace) and the accumulators are summed to rank 0.
+
+        m = MultiRenderer.create([0, 1, 2, 3])             # one process, four GPUs
+        m = MultiRenderer.create_rank(local, id, W, rank)  # one process per GPU (torchrun)
+        m.set_scene(scene); m.resize((w, h)); m.set_config(spp_per_call=64, ...)
+        m.render(view); m.reduce(); rgba8 = m.read_pixels()
+    """
+
+    def __init__(self, handle):
+        self._h = handle
+        w, fr, n, peer = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(_ffi.lib().lp_multi_info(self._h, C.byref(w), C.byref(fr), C.byref(n),
+                                        C.byref(peer)))
+        self.world, self.rank, self.local_devices = w.value, fr.value, n.value
+        self.peer_access = bool(peer.value)
+        self._cfg = RenderConfig()
+        _ffi.lib().lp_render_config_default(self._cfg)
+        self._size = (0, 0)
+        self._scene = None
+
+    @classmethod
+    def create(cls, cuda_ordinals=None, n_devices: Optional[int] = None) -> "MultiRenderer":
+        if cuda_ordinals is not None:
+            n = len(cuda_ordinals)
+            arr = (C.c_int * n)(*cuda_ordinals)
+        else:
+            n, arr = int(n_devices or 1), None
+        h = C.c_void_p()
+        _check(_ffi.lib().lp_multi_create(arr, n, C.byref(h)))
+        return cls(h)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(_ffi.LP_MULTI_ID_BYTES)
+        _check(_ffi.lib().lp_multi_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def create_rank(cls, cuda_ordinal: int, unique_id: bytes, world: int,
+                    rank: int) -> "MultiRenderer":
+        if len(unique_id) != _ffi.LP_MULTI_ID_BYTES:
+            raise ValueError("unique_id must be LP_MULTI_ID_BYTES long")
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, _ffi.LP_MULTI_ID_BYTES)
+        _check(_ffi.lib().lp_multi_create_rank(cuda_ordinal, buf, world, rank, C.byref(h)))
+        return cls(h)
+
+    def close(self) -> None:
+        if self._h:
+            _ffi.lib().lp_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device(self, local_index: int = 0) -> Device:
+        h = C.c_void_p()
+        _check(_ffi.lib().lp_multi_device(self._h, local_index, C.byref(h)))
+        return Device(_borrowed=h)
+
+    def renderer(self, local_index: int = 0) -> Renderer:
+        """The borrowed per-device Renderer (counters, kernel timing, first-hit read-backs)."""
+        h = C.c_void_p()
+        _check(_ffi.lib().lp_multi_renderer(self._h, local_index, C.byref(h)))
+        return Renderer(self.device(local_index), _borrowed=h)
+
+    def set_scene(self, scene: "Scene", device_build: bool = False) -> None:
+        self._scene = scene
+        _check(_ffi.lib().lp_multi_set_scene(self._h, scene._h, int(bool(device_build))))
+
+    def update_instances(self, scene: "Scene") -> None:
+        _check(_ffi.lib().lp_multi_update_instances(self._h, scene._h))
+
+    def set_probe(self, rgbe8: Optional[np.ndarray], width: int = 0, height: int = 0) -> None:
+        if rgbe8 is None:
+            _check(_ffi.lib().lp_multi_set_probe(self._h, None, 0, 0))
+            return
+        data = np.ascontiguousarray(rgbe8, dtype=np.uint8).reshape(-1)
+        _check(_ffi.lib().lp_multi_set_probe(self._h, data.ctypes.data, width, height))
+
+    def resize(self, size, downsample_factor: float = 1.0) -> None:
+        _check(_ffi.lib().lp_multi_resize(self._h, int(size[0]), int(size[1]),
+                                          float(downsample_factor)))
+        self._size = (max(1, int(size[0] * downsample_factor)),
+                      max(1, int(size[1] * downsample_factor)))
+
+    def set_config(self, **kwargs) -> RenderConfig:
+        """Fields of lp_render_config describing the frame ONE GPU would trace; spp_per_call is
+        the total over all ranks."""
+        for k, v in kwargs.items():
+            if k == "env_color":
+                self._cfg.env_color = (C.c_float * 3)(*v)
+            elif hasattr(self._cfg, k):
+                setattr(self._cfg, k, v)
+            else:
+                raise TypeError(f"unknown render config field {k!r}")
+        _check(_ffi.lib().lp_multi_set_config(self._h, C.byref(self._cfg)))
+        return self._cfg
+
+    def set_accumulate(self, flag: bool) -> None:
+        _check(_ffi.lib().lp_multi_set_accumulate(self._h, int(bool(flag))))
+
+    def set_reduce_mode(self, mode: ReduceMode) -> None:
+        _check(_ffi.lib().lp_multi_set_reduce_mode(self._h, int(mode)))
+
+    def render(self, view_transform) -> None:
+        m = _mat4(view_transform)
+        _check(_ffi.lib().lp_multi_render(self._h, m.ctypes.data_as(_ffi.c_float_p)))
+
+    def reduce(self) -> None:
+        _check(_ffi.lib().lp_multi_reduce(self._h))
+
+    def synchronize(self) -> None:
+        _check(_ffi.lib().lp_multi_synchronize(self._h))
+
+    def join(self) -> None:
+        """Device-side: the tracing streams wait for the exchange step enqueued so far."""
+        _check(_ffi.lib().lp_multi_join(self._h))
+
+    def read_pixels(self) -> np.ndarray:
+        w, h = self._size
+        out = np.empty((h, w, 4), dtype=np.uint8)
+        _check(_ffi.lib().lp_multi_read_pixels(self._h, out.ctypes.data, out.nbytes))
+        return out
+
+    def read_accum_sum(self) -> np.ndarray:
+        w, h = self._size
+        out = np.empty((h, w, 4), dtype=np.float32)
+        _check(_ffi.lib().lp_multi_read_accum_sum(self._h, out.ctypes.data, out.size))
+        return out
+
+    def ray_counters(self, reset: bool = False) -> dict:
+        c = RayCounters()
+        out = C.byref(c) if self.rank == 0 else None
+        _check(_ffi.lib().lp_multi_ray_counters(self._h, out, int(reset)))
+        return {"primary": c.primary, "bounce": c.bounce, "shadow": c.shadow,
+                "n_int": list(c.n_int), "n_tri": list(c.n_tri), "n_inst": list(c.n_inst)}
+
+    def reduce_time(self, reset: bool = False):
+        """(total ms of the exchange step on rank 0's communication stream, number of reduces)."""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(_ffi.lib().lp_multi_reduce_time(self._h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, int(n.value)
 
 
 def look_at_view(origin, forward) -> np.ndarray:

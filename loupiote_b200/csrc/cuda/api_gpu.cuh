@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../host/api_common.hpp"
@@ -61,6 +62,9 @@ struct lp_device {
   cudaStream_t stream2 = nullptr;  // shadow rays of bounce b overlap the extend of bounce b+1
   int sm_count = 0;
   cudaDeviceProp prop{};
+  // launch shapes of the persistent kernels on THIS device (kernel address -> grid size)
+  std::unordered_map<const void *, int> grid_cache;
+  int pool_grid = 0;  // resident ray-pool blocks (trace_pool.cuh), see pool_grid() in api_render.cu
 };
 
 struct lp_scene_gpu {

@@ -14,10 +14,13 @@
 #include "../host/api_common.hpp"
 #include "../host/scene.hpp"
 #include "api_gpu.cuh"
+#include "renderer_state.cuh"
 #include "kernels.cuh"
 #include "svgf.cuh"
 #include "svgf_temporal.cuh"
-#include "trace_persistent.cuh"
+#ifdef LP_VARIANTS
+#include "trace_persistent.cuh"  // measured and rejected alternatives
+#endif
 #include "traverse4.cuh"
 #include "trace_pool.cuh"
 
@@ -28,86 +31,18 @@ using namespace lp;
 static_assert(3 * lp::lbvh::kMaxLevels + 3 == kStackSize4,
               "lbvh_build.cu's depth limit must match the 4-wide traversal stack");
 
-struct lp_probe {
-  lp_device *dev = nullptr;
-  DevBuf<uchar4> texels;
-  DevBuf<float> pmf, cdf_row, cdf_col;
-  uint32_t w = 0, h = 0;
-};
-
-namespace {
-struct PingPong {
-  DevBuf<float4> radiance;
-  DevBuf<uint4> gbuffer;
-  DevBuf<float2> moments;
-  DevBuf<float> history;
-};
-}  // namespace
-
-struct lp_renderer {
-  lp_device *dev = nullptr;
-  lp_scene_gpu *sg = nullptr;
-  lp_probe *probe = nullptr;
-  uint32_t width = 0, height = 0;  // internal (downsampled) size
-  uint32_t tiles_x = 0, slots_per_sample = 0, wave_samples = 0, n_slots = 0;
-  float downsample = 0.5f;
-  bool accumulate = false;
-  lp_blit_mode mode = LP_BLIT_PAHTRACE;
-  bool frame_back = true;
-  bool svgf_back = true;
-  bool use_noise = false;
-  lp_render_config cfg{};
-  uint32_t seed_cursor = 0;
-  uint32_t samples_accumulated = 0;
-  float prev_w2s[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-  lp_camera camera{};
-
-  // per-slot path state + queues
-  DevBuf<float4> ray_o, ray_d, thr, rad, hit;
-  DevBuf<uint32_t> hit_inst, queue0, queue1;
-  DevBuf<float4> sl_o, sl_d, sl_c, se_o, se_d, se_c;
-  DevBuf<uint32_t> counts;
-  DevBuf<uint32_t> pool_scratch;  // traversal stacks of the ray-pool kernels
-  DevBuf<Counters> counters;
-  // render targets
-  DevBuf<float4> accum;  // main target: RGBA32F sum, alpha = sample count
-  DevBuf<float4> scratch;
-  DevBuf<uchar4> ldr;
-  DevBuf<uint32_t> fh_inst, fh_prim;
-  DevBuf<float> fh_t;
-  // ASVGF resources [ref asvgf.rs:9-152]
-  PingPong pp[2];
-  DevBuf<float2> motion;
-  DevBuf<float4> temp;
-  DevBuf<uchar4> noise;
-  uint32_t noise_w = 0, noise_h = 0;
-
-  // Queries [ref renderer.rs:321,444-517]
-  static constexpr int kMaxQueries = 10;
-  cudaEvent_t ev[kMaxQueries][2] = {};
-  cudaEvent_t ev_shaded = nullptr, ev_connected = nullptr;  // cross-stream ordering
-  std::vector<std::string> q_labels;
-  std::vector<const char *> q_label_ptrs;
-  std::vector<double> q_ms;
-  int q_open = -1;
-
-  // measurement hooks
-  bool kt_enabled = false;
-  std::vector<cudaEvent_t> kt_events;  // pairs
-  std::vector<int> kt_kind;
-  size_t kt_used = 0;
-  double kt_ms[4] = {0, 0, 0, 0};
-  uint64_t kt_launches[4] = {0, 0, 0, 0};
-
-};
-
 namespace {
 
 uint32_t downsampled(uint32_t v, float f) { return std::max(1u, (uint32_t)((float)v * f)); }
 
-lp_status allocate_targets(lp_renderer *r) {
+cudaError_t allocate_pool_scratch(lp_renderer *r);
+
+// Per-slot path state + queues: sized by the samples in flight per wave, so it is re-made when
+// spp_per_call changes.  Never touches the per-pixel targets: the accumulated image and its
+// sample count survive an spp-only lp_renderer_set_config (a split or resumed render changes
+// the batch size between calls).
+lp_status allocate_path_state(lp_renderer *r) {
   const uint32_t w = r->width, h = r->height;
-  const size_t P = (size_t)w * h;
   r->tiles_x = (w + 7) / 8;
   const uint32_t tiles_y = (h + 3) / 4;
   r->slots_per_sample = r->tiles_x * tiles_y * 32u;
@@ -144,6 +79,17 @@ lp_status allocate_targets(lp_renderer *r) {
     CUDA_CHECK(r->counters.alloc(1));
     CUDA_CHECK(cudaMemsetAsync(r->counters.ptr, 0, sizeof(Counters), r->dev->stream));
   }
+  CUDA_CHECK(allocate_pool_scratch(r));
+  return LP_OK;
+}
+
+// Per-pixel render targets (Renderer::new / resize [ref renderer.rs:220-358]): cleared, and the
+// accumulation restarts.
+lp_status allocate_targets(lp_renderer *r) {
+  const lp_status ps = allocate_path_state(r);
+  if (ps != LP_OK) return ps;
+  const uint32_t w = r->width, h = r->height;
+  const size_t P = (size_t)w * h;
   CUDA_CHECK(r->accum.alloc(P));
   CUDA_CHECK(r->scratch.alloc(P));
   CUDA_CHECK(r->ldr.alloc(P));
@@ -246,139 +192,160 @@ void query_end(lp_renderer *r) {
 //               nodes (traverse4.cuh); bounce and shadow rays through the shared-memory ray
 //               pool (trace_pool.cuh), also over the 4-wide fp16 nodes
 //   15          the first version: canonical BVH2, one ray per thread (kernels.cuh)
+// and, only in a library built with -DLP_VARIANTS (measured and rejected):
 //   1..9        persistent lanes with ray replacement + postponed phases (trace_persistent.cuh)
 //   10 / 13     4-wide nodes, one ray per thread (fp32 / fp16 boxes)
 //   11 / 12     ray pool for every ray (fp32 / fp16 boxes)
 // count_stats always runs the canonical BVH2 walk (exact slab test): its counters define the
-// roofline and equal the CPU restatement's.  Measurements: DESIGN.md section 6.
+// roofline and equal the CPU restatement's.
+//
+// Launch shapes are cached PER lp_device (one caller thread per device: lp_multi drives its
+// devices from one thread each).
 template <typename K>
-int cached_grid(K kernel, int sm_count) {
-  static int grid = 0;  // one per instantiation
-  if (!grid) grid = persistent_grid(kernel, 128, sm_count);
+int cached_grid(lp_device *dev, K kernel) {
+  int &grid = dev->grid_cache[(const void *)kernel];
+  if (!grid) grid = persistent_grid(kernel, 128, dev->sm_count);
   return grid;
 }
 
+bool variant_available(uint32_t v) {
+#ifdef LP_VARIANTS
+  return v <= 15;
+#else
+  return v == 0 || v == 14 || v == 15;
+#endif
+}
+
+#ifdef LP_VARIANTS
 template <int TRI_MIN, int ENTRY_MIN, int REFILL_MIN, int MIN_BLOCKS>
 void launch_persistent(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, int env,
-                       bool stats) {
-  cudaStream_t st = r->dev->stream;
-  const int sm = r->dev->sm_count;
+                       bool stats, cudaStream_t st) {
+  lp_device *d = r->dev;
   if (any) {
     if (stats) {
       auto k = trace_kernel<true, true, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
-      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+      k<<<cached_grid(d, k), 128, 0, st>>>(P, b, env);
     } else {
       auto k = trace_kernel<true, false, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
-      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+      k<<<cached_grid(d, k), 128, 0, st>>>(P, b, env);
     }
   } else {
     if (stats) {
       auto k = trace_kernel<false, true, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
-      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+      k<<<cached_grid(d, k), 128, 0, st>>>(P, b, env);
     } else {
       auto k = trace_kernel<false, false, TRI_MIN, ENTRY_MIN, REFILL_MIN, MIN_BLOCKS>;
-      k<<<cached_grid(k, sm), 128, 0, st>>>(P, b, env);
+      k<<<cached_grid(d, k), 128, 0, st>>>(P, b, env);
     }
+  }
+}
+#endif
+
+// Resident ray-pool blocks per launch on this device (the four instantiations share one launch
+// shape).  LP_POOL_BLOCKS (tuning knob): fewer blocks per SM than the shared-memory limit
+// leave more of the SM's 256 KB to the L1 cache (the carve-out is set to what the chosen
+// number of blocks needs).
+int pool_grid(lp_device *dev) {
+  if (dev->pool_grid) return dev->pool_grid;
+  const char *e = std::getenv("LP_POOL_BLOCKS");
+  const int want = e ? std::atoi(e) : 0;
+  int per_sm = 64;
+  for (auto kernel : {trace_pool_kernel<true, true>, trace_pool_kernel<true, false>,
+                      trace_pool_kernel<false, true>, trace_pool_kernel<false, false>}) {
+    int k_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_sm, kernel, 128, 0) != cudaSuccess ||
+        k_sm < 1)
+      k_sm = 1;
+    per_sm = std::min(per_sm, k_sm);
+  }
+  if (want > 0 && want < per_sm) {
+    per_sm = want;
+    const int pct = std::min(100, (int)((per_sm * (sizeof(PoolSmem) * kPoolWarps + 1024) * 100 +
+                                         (228 * 1024 - 1)) / (228 * 1024)));
+    for (auto kernel : {trace_pool_kernel<true, true>, trace_pool_kernel<true, false>,
+                        trace_pool_kernel<false, true>, trace_pool_kernel<false, false>})
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
+  return dev->pool_grid = per_sm * dev->sm_count;
+}
+
+// Overflow stacks of the ray-pool kernels: one region per concurrently running launch
+// (extend | connect).  Made with the path state, so a frame never allocates.
+cudaError_t allocate_pool_scratch(lp_renderer *r) {
+  const size_t need = (size_t)pool_grid(r->dev) * kPoolWarps * kPool * kPoolStack;
+  return r->pool_scratch.alloc(2 * need);
+}
+
+void launch_canonical(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, int env,
+                      bool stats, cudaStream_t st) {
+  lp_device *d = r->dev;
+  if (any) {
+    if (stats) connect_kernel<true><<<cached_grid(d, connect_kernel<true>), 128, 0, st>>>(P, b, env);
+    else connect_kernel<false><<<cached_grid(d, connect_kernel<false>), 128, 0, st>>>(P, b, env);
+  } else {
+    if (stats) extend_kernel<true><<<cached_grid(d, extend_kernel<true>), 128, 0, st>>>(P, b);
+    else extend_kernel<false><<<cached_grid(d, extend_kernel<false>), 128, 0, st>>>(P, b);
   }
 }
 
 void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, int env,
                   bool stats, cudaStream_t st) {
-  const int sm = r->dev->sm_count;
+  lp_device *d = r->dev;
   // 0 = production = 14 (hybrid); 15 = the first version (BVH2, one ray per thread)
   const uint32_t variant = r->cfg.traversal_variant == 0 ? 14u : r->cfg.traversal_variant;
+  if (stats || variant == 15) {  // STATS always keeps the canonical walk
+    launch_canonical(r, P, b, any, env, stats, st);
+    return;
+  }
   switch (variant) {
     default:
-      if (any) {
-        if (stats) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
-        else connect_kernel<false><<<cached_grid(connect_kernel<false>, sm), 128, 0, st>>>(P, b, env);
-      } else {
-        if (stats) extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
-        else extend_kernel<false><<<cached_grid(extend_kernel<false>, sm), 128, 0, st>>>(P, b);
-      }
+      launch_canonical(r, P, b, any, env, stats, st);
       break;
-    case 2: launch_persistent<16, 4, 4, 8>(r, P, b, any, env, stats); break;
-    case 3: launch_persistent<8, 4, 4, 10>(r, P, b, any, env, stats); break;
-    case 4: launch_persistent<16, 8, 8, 10>(r, P, b, any, env, stats); break;
-    case 5: launch_persistent<12, 4, 8, 10>(r, P, b, any, env, stats); break;
-    case 6: launch_persistent<8, 2, 4, 12>(r, P, b, any, env, stats); break;
-    case 7: launch_persistent<4, 2, 2, 8>(r, P, b, any, env, stats); break;
-    case 8: launch_persistent<20, 8, 4, 10>(r, P, b, any, env, stats); break;
-    case 9: launch_persistent<12, 6, 12, 10>(r, P, b, any, env, stats); break;
+#ifdef LP_VARIANTS
+    case 1: launch_persistent<8, 4, 4, 8>(r, P, b, any, env, stats, st); break;
+    case 2: launch_persistent<16, 4, 4, 8>(r, P, b, any, env, stats, st); break;
+    case 3: launch_persistent<8, 4, 4, 10>(r, P, b, any, env, stats, st); break;
+    case 4: launch_persistent<16, 8, 8, 10>(r, P, b, any, env, stats, st); break;
+    case 5: launch_persistent<12, 4, 8, 10>(r, P, b, any, env, stats, st); break;
+    case 6: launch_persistent<8, 2, 4, 12>(r, P, b, any, env, stats, st); break;
+    case 7: launch_persistent<4, 2, 2, 8>(r, P, b, any, env, stats, st); break;
+    case 8: launch_persistent<20, 8, 4, 10>(r, P, b, any, env, stats, st); break;
+    case 9: launch_persistent<12, 6, 12, 10>(r, P, b, any, env, stats, st); break;
+    case 10:  // 4-wide collapse, one ray per thread
+      if (any) connect4_kernel<false><<<cached_grid(d, connect4_kernel<false>), 128, 0, st>>>(P, b, env);
+      else extend4_kernel<false><<<cached_grid(d, extend4_kernel<false>), 128, 0, st>>>(P, b);
+      break;
+    case 13:  // ... with fp16 node boxes
+      if (any) connect4_kernel<true><<<cached_grid(d, connect4_kernel<true>), 128, 0, st>>>(P, b, env);
+      else extend4_kernel<true><<<cached_grid(d, extend4_kernel<true>), 128, 0, st>>>(P, b);
+      break;
     case 11:
     case 12:
-    case 14: {  // ray pool in shared memory (trace_pool.cuh); STATS keeps the canonical walk
-      if (stats) {
-        if (any) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
-        else extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
-        break;
-      }
+#endif
+    case 14: {  // ray pool in shared memory (trace_pool.cuh)
       // 12, 14: fp16 node boxes -- unless the scene is too far from the origin for binary16
       // (Scene::half_boxes_ok), where the same kernels run on the fp32 4-wide nodes
       const bool il = variant != 11 && r->sg->half_boxes_ok;
       if (variant == 14 && !any && b == 0) {
         // coherent primary rays: one ray per thread keeps the 8x4-tile locality in L1; the
         // camera rays are generated in the kernel (no generate_kernel, see fused_raygen)
-        if (il) extend4_kernel<true, true><<<cached_grid(extend4_kernel<true, true>, sm), 128, 0, st>>>(P, b);
-        else extend4_kernel<false, true><<<cached_grid(extend4_kernel<false, true>, sm), 128, 0, st>>>(P, b);
+        if (il) extend4_kernel<true, true><<<cached_grid(d, extend4_kernel<true, true>), 128, 0, st>>>(P, b);
+        else extend4_kernel<false, true><<<cached_grid(d, extend4_kernel<false, true>), 128, 0, st>>>(P, b);
         break;
       }
-      // LP_POOL_BLOCKS (tuning knob): resident pool blocks per SM.  Fewer blocks than the
-      // shared-memory limit leave more of the SM's 256 KB to the L1 cache (the carve-out is
-      // set to what the chosen number of blocks needs).
-      static int pool_grid = 0;  // the four instantiations share one launch shape
-      if (!pool_grid) {
-        const char *e = std::getenv("LP_POOL_BLOCKS");
-        const int want = e ? std::atoi(e) : 0;
-        int per_sm = 64;
-        for (auto kernel : {trace_pool_kernel<true, true>, trace_pool_kernel<true, false>,
-                            trace_pool_kernel<false, true>, trace_pool_kernel<false, false>}) {
-          int k_sm = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_sm, kernel, 128, 0) != cudaSuccess ||
-              k_sm < 1)
-            k_sm = 1;
-          per_sm = std::min(per_sm, k_sm);
-        }
-        if (want > 0 && want < per_sm) {
-          per_sm = want;
-          const int pct = std::min(100, (int)((per_sm * (sizeof(PoolSmem) * kPoolWarps + 1024) * 100 +
-                                               (228 * 1024 - 1)) / (228 * 1024)));
-          for (auto kernel : {trace_pool_kernel<true, true>, trace_pool_kernel<true, false>,
-                              trace_pool_kernel<false, true>, trace_pool_kernel<false, false>})
-            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        }
-        pool_grid = per_sm * sm;
-      }
-      const int g_any = pool_grid, g_closest = pool_grid;
-      // overflow stacks: one region per concurrently running launch (extend | connect)
-      const size_t need = (size_t)std::max(g_any, g_closest) * kPoolWarps * kPool * kPoolStack;
-      if (r->pool_scratch.count < 2 * need && r->pool_scratch.alloc(2 * need) != cudaSuccess) break;
-      uint32_t *scratch = r->pool_scratch.ptr + (any ? need : 0);
+      const int grid = pool_grid(d);
+      const size_t need = (size_t)grid * kPoolWarps * kPool * kPoolStack;
+      uint32_t *scratch = r->pool_scratch.ptr + (any ? need : 0);  // allocate_pool_scratch
       static const uint32_t chunk_max = [] {  // LP_POOL_CHUNK: tuning knob
         const char *e = std::getenv("LP_POOL_CHUNK");
         return e ? (uint32_t)std::max(32L, std::atol(e)) : 64u;
       }();
-      if (any && il) trace_pool_kernel<true, true><<<g_any, 128, 0, st>>>(P, b, env, scratch, chunk_max);
-      else if (any) trace_pool_kernel<true, false><<<g_any, 128, 0, st>>>(P, b, env, scratch, chunk_max);
-      else if (il) trace_pool_kernel<false, true><<<g_closest, 128, 0, st>>>(P, b, env, scratch, chunk_max);
-      else trace_pool_kernel<false, false><<<g_closest, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+      if (any && il) trace_pool_kernel<true, true><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+      else if (any) trace_pool_kernel<true, false><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+      else if (il) trace_pool_kernel<false, true><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+      else trace_pool_kernel<false, false><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
       break;
     }
-    case 10:  // 4-wide collapse, one ray per thread (STATS keeps the canonical BVH2 walk)
-    case 13:  // ... with fp16 node boxes
-      if (stats) {
-        if (any) connect_kernel<true><<<cached_grid(connect_kernel<true>, sm), 128, 0, st>>>(P, b, env);
-        else extend_kernel<true><<<cached_grid(extend_kernel<true>, sm), 128, 0, st>>>(P, b);
-      } else if (variant == 13) {
-        if (any) connect4_kernel<true><<<cached_grid(connect4_kernel<true>, sm), 128, 0, st>>>(P, b, env);
-        else extend4_kernel<true><<<cached_grid(extend4_kernel<true>, sm), 128, 0, st>>>(P, b);
-      } else if (any) {
-        connect4_kernel<false><<<cached_grid(connect4_kernel<false>, sm), 128, 0, st>>>(P, b, env);
-      } else {
-        extend4_kernel<false><<<cached_grid(extend4_kernel<false>, sm), 128, 0, st>>>(P, b);
-      }
-      break;
-    case 1: launch_persistent<8, 4, 4, 8>(r, P, b, any, env, stats); break;
   }
 }
 
@@ -543,6 +510,8 @@ cudaError_t lp::upload_shading_data(lp_scene_gpu *g, Scene &s, cudaStream_t st, 
   up(g->emission, s.emission.data(), s.emission.size() * 16);
   up(g->lights, s.lights.data(), s.lights.size() * sizeof(lp_light));
   up(g->indices, s.indices.data(), s.indices.size() * sizeof(uint32_t));
+  // room for every light: lp_scene_set_light may switch one on later (refresh_small_tables)
+  active.resize(s.lights.size(), 0u);
   up(g->active_lights, active.data(), active.size() * sizeof(uint32_t));
   up(g->atlas, s.atlas.texels.data(), s.atlas.texels.size());
   up(g->tex_blocks, s.atlas.gpu_blocks.data(), s.atlas.gpu_blocks.size() * sizeof(uint32_t));
@@ -871,6 +840,9 @@ LP_API lp_status lp_renderer_set_config(lp_renderer *r, const lp_render_config *
     return fail(LP_ERR_INVALID_ARG, "max_bounces must be in [1, 32]");
   if (cfg->spp_per_call < 1) return fail(LP_ERR_INVALID_ARG, "spp_per_call must be >= 1");
   if (!(cfg->v_fov > 0.0f && cfg->v_fov < 3.1f)) return fail(LP_ERR_INVALID_ARG, "bad v_fov");
+  if (!variant_available(cfg->traversal_variant))
+    return fail(LP_ERR_INVALID_ARG, "traversal_variant is not in this build (0, 14, 15; the "
+                                    "measured alternatives need a library built with -DLP_VARIANTS)");
   const bool realloc = cfg->spp_per_call != r->cfg.spp_per_call;
   r->cfg = *cfg;
   if (r->cfg.sample_stride == 0) r->cfg.sample_stride = 1;
@@ -878,7 +850,8 @@ LP_API lp_status lp_renderer_set_config(lp_renderer *r, const lp_render_config *
   if (realloc) {
     CUDA_CHECK(cudaSetDevice(r->dev->ordinal));
     CUDA_CHECK(cudaStreamSynchronize(r->dev->stream));
-    return allocate_targets(r);
+    CUDA_CHECK(cudaStreamSynchronize(r->dev->stream2));
+    return allocate_path_state(r);  // the accumulated image and its sample count are kept
   }
   return LP_OK;
 } LP_ABI_CATCH
@@ -965,7 +938,11 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
   // per-launch timing brackets each kernel with an event pair: keep them un-contended
   const bool overlap = overlap_env && !stats && !r->kt_enabled;
   bool connect_pending = false;
-  uint32_t remaining = cfg.spp_per_call;
+  // The SVGF modes consume ONE sample per frame, like the reference's raytrace [ref
+  // renderer.rs:392-549]: the temporal pass reads the frame's single sample, so tracing more
+  // would only be discarded (spp_per_call applies to the accumulating Pahtrace mode).
+  const bool one_sample = r->mode == LP_BLIT_DENOISED_PATHRACE || r->mode == LP_BLIT_TEMPORAL;
+  uint32_t remaining = one_sample ? 1u : cfg.spp_per_call;
   bool first_wave = true;
   while (remaining > 0) {
     const uint32_t S = std::min(remaining, r->wave_samples);
@@ -1023,6 +1000,10 @@ LP_API lp_status lp_renderer_raytrace(lp_renderer *r, const float view_transform
 
     if (r->mode == LP_BLIT_PAHTRACE) {
       if (first_wave) query_start(r, "accumulation");
+      if (r->accum_guard) {  // lp_multi: the previous batch's reduce still reads the target
+        CUDA_CHECK(cudaStreamWaitEvent(st, r->accum_guard, 0));
+        r->accum_guard = nullptr;
+      }
       { KtScope k(r, 3); accumulate_kernel<<<sm * 8, 256, 0, st>>>(P); }  // [ref renderer.rs:523-538]
       if (first_wave) query_end(r);
     }

@@ -12,6 +12,7 @@
 //   tonemap_kernel    = BlitPass into Rgba8UnormSrgb  (:756-770)
 #pragma once
 #include "frame.cuh"
+#include "tonemap.cuh"
 
 namespace lp {
 
@@ -149,24 +150,13 @@ __global__ void finalize_counts_kernel(const __grid_constant__ FrameParams P) {
   P.counters->rays[2] += s;
 }
 
-// BlitPass to Rgba8UnormSrgb: normalise by the sample count, clamp, sRGB OETF, round.
+// BlitPass to Rgba8UnormSrgb: normalise by the sample count, clamp, sRGB OETF, round
+// (tonemap.cuh: shared with the fused multi-GPU reduce of api_multi.cu).
 __global__ void __launch_bounds__(256) tonemap_kernel(const float4 *__restrict__ accum,
                                                       uchar4 *__restrict__ out, uint32_t n) {
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float4 a = accum[i];
-    const float inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
-    float c[3] = {a.x * inv, a.y * inv, a.z * inv};
-    unsigned char q[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float x = c[k];
-      x = !(x > 0.0f) ? 0.0f : (x > 1.0f ? 1.0f : x);
-      const float e = x <= 0.0031308f ? 12.92f * x : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f;
-      q[k] = (unsigned char)floorf(e * 255.0f + 0.5f);
-    }
-    out[i] = make_uchar4(q[0], q[1], q[2], 255);
-  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = tonemap_srgb8(accum[i]);
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const float4 *__restrict__ accum,

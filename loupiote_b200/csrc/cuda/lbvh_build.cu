@@ -457,10 +457,12 @@ lp_status build_tlas_on_device(lp_scene_gpu *sg, Scene &s) {
   DeviceExec ex{st, dev->sm_count};
   uint32_t n4 = 0, tlas_depth2 = 0;
   int depth4 = 0;
-  // LP_LBVH_BLOCK_TLAS=1 (opt-in until it has run on a GPU): a TLAS of <= 1024 instances is
-  // built by ONE launch of one block (BlockExec) instead of ~70 launches and 4 read-backs
+  // A TLAS of <= 1024 instances is built by ONE launch of one block (BlockExec) instead of ~70
+  // launches and 4 read-backs: update_instances 0.378 -> 0.204 ms at 51 instances, hits and
+  // arrays identical (profiles/r02_opt_in_bench.jsonl).  LP_LBVH_BLOCK_TLAS=0 restores the
+  // multi-launch build.
   const char *bt = std::getenv("LP_LBVH_BLOCK_TLAS");
-  const bool block_tlas = bt && std::atoi(bt) != 0;
+  const bool block_tlas = bt ? std::atoi(bt) != 0 : true;
   if (block_tlas && ids.size() <= kBlockJobMax && sg->tlas_capacity <= 4 * kBlockJobMax) {
     uint32_t *result = j.level_count + kMaxLevels + 3;  // 4 spare words of the counter block
     tlas_block_kernel<<<1, 1024, 0, st>>>(j, in, w.keys_tmp, w.vals_tmp, (uint4 *)sg->nodes4h.ptr,
@@ -584,9 +586,11 @@ extern "C" LP_API lp_status lp_scene_gpu_new_from_scene_lbvh(lp_scene *scene, lp
   const char *cb = std::getenv("LP_LBVH_COLLAPSE");
   j.collapse_by_area = cb ? (uint32_t)(std::atoi(cb) != 0) : 1u;
   // LP_LBVH_TREELETS=<passes> (default 0 = off): treelet restructuring of the binary trees
-  // (Karras & Aila 2013, lbvh_core.h section 4b).  Validated on the host only so far (optimal
-  // against exhaustive search, -5 % surface-area cost after two passes); off until it has run
-  // and been measured on a GPU.
+  // (Karras & Aila 2013, lbvh_core.h section 4b).  Measured on a B200, config 3
+  // (profiles/r02_opt_in_bench.jsonl): 1 / 2 passes trace 1.7 / 2.3 % faster (4668 -> 4747 ->
+  // 4775 Mrays/s; host SAH tree 4861) with bit-identical images, but the build grows from 9 to
+  // 44-52 ms.  A build-time / trace-rate trade the CALLER makes: off by default (the device
+  // build exists to reach the first frame fast), worth switching on for renders of seconds.
   const char *tp = std::getenv("LP_LBVH_TREELETS");
   j.treelet_passes = tp ? (uint32_t)std::min(8, std::max(0, std::atoi(tp))) : 0u;
   j.treelet_gamma = 7;

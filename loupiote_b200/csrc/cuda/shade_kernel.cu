@@ -408,10 +408,11 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
   }
 }
 
+// Resident shade blocks per SM (the same for every sm_100 device, so it is computed once per
+// instantiation; a C++11 magic static: safe when lp_multi's device threads race to it).
 template <typename K>
 int shade_grid(K kernel, int sm_count) {
-  static int grid = 0;  // one per instantiation
-  if (!grid) {
+  static const int per_sm_cached = [kernel] {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * kShadeWarps, 0) !=
             cudaSuccess ||
@@ -422,9 +423,9 @@ int shade_grid(K kernel, int sm_count) {
       const int want = std::atoi(e);
       if (want > 0 && want < per_sm) per_sm = want;
     }
-    grid = per_sm * sm_count;
-  }
-  return grid;
+    return per_sm;
+  }();
+  return per_sm_cached * sm_count;
 }
 
 }  // namespace

@@ -33,7 +33,13 @@ struct lp_scene {
 extern "C" {
 
 LP_API const char *lp_last_error(void) { return g_last_error.c_str(); }
-LP_API const char *lp_version(void) { return "loupiote-b200 0.1.0 (sm_100a)"; }
+LP_API const char *lp_version(void) {
+#ifdef LP_VARIANTS
+  return "loupiote-b200 0.2.0 (sm_100a) +variants";
+#else
+  return "loupiote-b200 0.2.0 (sm_100a)";
+#endif
+}
 
 LP_API lp_status lp_scene_create(lp_scene **out) {
   if (!out) return fail(LP_ERR_INVALID_ARG, "lp_scene_create: out is NULL");
@@ -104,8 +110,25 @@ LP_API lp_status lp_scene_set_material_emission(lp_scene *scene, uint32_t materi
   if (!scene || !rgb) return fail(LP_ERR_INVALID_ARG, "NULL argument");
   if (material_index >= scene->s.emission.size())
     return fail(LP_ERR_INVALID_ARG, "unknown material index");
+  // a small-table edit: no re-layout, no new layout_version, so lp_scene_gpu_update_instances
+  // refreshes it on an existing SceneGPU (host-built or device-built)
   scene->s.emission[material_index] = {rgb[0], rgb[1], rgb[2], 0.f};
-  scene->s.derived_dirty = true;
+  return LP_OK;
+}
+
+LP_API lp_status lp_scene_set_material(lp_scene *scene, uint32_t material_index,
+                                       const lp_material *material) {
+  if (!scene || !material) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (material_index >= scene->s.materials.size())
+    return fail(LP_ERR_INVALID_ARG, "unknown material index");
+  scene->s.materials[material_index] = *material;  // small-table edit, see above
+  return LP_OK;
+}
+
+LP_API lp_status lp_scene_set_light(lp_scene *scene, uint32_t light_index, const lp_light *light) {
+  if (!scene || !light) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  if (light_index >= scene->s.lights.size()) return fail(LP_ERR_INVALID_ARG, "unknown light index");
+  scene->s.lights[light_index] = *light;  // small-table edit, see above
   return LP_OK;
 }
 
@@ -118,6 +141,10 @@ LP_API lp_status lp_scene_push_light(lp_scene *scene, const lp_light *light, uin
 LP_API lp_status lp_scene_push_image(lp_scene *scene, const uint8_t *rgba8, uint32_t width,
                                      uint32_t height, uint32_t *out_index) {
   if (!scene || !rgba8) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  // the atlas layer limit: refused HERE, not when the atlas is built (an image that cannot be
+  // packed would make every later SceneGPU fail and there is no call that removes an image)
+  if (width < 1 || height < 1 || width > 16384u || height > 16384u)
+    return fail(LP_ERR_INVALID_ARG, "image dimensions must be in [1, 16384]");
   LP_TRY(Image img; img.width = width; img.height = height;
          img.data.assign(rgba8, rgba8 + (size_t)width * height * 4);
          scene->s.images.push_back(std::move(img)); scene->s.derived_dirty = true;

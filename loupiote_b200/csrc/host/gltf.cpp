@@ -420,6 +420,8 @@ lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string 
     return LP_ERR_FILE_NOT_FOUND;  // every import error maps to FileNotFound [ref gltf.rs:49-55]
   }
 
+  // everything below only appends to the scene: a failure half way rolls it all back
+  const Scene::Mark mark = scene.mark();
   try {
     // ---- meshes: one BLAS entry per primitive that has POSITION and a triangle mode
     const uint32_t bvh_offset = (uint32_t)scene.entries.size();
@@ -570,7 +572,9 @@ lp_status load_gltf(const uint8_t *data, size_t size, Scene &scene, std::string 
       }
     }
     build_scope.finish();
+    scene.derived_dirty = true;  // images / materials were pushed straight onto the arrays
   } catch (const std::exception &e) {
+    scene.rollback(mark);
     err = e.what();
     return LP_ERR_ACCEL_BUILD;
   }
@@ -629,6 +633,7 @@ lp_status load_binary(const char *path, Scene &scene, std::string &err) {
     for (int v = 0; v < 3; ++v)
       for (int k = 0; k < 3; ++k) nrm[3 * (i + v) + k] = n[k];
   }
+  const Scene::Mark mark = scene.mark();
   try {
     const uint32_t blas = scene.add_bvh(raw.data(), 16, nrm.data(), 12, nullptr, 0, vcount, nullptr, 0);
     const uint32_t material_index = (uint32_t)scene.materials.size();
@@ -642,7 +647,9 @@ lp_status load_binary(const char *path, Scene &scene, std::string &err) {
     m.mra_texture = LP_INVALID_INDEX;
     scene.materials.push_back(m);
     scene.emission.push_back({0.f, 0.f, 0.f, 0.f});
+    scene.derived_dirty = true;
   } catch (const std::exception &e) {
+    scene.rollback(mark);
     err = e.what();
     return LP_ERR_ACCEL_BUILD;
   }

@@ -202,6 +202,23 @@ void Scene::add_instance(uint32_t blas, const float m[16], uint32_t material) {
   derived_dirty = true;
 }
 
+void Scene::rollback(const Mark &m) {
+  materials.resize(m.materials);
+  emission.resize(m.materials);
+  entries.resize(m.entries);
+  nodes.resize(m.nodes);
+  primitives.resize(m.primitives);
+  vertices.resize(m.vertices);
+  indices.resize(m.indices);
+  instances.resize(m.instances);
+  lights.resize(m.lights);
+  images.resize(m.images);
+  pending_bvh.erase(std::remove_if(pending_bvh.begin(), pending_bvh.end(),
+                                   [&](uint32_t e) { return e >= m.entries; }),
+                    pending_bvh.end());
+  derived_dirty = true;
+}
+
 void Scene::set_instance_transform(uint32_t i, const float m[16]) {
   require_finite(m);
   std::memcpy(instances[i].model_to_world, m, 64);

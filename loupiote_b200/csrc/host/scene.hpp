@@ -134,6 +134,17 @@ struct Scene {
   void build_derived();  // TLAS + GPU layout (full, or TLAS-only after set_instance_transform)
   void ensure_host_bvh();  // builds the trees add_bvh deferred (all host cores, one per tree)
   void build_tlas();
+
+  // Loaders only append: a Mark remembers every array's length so that a load that fails half
+  // way (a NaN vertex, an allocation failure) leaves the scene exactly as it found it.
+  struct Mark {
+    size_t materials, entries, nodes, primitives, vertices, indices, instances, lights, images;
+  };
+  Mark mark() const {
+    return {materials.size(), entries.size(), nodes.size(), primitives.size(), vertices.size(),
+            indices.size(), instances.size(), lights.size(), images.size()};
+  }
+  void rollback(const Mark &m);
 };
 
 // The loaders add many meshes in a row: while one of these is alive add_bvh defers its tree,

@@ -521,3 +521,68 @@ def test_binary_loader_checks_the_count_against_the_file(tmp_path):
     s = lb.Scene()
     lb.loaders.load_binary_from_path(ok, s)
     assert s.array(_ffi.SCENE_ENTRIES)["primitive_count"][-1] == 2
+
+
+def _scene_sizes(s):
+    kinds = (_ffi.SCENE_ENTRIES, _ffi.SCENE_NODES, _ffi.SCENE_PRIMITIVES, _ffi.SCENE_VERTICES,
+             _ffi.SCENE_INSTANCES, _ffi.SCENE_MATERIALS, _ffi.SCENE_LIGHTS, _ffi.SCENE_INDICES,
+             _ffi.SCENE_EMISSION)
+    return [len(s.array(k)) for k in kinds] + [s.image_count]
+
+
+def test_failed_load_leaves_the_scene_untouched():
+    """A load that fails half way (here: a node whose translation overflows float, found after
+    the meshes and materials were pushed) rolls everything back: the scene can still be used
+    and holds exactly what it held before."""
+    import copy
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    from fuzz_ingest import join_glb, split_glb
+    doc, blob = split_glb(GLB.read_bytes())
+    bad = copy.deepcopy(doc)
+    bad["nodes"][-1]["translation"] = [1e39, 0.0, 0.0]
+    s = lb.Scene()
+    lb.loaders.load_gltf(GLB.read_bytes(), s)          # a good load first
+    before = _scene_sizes(s)
+    nodes_before = s.array(_ffi.SCENE_NODES).copy()
+    with pytest.raises(lb.Error) as e:
+        lb.loaders.load_gltf(join_glb(bad, blob), s)
+    assert e.value.code == lb.Error.AccelBuild
+    assert _scene_sizes(s) == before
+    assert np.array_equal(s.array(_ffi.SCENE_NODES), nodes_before)
+    s.array(_ffi.SCENE_GPU_NODES4H)                    # derived data still builds
+    lb.loaders.load_gltf(GLB.read_bytes(), s)          # and the scene still loads
+    assert _scene_sizes(s)[2] == before[2] + 34
+
+
+def test_small_table_edits_do_not_relayout():
+    """Emission / material / light edits of EXISTING entries are small-table edits: the GPU
+    node arrays (and so a SceneGPU's layout version) stay as they are; pushing an entry is not."""
+    c = scenes.spheres_1m(grid=2, subdivisions=1)
+    s = c["scene"]
+    nodes = s.array(_ffi.SCENE_GPU_NODES4H).copy()
+    s.set_material_emission(2, (3.0, 2.0, 1.0))
+    s.set_material(1, color=(0.2, 0.3, 0.4, 1.0), roughness=0.25, reflectivity=1.0)
+    s.set_light(0, (0, 5, 0), (1, 0, 0), (0, 0, 1), 4.0)
+    assert np.array_equal(s.array(_ffi.SCENE_GPU_NODES4H), nodes)
+    assert np.allclose(s.emission[2][:3], (3.0, 2.0, 1.0))
+    assert np.isclose(s.materials[1]["roughness"], 0.25) and s.materials[1]["reflectivity"] == 1.0
+    assert s.lights[0]["intensity"] == 4.0
+    for call in (lambda: s.set_material(99, color=(1, 1, 1, 1)),
+                 lambda: s.set_light(7, (0, 0, 0), (1, 0, 0), (0, 0, 1), 1.0),
+                 lambda: s.set_material_emission(99, (1, 1, 1))):
+        with pytest.raises(lb.Error) as e:
+            call()
+        assert e.value.code == lb.Error.InvalidArg
+
+
+def test_push_image_rejects_impossible_dimensions():
+    """Dimensions outside [1, 16384] are refused when the image is pushed: an image the atlas
+    cannot hold would make every later SceneGPU fail and no call removes an image."""
+    s = lb.Scene()
+    px = np.zeros(16, np.uint8)
+    for w, h in ((0, 4), (4, 0), (16385, 1), (1, 16385)):
+        st = _ffi.lib().lp_scene_push_image(s._h, px.ctypes.data, w, h, None)
+        assert st == _ffi.LP_ERR_INVALID_ARG
+    assert s.image_count == 0
+    assert s.push_image(np.zeros((2, 2, 4), np.uint8)) == 0

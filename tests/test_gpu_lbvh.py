@@ -38,8 +38,10 @@ def first_hit_equals_oracle(device, scene, view, size):
     cam = O.camera_from_view(view, w, h, V_FOV)
     oi, op, ot, _, _ = O.first_hit_image(osc, cam, 1)
     r, sg = renderer_for(device, scene, size, "lbvh", max_bounces=1, spp_per_call=1, jitter=0)
-    # production kernels (4-wide fp16 / fp32 nodes), the canonical 2-wide walk, 4-wide fp32
-    for variant in (0, 15, 10):
+    # production kernels (4-wide fp16 / fp32 nodes), the canonical 2-wide walk and -- in a
+    # library built with -DLP_VARIANTS -- the one-ray-per-thread walk over the 4-wide fp32 nodes
+    variants = (0, 15, 10) if b"+variants" in _ffi.lib().lp_version() else (0, 15)
+    for variant in variants:
         r.set_config(traversal_variant=variant)
         r.raytrace(view)
         inst, prim, t = r.read_first_hit()
@@ -56,6 +58,24 @@ def test_lbvh_first_hit_cornell(device):
 def test_lbvh_first_hit_soup_instances(device):
     scene, view = soup_scene()
     first_hit_equals_oracle(device, scene, view, (192, 128))
+
+
+def test_lbvh_first_hit_far_from_origin_uses_fp32_nodes(device):
+    """A device-built scene 1e5 units from the origin: binary16 boxes cannot resolve it, the
+    production kernels traverse the device-built fp32 4-wide nodes."""
+    far = lb.Scene()
+    rng = np.random.default_rng(2)
+    c = rng.uniform(-1, 1, size=(1500, 1, 3))
+    pos = (c + rng.normal(scale=0.08, size=(1500, 3, 3))).reshape(-1, 3).astype(np.float32)
+    b = far.blas.add_bvh(pos)
+    mat = far.push_material(color=(0.7, 0.6, 0.5, 1.0), roughness=0.8)
+    for k in range(4):
+        m = np.eye(4, dtype=np.float32)
+        m[:3, 3] = (1.0e5 + 2.5 * k, -2.0e4, 3.0e4 + k)
+        far.blas.add_instance(b, m, mat)
+    assert not far.fp16_node_boxes
+    view = lb.look_at_view((1.0e5 + 3.5, -2.0e4 + 0.3, 3.0e4 + 12.0), (0.0, 0.0, -1.0))
+    first_hit_equals_oracle(device, far, view, (200, 120))
 
 
 def test_lbvh_first_hit_spheres(device):
@@ -191,9 +211,6 @@ def test_lbvh_device_arrays_are_valid_trees(device):
         assert sorted(seen) == want
 
 
-@pytest.mark.skipif(os.environ.get("LP_TEST_LBVH_TREELETS", "0") != "1",
-                    reason="treelet restructuring is opt-in and not yet confirmed on hardware: "
-                           "set LP_TEST_LBVH_TREELETS=1")
 def test_lbvh_treelet_restructuring_keeps_hits_and_arrays_valid(device, monkeypatch):
     """LP_LBVH_TREELETS=2: the restructured trees give the oracle's hits and pass the
     structural check (every triangle once, exact boxes)."""
@@ -206,13 +223,12 @@ def test_lbvh_treelet_restructuring_keeps_hits_and_arrays_valid(device, monkeypa
     test_lbvh_path_traced_image_is_bit_identical_to_host_built_tree(device)
 
 
-@pytest.mark.skipif(os.environ.get("LP_TEST_LBVH_BLOCK_TLAS", "0") != "1",
-                    reason="the one-block TLAS build is opt-in and not yet confirmed on "
-                           "hardware: set LP_TEST_LBVH_BLOCK_TLAS=1")
-def test_lbvh_one_block_tlas_build(device, monkeypatch):
-    """LP_LBVH_BLOCK_TLAS=1: the TLAS built by one launch of one block (the same build sequence
-    under BlockExec) gives the oracle's hits, valid arrays, and survives instance updates."""
-    monkeypatch.setenv("LP_LBVH_BLOCK_TLAS", "1")
+def test_lbvh_multi_launch_tlas_build(device, monkeypatch):
+    """The default TLAS build is ONE launch of one block (the build sequence under BlockExec;
+    every other test of this file runs it).  LP_LBVH_BLOCK_TLAS=0 selects the multi-launch
+    build, which TLASes of more than 1024 instances use: same hits, valid arrays, survives
+    instance updates."""
+    monkeypatch.setenv("LP_LBVH_BLOCK_TLAS", "0")
     c = scenes.spheres_1m(grid=3, subdivisions=3)
     first_hit_equals_oracle(device, c["scene"], c["view"], (256, 144))
     scene, view = soup_scene()

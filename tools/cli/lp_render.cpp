@@ -10,9 +10,12 @@
 //   lp_render --glb scene.glb [--out image.ppm] [--size 960x540] [--spp 64] [--bounces 4]
 //             [--eye x,y,z] [--dir x,y,z] [--fov degrees] [--env r,g,b]
 //             [--light cx,cy,cz,tx,ty,tz,bx,by,bz,intensity] [--denoise] [--seed n]
-//             [--checkpoint file] [--resume file] [--device-build]
+//             [--checkpoint file] [--resume file] [--device-build] [--gpus N]
 //   --device-build: every BLAS and the TLAS are built on the GPU (LBVH) and the loader skips
 //   the host BVH build; the image is the same, bit for bit
+//   --gpus N: the samples are split over N GPUs of this box (lp_multi_*: replicated scene,
+//   interleaved sample indices, accumulators summed to GPU 0 over NVLink); the image is the
+//   1-GPU image up to FP32 summation order
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -61,6 +64,79 @@ void look_at_view(const float eye[3], const float dir_in[3], float m[16]) {
   std::memcpy(m, cols, sizeof(cols));
 }
 
+int write_ppm(const std::string &out, const std::vector<uint8_t> &px, uint32_t w, uint32_t h) {
+  FILE *f = std::fopen(out.c_str(), "wb");
+  if (!f) {
+    std::fprintf(stderr, "cannot write %s\n", out.c_str());
+    return 1;
+  }
+  std::fprintf(f, "P6\n%u %u\n255\n", w, h);
+  for (size_t i = 0; i < (size_t)w * h; ++i) std::fwrite(&px[4 * i], 1, 3, f);
+  std::fclose(f);
+  return 0;
+}
+
+// --gpus N: the same frame through lp_multi_* (one process drives the N GPUs).  Every GPU
+// accumulates its share of every batch locally; ONE exchange step at the end.
+int render_multi(const std::string &glb, const std::string &out, const std::string &checkpoint,
+                 const std::vector<lp_light> &lights, uint32_t w, uint32_t h, uint32_t spp,
+                 uint32_t bounces, uint32_t seed, float fov, const float env[3],
+                 const float eye[3], const float dir[3], bool device_build, uint32_t gpus) {
+  lp_multi *m = nullptr;
+  CHECK(lp_multi_create(nullptr, (int)gpus, &m));
+  lp_scene *scene = nullptr;
+  CHECK(lp_scene_create(&scene));
+  if (device_build) CHECK(lp_scene_set_deferred_build(scene, 1));
+  CHECK(lp_load_gltf_path(glb.c_str(), scene));
+  for (const lp_light &l : lights) CHECK(lp_scene_push_light(scene, &l, nullptr));
+  CHECK(lp_multi_set_scene(m, scene, device_build ? 1 : 0));
+  CHECK(lp_multi_resize(m, w, h, 1.0f));
+  lp_render_config cfg;
+  lp_render_config_default(&cfg);
+  cfg.max_bounces = bounces;
+  cfg.seed = seed;
+  cfg.v_fov = fov * 3.14159265358979f / 180.f;
+  std::memcpy(cfg.env_color, env, 12);
+  float view[16];
+  look_at_view(eye, dir, view);
+  // batches of 16 spp PER GPU (a multiple of N keeps the union of the ranks' samples contiguous)
+  uint32_t done = 0;
+  while (done < spp) {
+    const uint32_t batch = spp - done < 16 * gpus ? spp - done : 16 * gpus;
+    cfg.spp_per_call = batch;
+    cfg.sample_offset = done;
+    CHECK(lp_multi_set_config(m, &cfg));
+    CHECK(lp_multi_set_accumulate(m, 1));
+    CHECK(lp_multi_render(m, view));
+    done += batch;
+  }
+  CHECK(lp_multi_reduce(m));
+  std::vector<uint8_t> px((size_t)w * h * 4);
+  CHECK(lp_multi_read_pixels(m, px.data(), px.size()));
+  if (!checkpoint.empty()) {
+    std::vector<float> acc((size_t)w * h * 4);
+    CHECK(lp_multi_read_accum_sum(m, acc.data(), acc.size()));
+    FILE *f = std::fopen(checkpoint.c_str(), "wb");
+    if (!f) return 1;
+    const uint32_t hdr[3] = {w, h, spp};
+    std::fwrite(hdr, 4, 3, f);
+    std::fwrite(acc.data(), 4, acc.size(), f);
+    std::fclose(f);
+  }
+  if (write_ppm(out, px, w, h)) return 1;
+  lp_ray_counters c{};
+  CHECK(lp_multi_ray_counters(m, &c, 0));
+  double reduce_ms = 0.0;
+  CHECK(lp_multi_reduce_time(m, &reduce_ms, nullptr, 0));
+  std::printf("{\"image\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %u, \"rays\": %llu, "
+              "\"gpus\": %u, \"reduce_ms\": %.4f}\n",
+              out.c_str(), w, h, spp, (unsigned long long)(c.primary + c.bounce + c.shadow), gpus,
+              reduce_ms);
+  lp_multi_destroy(m);
+  lp_scene_destroy(scene);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -68,7 +144,7 @@ int main(int argc, char **argv) {
   float size[2] = {960, 540}, eye[3] = {0.f, 0.6f, 11.5f}, dir[3] = {0.f, 0.f, -1.f};
   float env[3] = {0.f, 0.f, 0.f}, fov = 45.f;
   std::vector<lp_light> lights;
-  uint32_t spp = 64, bounces = 4, seed = 0;
+  uint32_t spp = 64, bounces = 4, seed = 0, gpus = 1;
   bool denoise = false, device_build = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -88,6 +164,7 @@ int main(int argc, char **argv) {
     else if (a == "--spp") spp = (uint32_t)std::atoi(need());
     else if (a == "--bounces") bounces = (uint32_t)std::atoi(need());
     else if (a == "--seed") seed = (uint32_t)std::atoi(need());
+    else if (a == "--gpus") gpus = (uint32_t)std::atoi(need());
     else if (a == "--eye") ok = parse_floats(need(), eye, 3);
     else if (a == "--dir") ok = parse_floats(need(), dir, 3);
     else if (a == "--fov") ok = parse_floats(need(), &fov, 1);
@@ -120,6 +197,15 @@ int main(int argc, char **argv) {
     return 2;
   }
   const uint32_t w = (uint32_t)size[0], h = (uint32_t)size[1];
+  if (gpus > 1) {
+    if (denoise || !resume.empty()) {
+      std::fprintf(stderr, "--gpus N splits the samples of an accumulated frame: not with "
+                           "--denoise (per-image history, replicas only) or --resume\n");
+      return 2;
+    }
+    return render_multi(glb, out, checkpoint, lights, w, h, spp, bounces, seed, fov, env, eye,
+                        dir, device_build, gpus);
+  }
 
   lp_device *dev = nullptr;
   CHECK(lp_device_create(0, &dev));
@@ -195,14 +281,7 @@ int main(int argc, char **argv) {
     std::fwrite(acc.data(), 4, acc.size(), f);
     std::fclose(f);
   }
-  FILE *f = std::fopen(out.c_str(), "wb");
-  if (!f) {
-    std::fprintf(stderr, "cannot write %s\n", out.c_str());
-    return 1;
-  }
-  std::fprintf(f, "P6\n%u %u\n255\n", w, h);
-  for (size_t i = 0; i < (size_t)w * h; ++i) std::fwrite(&px[4 * i], 1, 3, f);
-  std::fclose(f);
+  if (write_ppm(out, px, w, h)) return 1;
 
   lp_ray_counters c{};
   CHECK(lp_renderer_ray_counters(r, &c, 0));
