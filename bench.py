@@ -366,7 +366,9 @@ def run_ours(args) -> None:
     if rank == 0:
         sampler.start()
     ms = timed_steps(args.steps)
-    launches = sum(v[1] for v in r.kernel_times(reset=True).values())
+    # this repository's kernels launched in the timed region on this rank: the renderer's own
+    # count + the tone map behind every reduce on rank 0 (NCCL's kernels are not counted)
+    launches = sum(v[1] for v in r.kernel_times(reset=True).values()) + args.steps
     rays = total_rays()
 
     # ---- per-kernel durations: the same K steps again with an event pair around every launch.

@@ -504,19 +504,31 @@ static inline float ulpf(float x) {
 
 void lpo_first_hit_image(const lpo_scene *s, const lp_camera *cam, int mode, uint32_t *instance,
                          uint32_t *primitive, float *t, uint8_t *tie, lpo_stats *stats) {
+  lpo_first_hit_image_step(s, cam, mode, 1, instance, primitive, t, tie, stats);
+}
+
+/* Every pixel_step-th pixel (flattened index 0, step, 2 step, ...): what makes the brute-force
+ * comparison affordable on the 1M-triangle benchmark scene.  Output arrays are full-image
+ * sized; pixels that are not sampled are left untouched. */
+void lpo_first_hit_image_step(const lpo_scene *s, const lp_camera *cam, int mode,
+                              uint32_t pixel_step, uint32_t *instance, uint32_t *primitive,
+                              float *t, uint8_t *tie, lpo_stats *stats) {
   const uint32_t w = cam->width, h = cam->height;
+  if (pixel_step == 0) pixel_step = 1;
+  const long n_sampled = ((long)w * h + pixel_step - 1) / pixel_step;
   lpo_stats total = {0, 0, 0, 0};
 #pragma omp parallel
   {
     lpo_stats local = {0, 0, 0, 0};
-#pragma omp for schedule(dynamic, 64)
-    for (long i = 0; i < (long)w * h; ++i) {
+#pragma omp for schedule(dynamic, 16)
+    for (long k = 0; k < n_sampled; ++k) {
+      const long i = k * (long)pixel_step;
       const uint32_t px = (uint32_t)(i % w), py = (uint32_t)(i / w);
       float o[3], d[3];
       lpo_camera_ray(cam, px, py, 0.5f, 0.5f, o, d);
       lpo_hit hit;
       if (mode == 0) {
-        lpo_closest_hit_brute(s, o, d, 0.0f, INFINITY, &hit);
+        lpo_closest_hit_brute(s, o, d, 0.0f, INFINITY, &hit); /* triangles AND area lights */
         if (tie) {
           lpo_hit two[2];
           lpo_two_nearest_brute(s, o, d, 0.0f, INFINITY, two);

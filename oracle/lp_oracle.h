@@ -112,6 +112,10 @@ void lpo_world_to_screen(const lp_camera *cam, const float view[16], float znear
  * tie (optional, mode 0 only): 1 where the pixel is in the tie set of SURVEY 8(d). */
 void lpo_first_hit_image(const lpo_scene *s, const lp_camera *cam, int mode, uint32_t *instance,
                          uint32_t *primitive, float *t, uint8_t *tie, lpo_stats *stats);
+/* the same on every pixel_step-th pixel (flattened index); unsampled pixels are left untouched */
+void lpo_first_hit_image_step(const lpo_scene *s, const lp_camera *cam, int mode,
+                              uint32_t pixel_step, uint32_t *instance, uint32_t *primitive,
+                              float *t, uint8_t *tie, lpo_stats *stats);
 
 /* RNG: pcg4d hash of (pixel, sample, dimension block, seed) -> 4 x u32 */
 void lpo_rng(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t seed, uint32_t out[4]);

@@ -205,18 +205,22 @@ def world_to_screen(cam, view, znear=0.01, zfar=100.0):
     return out
 
 
-def first_hit_image(oscene: OracleScene, cam, mode: int, want_tie: bool = False):
-    """mode 0 = brute force, 1 = canonical BVH. Returns inst, prim, t, tie, stats."""
+def first_hit_image(oscene: OracleScene, cam, mode: int, want_tie: bool = False,
+                    pixel_step: int = 1):
+    """mode 0 = brute force, 1 = canonical BVH. Returns inst, prim, t, tie, stats.  With
+    pixel_step > 1 only every pixel_step-th pixel (flattened index) is traced; the others
+    read LP_INVALID_INDEX / 0 (use `np.arange(w * h) % pixel_step == 0` as the mask)."""
     w, h = cam.width, cam.height
-    inst = np.empty((h, w), dtype=np.uint32)
-    prim = np.empty((h, w), dtype=np.uint32)
-    t = np.empty((h, w), dtype=np.float32)
+    inst = np.full((h, w), 0xFFFFFFFF, dtype=np.uint32)
+    prim = np.full((h, w), 0xFFFFFFFF, dtype=np.uint32)
+    t = np.zeros((h, w), dtype=np.float32)
     tie = np.zeros((h, w), dtype=np.uint8) if want_tie else None
     st = LpoStats()
-    lib().lpo_first_hit_image(C.byref(oscene.c), C.byref(cam), C.c_int(mode),
-                              C.c_void_p(inst.ctypes.data), C.c_void_p(prim.ctypes.data),
-                              C.c_void_p(t.ctypes.data),
-                              C.c_void_p(tie.ctypes.data) if want_tie else None, C.byref(st))
+    lib().lpo_first_hit_image_step(C.byref(oscene.c), C.byref(cam), C.c_int(mode),
+                                   C.c_uint32(pixel_step),
+                                   C.c_void_p(inst.ctypes.data), C.c_void_p(prim.ctypes.data),
+                                   C.c_void_p(t.ctypes.data),
+                                   C.c_void_p(tie.ctypes.data) if want_tie else None, C.byref(st))
     return inst, prim, t, tie, {"n_int": st.n_int, "n_tri": st.n_tri, "n_inst": st.n_inst,
                                 "n_rays": st.n_rays}
 

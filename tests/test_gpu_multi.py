@@ -185,3 +185,21 @@ def test_two_processes_one_gpu_each(device, tmp_path):
     res = np.load(tmp_path / "out.npz")
     assert_same_frame((res["accum"], res["pixels"], res["counters"].tolist()), want, 6,
                       batches=2)
+
+
+@needs_two
+def test_cli_gpus_two_writes_the_one_gpu_image(device, tmp_path):
+    """lp_render --gpus 2 (the C++ host over lp_multi_*): same image as --gpus 1 up to FP32
+    summation order, every pixel holds all samples."""
+    from test_gpu_cli import read_checkpoint, read_ppm, run_cli
+    a, b, cka, ckb = tmp_path / "a.ppm", tmp_path / "b.ppm", tmp_path / "a.bin", tmp_path / "b.bin"
+    ia = run_cli("--size", "128x96", "--spp", 40, "--bounces", 4, "--seed", 2, "--out", a,
+                 "--checkpoint", cka)
+    ib = run_cli("--size", "128x96", "--spp", 40, "--bounces", 4, "--seed", 2, "--out", b,
+                 "--checkpoint", ckb, "--gpus", 2)
+    assert ia["rays"] == ib["rays"] > 0 and ib["gpus"] == 2 and ib["reduce_ms"] > 0
+    acc_a, na = read_checkpoint(cka)
+    acc_b, nb = read_checkpoint(ckb)
+    assert na == nb == 40 and np.all(acc_b[..., 3] == 40.0)
+    np.testing.assert_allclose(acc_b, acc_a, rtol=1e-5, atol=1e-5)
+    assert np.abs(read_ppm(a).astype(int) - read_ppm(b).astype(int)).max() <= 1
