@@ -90,25 +90,28 @@ lp_status allocate_targets(lp_renderer *r) {
   if (ps != LP_OK) return ps;
   const uint32_t w = r->width, h = r->height;
   const size_t P = (size_t)w * h;
-  CUDA_CHECK(r->accum.alloc(P));
+  // images the a-trous kernels read carry kSvgfPadRows zeroed rows behind the last one (svgf.cuh)
+  const size_t Ppad = P + (size_t)w * kSvgfPadRows;
+  CUDA_CHECK(r->accum.alloc(Ppad));
   CUDA_CHECK(r->scratch.alloc(P));
   CUDA_CHECK(r->ldr.alloc(P));
   CUDA_CHECK(r->fh_inst.alloc(P));
   CUDA_CHECK(r->fh_prim.alloc(P));
   CUDA_CHECK(r->fh_t.alloc(P));
   for (int k = 0; k < 2; ++k) {
-    CUDA_CHECK(r->pp[k].radiance.alloc(P));
-    CUDA_CHECK(r->pp[k].gbuffer.alloc(P));
+    CUDA_CHECK(r->pp[k].radiance.alloc(Ppad));
+    CUDA_CHECK(r->pp[k].gbuffer.alloc(Ppad));
     CUDA_CHECK(r->pp[k].moments.alloc(P));
     CUDA_CHECK(r->pp[k].history.alloc(P));
-    CUDA_CHECK(cudaMemsetAsync(r->pp[k].radiance.ptr, 0, P * sizeof(float4), r->dev->stream));
-    CUDA_CHECK(cudaMemsetAsync(r->pp[k].gbuffer.ptr, 0xFF, P * sizeof(uint4), r->dev->stream));
+    CUDA_CHECK(cudaMemsetAsync(r->pp[k].radiance.ptr, 0, Ppad * sizeof(float4), r->dev->stream));
+    CUDA_CHECK(cudaMemsetAsync(r->pp[k].gbuffer.ptr, 0xFF, Ppad * sizeof(uint4), r->dev->stream));
     CUDA_CHECK(cudaMemsetAsync(r->pp[k].moments.ptr, 0, P * sizeof(float2), r->dev->stream));
     CUDA_CHECK(cudaMemsetAsync(r->pp[k].history.ptr, 0, P * sizeof(float), r->dev->stream));
   }
   CUDA_CHECK(r->motion.alloc(P));
-  CUDA_CHECK(r->temp.alloc(P));
-  CUDA_CHECK(cudaMemsetAsync(r->accum.ptr, 0, P * sizeof(float4), r->dev->stream));
+  CUDA_CHECK(r->temp.alloc(Ppad));
+  CUDA_CHECK(cudaMemsetAsync(r->temp.ptr, 0, Ppad * sizeof(float4), r->dev->stream));
+  CUDA_CHECK(cudaMemsetAsync(r->accum.ptr, 0, Ppad * sizeof(float4), r->dev->stream));
   CUDA_CHECK(cudaMemsetAsync(r->fh_inst.ptr, 0xFF, P * sizeof(uint32_t), r->dev->stream));
   CUDA_CHECK(cudaMemsetAsync(r->fh_prim.ptr, 0xFF, P * sizeof(uint32_t), r->dev->stream));
   CUDA_CHECK(cudaMemsetAsync(r->fh_t.ptr, 0, P * sizeof(float), r->dev->stream));

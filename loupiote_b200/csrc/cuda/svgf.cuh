@@ -12,6 +12,10 @@
 namespace lp {
 
 constexpr float kSvgfMaxHistory = 32.0f;
+// Rows of padding behind every image the a-trous kernels read (radiance targets, G-buffers):
+// the TMA kernel addresses row y as (y % s, y / s) of a 4-D view whose last row of q may reach
+// up to s - 1 <= 15 rows past the image.  Zeroed at allocation, never written.
+constexpr uint32_t kSvgfPadRows = 16;
 
 struct SvgfTemporalParams {
   uint32_t w, h, tiles_x;
