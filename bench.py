@@ -480,6 +480,8 @@ def run_ours(args) -> None:
             "scene_bytes": 0,
             "spp_per_s": world * spp * args.steps / (ms * 1e-3),
             "rays_per_step": rays / args.steps,
+            "rays_by_kind": {k: v / max(sum(stats["rays"]), 1) * rays / args.steps
+                             for k, v in zip(("primary", "bounce", "shadow"), stats["rays"])},
             "roofline_fraction_of_path": value / (world * roof_mrays),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],

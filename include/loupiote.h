@@ -220,6 +220,15 @@ LP_API lp_status lp_scene_add_instance(lp_scene *scene, uint32_t blas_index,
 /* Instance::set_transform [ref standalone/src/lib.rs:118-121]. */
 LP_API lp_status lp_scene_set_instance_transform(lp_scene *scene, uint32_t instance_index,
                                                  const float model_to_world[16]);
+/* Extension (refit): new positions (and normals, or NULL) for the vertices of
+ * an existing BLAS -- a deforming mesh.  vertex_count must equal the BLAS's; indices, triangle
+ * count and the canonical tree's TOPOLOGY are kept, its boxes are refitted bottom-up (no SAH
+ * build: the reference would call BLASArray::add_bvh again [ref gltf.rs:97-105]).  Hits are those
+ * of a fresh build; lp_scene_gpu_refit carries the change to an existing SceneGPU. */
+LP_API lp_status lp_scene_update_bvh_vertices(lp_scene *scene, uint32_t blas_index,
+                                              const void *positions, size_t position_stride,
+                                              const void *normals, size_t normal_stride,
+                                              size_t vertex_count);
 /* scene.materials.push(..) [ref binary.rs:63-69]; returns the new index. */
 LP_API lp_status lp_scene_push_material(lp_scene *scene, const lp_material *material,
                                         uint32_t *out_index);
@@ -306,6 +315,13 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
  * LP_ERR_INVALID_ARG when geometry or any count changed since new_from_scene (make a new
  * SceneGPU then).  Synchronises the device; the renderer keeps its binding. */
 LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene);
+/* After lp_scene_update_bvh_vertices (or any other geometry edit): brings an EXISTING SceneGPU up
+ * to date in place, so a renderer bound to it keeps its binding.  Host-built: the refitted
+ * trees are re-laid out and uploaded (no SAH build); device-built (lp_scene_gpu_new_from_scene_lbvh):
+ * vertices are re-uploaded and every BLAS and the TLAS are rebuilt on the device (about 1 ms of
+ * kernels per million triangles, which is why there is no separate device-side refit).
+ * Synchronises the device. */
+LP_API lp_status lp_scene_gpu_refit(lp_scene_gpu *sg, lp_scene *scene);
 /* SceneGPU::new_from_scene with the acceleration structures built ON THE DEVICE
  * (SURVEY 8(f) row 4): replaces the host BVH build behind BLASArray::add_bvh
  * [ref loaders/gltf.rs:97-105] and the node upload [ref scene.rs:151-170] by an LBVH build

@@ -106,6 +106,8 @@ _PROTOTYPES = {
                                            C.c_size_t, _vp, C.c_size_t, c_u32_p]),
     "lp_scene_add_instance": (C.c_int, [_vp, C.c_uint32, c_float_p, C.c_uint32]),
     "lp_scene_set_instance_transform": (C.c_int, [_vp, C.c_uint32, c_float_p]),
+    "lp_scene_update_bvh_vertices": (C.c_int, [_vp, C.c_uint32, _vp, C.c_size_t, _vp, C.c_size_t,
+                                               C.c_size_t]),
     "lp_scene_push_material": (C.c_int, [_vp, C.POINTER(Material), c_u32_p]),
     "lp_scene_set_material_emission": (C.c_int, [_vp, C.c_uint32, c_float_p]),
     "lp_scene_set_material": (C.c_int, [_vp, C.c_uint32, C.POINTER(Material)]),
@@ -126,6 +128,7 @@ _PROTOTYPES = {
     "lp_scene_gpu_new_from_scene": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "lp_scene_set_deferred_build": (C.c_int, [_vp, C.c_int]),
     "lp_scene_gpu_update_instances": (C.c_int, [_vp, _vp]),
+    "lp_scene_gpu_refit": (C.c_int, [_vp, _vp]),
     "lp_scene_gpu_new_from_scene_lbvh": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "lp_scene_gpu_read_array": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "lp_scene_gpu_roots": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

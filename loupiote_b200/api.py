@@ -338,6 +338,17 @@ class Scene:
         canonical tree (a device-built SceneGPU never needs it); False builds what is pending."""
         _check(_ffi.lib().lp_scene_set_deferred_build(self._h, int(bool(flag))))
 
+    def update_bvh_vertices(self, blas_index: int, positions, normals=None) -> None:
+        """Deforming mesh: new positions (and normals) of an existing BLAS; the canonical tree
+        keeps its topology and is refitted (no SAH build).  SceneGPU.refit carries it over."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32)
+        if pos.ndim != 2 or pos.shape[1] not in (3, 4):
+            raise ValueError("positions must be (N,3) or (N,4) float32")
+        nrm = None if normals is None else _f32(normals, (pos.shape[0], 3))
+        _check(_ffi.lib().lp_scene_update_bvh_vertices(
+            self._h, blas_index, pos.ctypes.data, pos.strides[0],
+            nrm.ctypes.data if nrm is not None else None, 12, pos.shape[0]))
+
     def set_instance_transform(self, instance_index: int, model_to_world) -> None:
         m = _mat4(model_to_world)
         _check(_ffi.lib().lp_scene_set_instance_transform(self._h, instance_index,
@@ -395,6 +406,11 @@ class SceneGPU:
         """After Scene.set_instance_transform (or edits of existing materials / lights):
         re-uploads the TLAS region + instance records only."""
         _check(_ffi.lib().lp_scene_gpu_update_instances(self._h, (scene or self.scene)._h))
+
+    def refit(self, scene: Optional[Scene] = None) -> None:
+        """After Scene.update_bvh_vertices: brings this SceneGPU up to date in place (host-built:
+        refitted trees re-laid out and uploaded; device-built: rebuilt on the device)."""
+        _check(_ffi.lib().lp_scene_gpu_refit(self._h, (scene or self.scene)._h))
 
     DEVICE_ARRAYS = {"nodes2": (0, _ARRAY_DTYPES[_ffi.SCENE_GPU_NODES]),
                      "nodes4": (1, _ARRAY_DTYPES[_ffi.SCENE_GPU_NODES4]),

@@ -6,6 +6,7 @@
 
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../host/api_common.hpp"
@@ -47,6 +48,14 @@ struct DevBuf {
     if (e == cudaSuccess) count = n;
     return e;
   }
+  void swap(DevBuf &o) {
+    T *p = ptr;
+    ptr = o.ptr;
+    o.ptr = p;
+    const size_t c = count;
+    count = o.count;
+    o.count = c;
+  }
   cudaError_t upload(const void *src, size_t n, cudaStream_t s) {
     cudaError_t e = alloc(n);
     if (e != cudaSuccess || n == 0) return e;
@@ -86,6 +95,26 @@ struct lp_scene_gpu {
   std::vector<uint32_t> lbvh_root2, lbvh_root4;   // child reference of every BLAS root
   std::vector<float> lbvh_root_box;               // 6 floats per BLAS (lo.xyz, hi.xyz)
   uint32_t lbvh_blas_depth4 = 0, lbvh_blas_depth2 = 0, tlas_capacity = 1;
+
+  // exchanges everything but the device with `o` (lp_scene_gpu_refit builds a fresh copy and
+  // swaps it into the handle the renderer is bound to)
+  void swap_contents(lp_scene_gpu &o) {
+    nodes.swap(o.nodes); nodes4.swap(o.nodes4); nodes4h.swap(o.nodes4h); tris.swap(o.tris);
+    instances.swap(o.instances); vertices.swap(o.vertices); materials.swap(o.materials);
+    emission.swap(o.emission); lights.swap(o.lights); indices.swap(o.indices);
+    active_lights.swap(o.active_lights); atlas.swap(o.atlas); tex_blocks.swap(o.tex_blocks);
+    srgb_lut.swap(o.srgb_lut);
+    std::swap(sc, o.sc);
+    std::swap(node_bytes, o.node_bytes); std::swap(tri_bytes, o.tri_bytes);
+    std::swap(total_bytes, o.total_bytes); std::swap(max_depth, o.max_depth);
+    std::swap(half_boxes_ok, o.half_boxes_ok); std::swap(layout_version, o.layout_version);
+    std::swap(n_instances, o.n_instances); std::swap(n_materials, o.n_materials);
+    std::swap(n_lights, o.n_lights); std::swap(lbvh, o.lbvh);
+    lbvh_root2.swap(o.lbvh_root2); lbvh_root4.swap(o.lbvh_root4);
+    lbvh_root_box.swap(o.lbvh_root_box);
+    std::swap(lbvh_blas_depth4, o.lbvh_blas_depth4); std::swap(lbvh_blas_depth2, o.lbvh_blas_depth2);
+    std::swap(tlas_capacity, o.tlas_capacity);
+  }
 };
 
 

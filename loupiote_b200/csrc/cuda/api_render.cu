@@ -674,6 +674,22 @@ LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene
   return LP_OK;
 } LP_ABI_CATCH
 
+// Deforming meshes (lp_scene_update_bvh_vertices): a fresh copy is made the way the handle was
+// made and swapped into it, so renderers bound to `sg` keep their binding.
+LP_API lp_status lp_scene_gpu_refit(lp_scene_gpu *sg, lp_scene *scene) try {
+  if (!sg || !scene) return fail(LP_ERR_INVALID_ARG, "NULL argument");
+  lp_device *dev = sg->dev;
+  CUDA_CHECK(cudaSetDevice(dev->ordinal));
+  CUDA_CHECK(cudaStreamSynchronize(dev->stream));  // frames in flight still read the old copy
+  CUDA_CHECK(cudaStreamSynchronize(dev->stream2));
+  lp_scene_gpu *fresh = nullptr;
+  const lp_status st = sg->lbvh ? lp_scene_gpu_new_from_scene_lbvh(scene, dev, &fresh)
+                                : lp_scene_gpu_new_from_scene(scene, dev, &fresh);
+  if (st != LP_OK) return st;
+  sg->swap_contents(*fresh);
+  return lp_scene_gpu_destroy(fresh);
+} LP_ABI_CATCH
+
 LP_API lp_status lp_scene_gpu_read_array(lp_scene_gpu *sg, int which, void *dst, size_t cap_bytes,
                                          size_t *out_bytes) try {
   if (!sg || !out_bytes) return fail(LP_ERR_INVALID_ARG, "NULL argument");

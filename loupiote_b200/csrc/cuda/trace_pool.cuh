@@ -39,6 +39,38 @@ constexpr int kPoolWarps = 4;            // warps per block
 #endif
 constexpr int kRing = LP_POOL_RING;      // newest stack entries of a ray kept in shared memory
 
+// LP_POOL_PREFETCH (A/B knob, profiles/r02_ab.txt): when a ray's NEXT reference becomes known --
+// after a node test, a stack pop or an instance entry -- the record it names is prefetched, since
+// the ray waits in the pool for at least one scheduling round before a lane touches it.
+// 1 = into L1 (prefetch.global.L1), 2 = into L2 only (the bounce kernels miss L2 on 32-47 % of
+// their sectors: ncu, profiles/r02_v2_physical_counters.csv).
+#ifndef LP_POOL_PREFETCH
+#define LP_POOL_PREFETCH 0
+#endif
+template <bool HALF>
+__device__ __forceinline__ void pool_prefetch(const SceneDev &sc, uint32_t ref, bool in_blas) {
+#if LP_POOL_PREFETCH
+  const void *p;
+  if (ref & kLeaf) {
+    const uint32_t idx = ref & 0x0FFFFFFFu;
+    p = in_blas ? (const void *)(sc.tris + 4u * (size_t)idx)
+                : (const void *)(sc.instances + 8u * (size_t)idx);
+  } else {
+    p = HALF ? (const void *)(sc.nodes4h + 4u * (size_t)ref)
+             : (const void *)(sc.nodes4 + 8u * (size_t)ref);
+  }
+#if LP_POOL_PREFETCH == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+#else
+  (void)sc;
+  (void)ref;
+  (void)in_blas;
+#endif
+}
+
 enum : uint32_t { kStEmpty = 0u, kStNode = 1u, kStEntry = 2u, kStTri = 3u };
 constexpr uint32_t kFlagInBlas = 4u;
 
@@ -175,6 +207,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       }
       S.b[s].w = __uint_as_float(c);
       S.e[s].x = sp | (base << 16);
+      pool_prefetch<HALF>(sc, c, (flags & kFlagInBlas) != 0u);
       const uint32_t st = (c & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode;
       S.state[s] = st | (flags & kFlagInBlas);
       return;
@@ -321,6 +354,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
           }
       }
       if (next != kNoChildRef) {
+        pool_prefetch<HALF>(sc, next, (flags & kFlagInBlas) != 0u);
         S.b[s].w = __uint_as_float(next);
         if (spb != e.x) S.e[s].x = spb;
         S.state[s] =
@@ -348,6 +382,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       uint32_t spb = e.x;
       push(s, stk, spb, kSentinel);
       S.e[s].x = spb;
+      pool_prefetch<HALF>(sc, root, true);
       S.state[s] = ((root & kLeaf) ? kStTri : kStNode) | kFlagInBlas;
     } else {
       // -------------------------------------------------------------- the triangles of a leaf

@@ -97,6 +97,22 @@ LP_API lp_status lp_scene_set_instance_transform(lp_scene *scene, uint32_t insta
   LP_TRY(scene->s.set_instance_transform(instance_index, model_to_world); return LP_OK;)
 }
 
+LP_API lp_status lp_scene_update_bvh_vertices(lp_scene *scene, uint32_t blas_index,
+                                              const void *positions, size_t position_stride,
+                                              const void *normals, size_t normal_stride,
+                                              size_t vertex_count) {
+  if (!scene) return fail(LP_ERR_INVALID_ARG, "scene is NULL");
+  try {
+    scene->s.update_bvh_vertices(blas_index, positions, position_stride, normals, normal_stride,
+                                 vertex_count);
+    return LP_OK;
+  } catch (const std::bad_alloc &) {
+    return fail(LP_ERR_OOM, "out of host memory");
+  } catch (const std::exception &e) {
+    return fail(LP_ERR_INVALID_ARG, e.what());
+  }
+}
+
 LP_API lp_status lp_scene_push_material(lp_scene *scene, const lp_material *material,
                                         uint32_t *out_index) {
   if (!scene || !material) return fail(LP_ERR_INVALID_ARG, "NULL argument");

@@ -202,6 +202,69 @@ void Scene::add_instance(uint32_t blas, const float m[16], uint32_t material) {
   derived_dirty = true;
 }
 
+// Refit ("build / refit"): vertices move, triangles and tree topology stay.
+// Children live behind their parent in `nodes` (build_bvh2 appends them), so one reverse sweep
+// over the tree's nodes recomputes every box from its leaves up.  A refitted tree is a valid
+// BVH of the deformed mesh -- closest hits are those of a fresh build, only the traversal cost
+// drifts with the deformation.
+void Scene::update_bvh_vertices(uint32_t blas, const void *positions, size_t pstride,
+                                const void *normals, size_t nstride, size_t vertex_count) {
+  if (blas >= entries.size()) throw std::invalid_argument("unknown BLAS index");
+  lp_blas_entry &e = entries[blas];
+  if (vertex_count != e.vertex_count)
+    throw std::invalid_argument("vertex count differs from the BLAS's: a refit keeps the topology");
+  if (!positions || pstride < 12) throw std::invalid_argument("positions missing or stride < 12");
+  if (normals && nstride < 12) throw std::invalid_argument("normal stride < 12");
+  const uint8_t *pp = (const uint8_t *)positions;
+  const uint8_t *np = (const uint8_t *)normals;
+  for (size_t i = 0; i < vertex_count; ++i) {  // validate before mutating
+    float p[3];
+    std::memcpy(p, pp + i * pstride, 12);
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2]))
+      throw std::invalid_argument("non-finite vertex position");
+  }
+  lp_vertex *vb = vertices.data() + e.vertex_offset;
+  for (size_t i = 0; i < vertex_count; ++i) {
+    std::memcpy(vb[i].position, pp + i * pstride, 12);
+    if (np) std::memcpy(vb[i].normal, np + i * nstride, 12);
+  }
+  derived_dirty = true;
+  if (std::find(pending_bvh.begin(), pending_bvh.end(), blas) != pending_bvh.end())
+    return;  // deferred build: no host tree yet, the first use builds it from the new vertices
+  const uint32_t *ib = indices.data() + e.index_offset;
+  lp_bvh_primitive *prims = primitives.data() + e.primitive_offset;
+  for (uint32_t k = 0; k < e.primitive_count; ++k) {
+    uint32_t t;
+    std::memcpy(&t, &prims[k].v0[3], 4);  // original triangle index rides in v0.w
+    std::memcpy(prims[k].v0, vb[ib[3 * t]].position, 12);
+    std::memcpy(prims[k].v1, vb[ib[3 * t + 1]].position, 12);
+    std::memcpy(prims[k].v2, vb[ib[3 * t + 2]].position, 12);
+  }
+  lp_bvh_node *tree = nodes.data() + e.node_offset;
+  for (uint32_t n = e.node_count; n-- > 0;) {
+    lp_bvh_node &nd = tree[n];
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    auto grow = [&](const float *a, const float *b) {
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = std::min(lo[k], a[k]);
+        hi[k] = std::max(hi[k], b[k]);
+      }
+    };
+    if (nd.count > 0) {
+      for (uint32_t k = nd.left_first; k < nd.left_first + nd.count; ++k) {
+        grow(prims[k].v0, prims[k].v0);
+        grow(prims[k].v1, prims[k].v1);
+        grow(prims[k].v2, prims[k].v2);
+      }
+    } else {
+      grow(tree[nd.left_first].aabb_min, tree[nd.left_first].aabb_max);
+      grow(tree[nd.left_first + 1].aabb_min, tree[nd.left_first + 1].aabb_max);
+    }
+    std::memcpy(nd.aabb_min, lo, 12);
+    std::memcpy(nd.aabb_max, hi, 12);
+  }
+}
+
 void Scene::rollback(const Mark &m) {
   materials.resize(m.materials);
   emission.resize(m.materials);

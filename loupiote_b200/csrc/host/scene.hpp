@@ -131,6 +131,10 @@ struct Scene {
                    size_t index_count);
   void add_instance(uint32_t blas, const float m[16], uint32_t material);
   void set_instance_transform(uint32_t instance, const float m[16]);
+  // Deforming mesh: new positions (and normals) for the vertices of an existing BLAS.  The
+  // canonical tree keeps its TOPOLOGY and its boxes are refitted bottom-up (no SAH build).
+  void update_bvh_vertices(uint32_t blas, const void *positions, size_t pstride,
+                           const void *normals, size_t nstride, size_t vertex_count);
   void build_derived();  // TLAS + GPU layout (full, or TLAS-only after set_instance_transform)
   void ensure_host_bvh();  // builds the trees add_bvh deferred (all host cores, one per tree)
   void build_tlas();

@@ -586,3 +586,92 @@ def test_push_image_rejects_impossible_dimensions():
         assert st == _ffi.LP_ERR_INVALID_ARG
     assert s.image_count == 0
     assert s.push_image(np.zeros((2, 2, 4), np.uint8)) == 0
+
+
+def _deforming_scene(phase: float):
+    """One icosphere (1280 triangles) squashed and waved by `phase`, plus a static ground quad:
+    returns (scene, sphere BLAS index, positions, normals, faces)."""
+    v, f = scenes.icosphere(3)
+    s = lb.Scene()
+    mat = s.push_material(color=(0.7, 0.6, 0.5, 1.0), roughness=0.6)
+    pos, nrm = _deformed(v, phase)
+    blas = s.blas.add_bvh_indexed(pos, f.reshape(-1), nrm)
+    s.blas.add_instance(blas, np.eye(4, dtype=np.float32), mat)
+    quad = np.array([[-4, -1.5, -4], [4, -1.5, -4], [4, -1.5, 4], [-4, -1.5, -4], [4, -1.5, 4],
+                     [-4, -1.5, 4]], dtype=np.float32)
+    s.blas.add_instance(s.blas.add_bvh(quad), np.eye(4, dtype=np.float32), mat)
+    return s, blas
+
+
+def _deformed(v, phase):
+    p = v.copy()
+    p[:, 1] *= 1.0 - 0.5 * phase                                    # squash
+    p[:, 0] += 0.35 * phase * np.sin(3.0 * v[:, 1] + 2.0 * phase)   # wave
+    p[:, 2] += 0.2 * phase * np.cos(4.0 * v[:, 0])
+    n = p / np.linalg.norm(p, axis=1, keepdims=True)
+    return p.astype(np.float32), n.astype(np.float32)
+
+
+def test_bvh_refit_keeps_topology_and_gives_the_fresh_builds_hits():
+    """lp_scene_update_bvh_vertices: the canonical tree keeps its topology, every box becomes the
+    exact bounds of its (moved) subtree, and the oracle's BVH walk over the refitted tree
+    returns the hits of brute force and of a freshly built tree of the deformed mesh."""
+    from oracle import oracle as O
+    v, f = scenes.icosphere(3)
+    s, blas = _deforming_scene(0.0)
+    e0 = s.array(_ffi.SCENE_ENTRIES)[blas].copy()
+    n0 = s.array(_ffi.SCENE_NODES).copy()
+    p0 = s.array(_ffi.SCENE_PRIMITIVES).copy()
+    pos, nrm = _deformed(v, 1.0)
+    s.update_bvh_vertices(blas, pos, nrm)
+    e1 = s.array(_ffi.SCENE_ENTRIES)[blas]
+    n1, p1 = s.array(_ffi.SCENE_NODES), s.array(_ffi.SCENE_PRIMITIVES)
+    assert e0.tobytes() == e1.tobytes()
+    lo, cnt = int(e1["node_offset"]), int(e1["node_count"])
+    assert np.array_equal(n0["left_first"], n1["left_first"]) and np.array_equal(n0["count"], n1["count"])
+    assert not np.array_equal(n0["aabb_min"][lo:lo + cnt], n1["aabb_min"][lo:lo + cnt])
+    # leaf order (the original triangle ids in v0.w) is kept, the positions moved
+    po = int(e1["primitive_offset"])
+    ids0 = p0["v0"][po:po + 1280, 3].view(np.uint32)
+    ids1 = p1["v0"][po:po + 1280, 3].view(np.uint32)
+    assert np.array_equal(ids0, ids1)
+    assert np.array_equal(p1["v0"][po:po + 1280, :3], pos[f[ids1, 0]])
+    # every box = exact bounds of its subtree, bottom-up
+    tree = n1[lo:lo + cnt]
+    prims = p1[po:po + 1280]
+
+    def bounds(i):
+        nd = tree[i]
+        if nd["count"] > 0:
+            k = slice(int(nd["left_first"]), int(nd["left_first"]) + int(nd["count"]))
+            pts = np.concatenate([prims["v0"][k, :3], prims["v1"][k, :3], prims["v2"][k, :3]])
+            return pts.min(0), pts.max(0)
+        a, b = bounds(int(nd["left_first"])), bounds(int(nd["left_first"]) + 1)
+        return np.minimum(a[0], b[0]), np.maximum(a[1], b[1])
+
+    for i in range(cnt):
+        mn, mx = bounds(i)
+        assert np.array_equal(tree[i]["aabb_min"], mn) and np.array_equal(tree[i]["aabb_max"], mx)
+    # hits: refitted tree == brute force == fresh build of the deformed mesh
+    view = lb.look_at_view((0.5, 1.0, 5.0), (0.0, -0.15, -1.0))
+    cam = O.camera_from_view(view, 160, 120, 0.78539816339)
+    osc = O.OracleScene(s)
+    ri, rp, rt, _, _ = O.first_hit_image(osc, cam, 1)
+    bi, bp, bt, tie, _ = O.first_hit_image(osc, cam, 0, want_tie=True)
+    ok = ~tie.astype(bool)
+    assert np.array_equal(ri[ok], bi[ok]) and np.array_equal(rp[ok], bp[ok])
+    fresh, _ = _deforming_scene(1.0)
+    fi, fp, ft, _, _ = O.first_hit_image(O.OracleScene(fresh), cam, 1)
+    assert np.array_equal(ri, fi) and np.array_equal(rp, fp)
+    assert np.array_equal(rt.view(np.uint32), ft.view(np.uint32))
+    assert (ri == 1).sum() > 500, "the deformed sphere is in view"
+    # argument errors leave the scene untouched
+    before = s.array(_ffi.SCENE_NODES).copy()
+    for bad in (lambda: s.update_bvh_vertices(blas, pos[:-1]),
+                lambda: s.update_bvh_vertices(99, pos),
+                lambda: s.update_bvh_vertices(blas, np.where(np.arange(len(pos))[:, None] == 7,
+                                                              np.nan, pos).astype(np.float32))):
+        with pytest.raises(lb.Error) as e:
+            bad()
+        assert e.value.code == lb.Error.InvalidArg
+    assert np.array_equal(s.array(_ffi.SCENE_NODES), before)

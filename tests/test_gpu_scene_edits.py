@@ -56,3 +56,51 @@ def test_small_table_edits_reach_an_existing_scene_gpu(device, builder):
     assert e.value.code == lb.Error.InvalidArg
 
 
+
+
+@pytest.mark.parametrize("builder", ["host", "lbvh"])
+def test_deforming_mesh_refit(device, builder):
+    """Scene.update_bvh_vertices + SceneGPU.refit: a renderer stays bound to
+    the refreshed SceneGPU; first-hit ids and t bits are the oracle's on the refitted scene and
+    the path-traced frame equals, bit for bit, the frame of a fresh upload of a freshly BUILT
+    tree of the deformed mesh (closest hits do not depend on the tree)."""
+    from oracle import oracle as O
+    from test_cpu_host import _deformed, _deforming_scene
+    v, f = scenes.icosphere(3)
+    scene, blas = _deforming_scene(0.0)
+    view = lb.look_at_view((0.5, 1.0, 5.0), (0.0, -0.15, -1.0))
+    env = (0.6, 0.7, 0.9)
+    sg = lb.SceneGPU.new_from_scene(scene, device, builder=builder)
+    r = lb.Renderer(device, SIZE, downsample_factor=1.0)
+    r.resize(sg, None, SIZE)
+    cam = O.camera_from_view(view, SIZE[0], SIZE[1], 0.78539816339)
+    frames = []
+    for phase in (0.0, 0.5, 1.0):
+        if phase > 0.0:
+            pos, nrm = _deformed(v, phase)
+            scene.update_bvh_vertices(blas, pos, nrm)
+            sg.refit(scene)  # in place: `r` keeps its binding
+        r.set_config(max_bounces=1, spp_per_call=1, jitter=0, env_color=env)
+        r.raytrace(view)
+        inst, prim, t = r.read_first_hit()
+        oi, op, ot, _, _ = O.first_hit_image(O.OracleScene(scene, env_color=env), cam, 1)
+        assert np.array_equal(inst, oi) and np.array_equal(prim, op), f"phase {phase}"
+        assert np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+        r.set_config(max_bounces=4, spp_per_call=4, jitter=1, seed=3, env_color=env)
+        r.raytrace(view)
+        acc, _ = r.read_accum_sum()
+        fresh_scene, _ = _deforming_scene(phase)
+        fresh = frame_of(device, lb.SceneGPU.new_from_scene(fresh_scene, device, builder=builder),
+                         view, env)
+        assert np.array_equal(acc, fresh), f"phase {phase}: refit == fresh build, bit for bit"
+        frames.append(acc)
+    assert not np.array_equal(frames[0], frames[2])
+
+
+def frame_of(device, sg, view, env):
+    r = lb.Renderer(device, SIZE, downsample_factor=1.0)
+    r.resize(sg, None, SIZE)
+    r.set_config(max_bounces=4, spp_per_call=4, jitter=1, seed=3, env_color=env)
+    r.raytrace(view)
+    acc, _ = r.read_accum_sum()
+    return acc
