@@ -18,8 +18,9 @@ dominant kernels (closest-hit traversal) against the fetch roofline of SURVEY 8(
 cpu_baseline = the CPU restatement (oracle) timed on a bounded sample of the same workload,
 and parity_check = the GPU image of exactly that sample set against the oracle's.  Extra
 blocks: strong scaling (a FIXED --spp-per-step split over the ranks), multi_check (the reduced
-N-GPU image against one GPU tracing the same sample set), config5 (1 spp + SVGF frame
-latency, N = 1), config4 (10M-triangle lattice at 4K, N = 8).
+N-GPU image against one GPU tracing the same sample set), job (config 3's 1024-spp budget split
+over the ranks, one reduce at the end), config5 (1 spp + SVGF frame latency, N = 1), config4
+(10M-triangle lattice at 4K, N = 8).
 """
 from __future__ import annotations
 
@@ -424,6 +425,40 @@ def run_ours(args) -> None:
                   "ms_per_step": s_ms / k_strong, "mrays_s": s_rays / (s_ms * 1e-3) / 1e6,
                   "nccl_ms": s_red / max(s_n, 1) if rank == 0 else None}
 
+    # ---- BASELINE config 3 as a JOB: the whole 1024-spp budget split over the ranks, every GPU
+    # accumulating its share locally in batches of <= spp samples, ONE exchange step at the end
+    job = None
+    if args.job_spp > 0:
+        total = args.job_spp
+        per_call = min(spp * world, total)          # samples per pixel of one call, all ranks
+        calls = max(total // per_call, 1)
+        total = calls * per_call
+        m.set_config(**common, spp_per_call=per_call, count_stats=0)
+        m.ray_counters(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            r.reset_accumulation()
+            for _ in range(calls):
+                m.set_accumulate(True)   # the sample sequence continues from call to call
+                m.render(view)
+            m.reduce()
+            m.join()
+            e1.record(stream)
+        barrier()
+        (j_ms,) = max_over_ranks(e0.elapsed_time(e1))
+        j_rays = total_rays()
+        alpha_ok = None
+        if rank == 0:
+            acc = m.read_accum_sum()
+            alpha_ok = bool(np.all(acc[..., 3] == float(total)))
+        m.set_accumulate(False)
+        r.reset_accumulation()
+        job = {"spp_total": total, "spp_per_gpu": total / world, "calls_per_gpu": calls,
+               "seconds": j_ms * 1e-3, "mrays_s": j_rays / (j_ms * 1e-3) / 1e6,
+               "spp_per_s": total / (j_ms * 1e-3), "every_pixel_holds_all_samples": alpha_ok}
+
     # ---- the reduced N-GPU image against ONE GPU tracing the same sample set
     multi_check = None
     if world > 1:
@@ -516,6 +551,7 @@ def run_ours(args) -> None:
                 "ms_per_step": ms / args.steps, "mrays_s": value,
                 "nccl_ms": reduce_ms_total / max(reduce_n, 1)},
             "multi_check": multi_check,
+            "job": job,
         }
 
     # ---- BASELINE config 4 inside the N-GPU record (default at N = 8): 10,240,002 instanced
@@ -625,6 +661,9 @@ def main() -> None:
     ap.add_argument("--no-extras", action="store_true", help="skip the config-5 block (N = 1)")
     ap.add_argument("--config4", default="auto", choices=["auto", "on", "off"],
                     help="BASELINE config 4 block (10M-triangle lattice at 4K): auto = at N = 8")
+    ap.add_argument("--job-spp", type=int, default=1024,
+                    help="`job` block: BASELINE config 3's whole sample budget split over the GPUs "
+                         "(strong scaling of the job; 0 = skip)")
     ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (tuning)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there while the bench

@@ -689,7 +689,9 @@ __global__ void __launch_bounds__(256)
 void launch_svgf_atrous(uint32_t w, uint32_t h, const float4 *in, const uint4 *gbuffer,
                         uint32_t iteration, float4 *out, bool composite, int sm_count,
                         cudaStream_t stream) {
-  static const bool gather_only = [] {  // LP_SVGF_GATHER=1: the round-1 kernel (A/B, tests)
+  // LP_SVGF_GATHER=1: the round-1 kernel (A/B, tests).  Read per launch so that a test can
+  // switch kernels inside one process (a getenv is nothing next to a launch).
+  const bool gather_only = [] {
     const char *e = std::getenv("LP_SVGF_GATHER");
     return e && std::atoi(e) != 0;
   }();
@@ -697,7 +699,7 @@ void launch_svgf_atrous(uint32_t w, uint32_t h, const float4 *in, const uint4 *g
   // 4, one block (8 warps) at 8 and 16; at stride 16 that one block no longer beats two blocks
   // of the plain tile kernel (72 vs 74 us, profiles/r02_svgf_ab.txt).  LP_SVGF_TMA=0 / 1 forces none / every stride (A/B);
   // the plain tile kernel is also the fallback when the driver offers no tensor maps.
-  static const int tma_mode = [] {
+  const int tma_mode = [] {
     const char *e = std::getenv("LP_SVGF_TMA");
     return e ? (std::atoi(e) != 0 ? 1 : 0) : 2;
   }();

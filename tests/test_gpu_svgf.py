@@ -141,3 +141,50 @@ def test_blit_modes_do_not_touch_main_target(device):
     assert np.array_equal(a, r.read_accum_f32())
     gb = r.read_aux("gbuffer")
     assert (gb[..., 2] != 0xFFFFFFFF).mean() > 0.5
+
+
+@pytest.mark.parametrize("size", [(203, 131), (64, 16), (1, 1), (333, 5)])
+def test_atrous_kernel_families_agree_on_ragged_images(device, monkeypatch, size):
+    """The three a-trous implementations -- persistent TMA tiles (cp.async.bulk.tensor), plain
+    shared-memory tiles, the round-1 gather kernel -- filter the same frames to the oracle's
+    result on image sizes that are no multiple of the 64 x 16 tile (ragged right and bottom
+    tiles, images smaller than one tile and than the 2 s halo)."""
+    c = scenes.spheres_1m(grid=3, subdivisions=2)
+    w, h = size
+    outs = {}
+    for name, env in (("default", {}), ("tma", {"LP_SVGF_TMA": "1"}), ("tile", {"LP_SVGF_TMA": "0"}),
+                      ("gather", {"LP_SVGF_GATHER": "1"})):
+        for k in ("LP_SVGF_TMA", "LP_SVGF_GATHER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r, sg = make(device, c, (w, h), max_bounces=2, spp_per_call=1, jitter=1, seed=4,
+                     atrous_iterations=5)
+        r.set_blit_mode(lb.BlitMode.DenoisedPathrace)
+        for k in range(2):
+            r.raytrace(scenes.orbit_view(c["view"], 0.5 * k))
+        outs[name] = r.read_accum_f32()
+        if name == "default":
+            f, gb = r.read_aux("radiance"), r.read_aux("gbuffer")
+            for it in range(5):
+                f = O.svgf_atrous(f, gb, it)
+            want = O.svgf_composite(f, gb)
+    scale = max(float(np.abs(want[..., :3]).max()), 1e-3)
+    for name, out in outs.items():
+        assert np.isfinite(out).all(), name
+        assert np.abs(out[..., :3] - want[..., :3]).max() < 2e-4 * scale, name
+
+
+def test_svgf_modes_trace_one_sample_per_frame(device):
+    """The SVGF blit modes consume one sample per frame like the reference's raytrace
+    [ref renderer.rs:392-549]: spp_per_call > 1 is not traced and thrown away."""
+    c = scenes.spheres_1m(grid=3, subdivisions=2)
+    r, sg = make(device, c, (96, 64), max_bounces=2, spp_per_call=4, jitter=1, seed=1)
+    r.set_blit_mode(lb.BlitMode.DenoisedPathrace)
+    r.ray_counters(reset=True)
+    r.raytrace(c["view"])
+    assert r.ray_counters()["primary"] == 96 * 64
+    r.set_blit_mode(lb.BlitMode.Pahtrace)
+    r.ray_counters(reset=True)
+    r.raytrace(c["view"])
+    assert r.ray_counters()["primary"] == 4 * 96 * 64

@@ -11,12 +11,12 @@ OUT=gpurun_out/${TAG}_ab.jsonl
 for v in $VARIANTS; do
   if [ "$v" = base ]; then unset LP_LIB_VARIANT; else export LP_LIB_VARIANT=$v; fi
   echo "{\"variant\": \"$v\"}" >> $OUT
-  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras >> $OUT 2>> gpurun_out/${TAG}_ab.err
+  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --job-spp 0 >> $OUT 2>> gpurun_out/${TAG}_ab.err
 done
 unset LP_LIB_VARIANT
 for b in $BLOCKS; do
   echo "{\"env\": \"$b\"}" >> $OUT
-  env $b timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras >> $OUT 2>> gpurun_out/${TAG}_ab.err
+  env $b timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --job-spp 0 >> $OUT 2>> gpurun_out/${TAG}_ab.err
 done
 python - <<PY
 import json
