@@ -37,6 +37,11 @@ constexpr int kPoolWarps = 4;            // warps per block
 #ifndef LP_POOL_MIN_BLOCKS
 #define LP_POOL_MIN_BLOCKS 8
 #endif
+#ifndef LP_POOL_TAIL
+#define LP_POOL_TAIL 0  // A/B knob: mixed-work rounds once the queue is empty and <= 32 rays
+                        // remain; measured -0.9 % on config 3 and +2 % frame time on config 5
+                        // (profiles/r02_ab.txt), so off
+#endif
 constexpr int kRing = LP_POOL_RING;      // newest stack entries of a ray kept in shared memory
 
 // LP_POOL_PREFETCH (A/B knob, profiles/r02_ab.txt): when a ray's NEXT reference becomes known --
@@ -233,11 +238,24 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
     // ---------------------------------------------------------------- choose the work
     unsigned m_lo, m_hi;
     uint32_t phase;
+    bool tail = false;
     if ((!exhausted && c_empty >= LP_POOL_REFILL) || (c_empty == kPool)) {
       if (exhausted) break;
       phase = kStEmpty;
       m_lo = e_lo;
       m_hi = e_hi;
+#if LP_POOL_TAIL
+    } else if (exhausted && kPool - c_empty <= 32) {
+      // Tail of the launch: the queue is empty and every ray left fits one round.  Picking ONE
+      // kind of work would leave the others waiting while the SMs run dry, so every ray
+      // advances every round instead, each lane doing what ITS ray needs (divergent, but the
+      // lanes have nothing else to do); a ray's remaining rounds -- the critical path of the
+      // launch -- roughly halve.
+      tail = true;
+      phase = kStNode;  // per lane below
+      m_lo = ~e_lo;
+      m_hi = ~e_hi & kHiMask;
+#endif
     } else if (c_tri >= 32 || (c_tri >= c_node && c_tri >= c_entry)) {
       phase = kStTri;
       m_lo = t_lo;
@@ -321,6 +339,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
     if (!active) continue;
     const uint2 e = S.e[s];  // sp, item
     const uint32_t flags = S.state[s] & ~3u;
+    if (tail) phase = S.state[s] & 3u;  // this lane's own kind of work
 
     if (phase == kStNode) {
       // -------------------------------------------------------------- 4-wide node test
