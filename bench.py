@@ -297,11 +297,13 @@ def run_ours(args) -> None:
     if world > 1:
         dist.broadcast_object_list(uid, src=0)
     m = lb.MultiRenderer.create_rank(local_rank, uid[0], world, rank)
-    m.set_reduce_mode(lb.ReduceMode.NCCL)
+    if args.exchange != "auto":
+        m.set_reduce_mode(lb.ReduceMode.NCCL if args.exchange == "nccl" else lb.ReduceMode.PEER)
     c, w, h, bounces = build_workload(args.workload)
     m.set_scene(c["scene"])
     m.resize((w, h))
     dev, r = m.device(0), m.renderer(0)
+    exchange_peer = world > 1 and args.exchange != "nccl" and m.peer_access
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
     view = c["view"]
     spp = args.spp_per_step
@@ -403,6 +405,20 @@ def run_ours(args) -> None:
     e2e_rays = total_rays()
     reduce_ms_total, reduce_n = m.reduce_time(reset=True)
     ms, e2e_s, serial_ms = max_over_ranks(ms, e2e_s, serial_ms)
+
+    # ---- the other implementation of the exchange step, for the record (3 synchronised steps)
+    other_exchange = None
+    if world > 1 and args.exchange == "auto" and exchange_peer:
+        m.set_reduce_mode(lb.ReduceMode.NCCL)
+        m.reduce_time(reset=True)
+        for _ in range(3):
+            m.render(view)
+            m.reduce()
+            m.synchronize()
+        o_ms, o_n = m.reduce_time(reset=True)
+        m.set_reduce_mode(lb.ReduceMode.AUTO)
+        other_exchange = {"mode": "ncclReduce + tone map", "ms": o_ms / max(o_n, 1)}
+        m.ray_counters(reset=True)
 
     # ---- strong scaling: the SAME total work per step (spp samples per pixel) split over the
     # ranks; at N = 1 it is the headline itself
@@ -510,8 +526,13 @@ def run_ours(args) -> None:
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, c, w, h, bounces),
-            "api": "lp_multi_* (C ABI): lp_multi_create_rank + lp_multi_render + lp_multi_reduce "
-                   "(ncclReduce inside libloupiote_b200.so)",
+            "api": "lp_multi_* (C ABI): lp_multi_create_rank + lp_multi_render + lp_multi_reduce",
+            "exchange": ("single GPU: tone map only" if world == 1 else
+                         "fused peer-memory reduce-scatter + tone map + gather over CUDA IPC "
+                         "mappings (one kernel per GPU, two one-word ncclAllReduce barriers)"
+                         if exchange_peer else
+                         "ncclReduce(sum, fp32, root 0) + tone map on rank 0, inside "
+                         "libloupiote_b200.so"),
             "scene_bytes": 0,
             "spp_per_s": world * spp * args.steps / (ms * 1e-3),
             "rays_per_step": rays / args.steps,
@@ -542,7 +563,9 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "nccl_ms": reduce_ms_total / max(reduce_n, 1),
             "nccl_ms_note": "device time of one exchange step on rank 0's communication stream "
-                            "(inputs ready -> reduced sRGB8 frame), mean over the e2e pass",
+                            "(inputs ready -> reduced sRGB8 frame), mean over the e2e pass; "
+                            "the name is the contract's, `exchange` says what ran",
+            "other_exchange": other_exchange,
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",
                     "h2d_bytes_per_step": 64 + 256, "d2h_bytes_per_step": int(img.nbytes),
                     "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -664,6 +687,10 @@ def main() -> None:
     ap.add_argument("--job-spp", type=int, default=1024,
                     help="`job` block: BASELINE config 3's whole sample budget split over the GPUs "
                          "(strong scaling of the job; 0 = skip)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
+                    help="how the accumulators are summed to rank 0: auto = the fused "
+                         "peer-memory kernel when every GPU can map the others (CUDA IPC), else "
+                         "ncclReduce")
     ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (tuning)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there while the bench

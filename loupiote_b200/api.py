@@ -700,11 +700,18 @@ class MultiRenderer:
         _check(_ffi.lib().lp_multi_info(self._h, C.byref(w), C.byref(fr), C.byref(n),
                                         C.byref(peer)))
         self.world, self.rank, self.local_devices = w.value, fr.value, n.value
-        self.peer_access = bool(peer.value)
         self._cfg = RenderConfig()
         _ffi.lib().lp_render_config_default(self._cfg)
         self._size = (0, 0)
         self._scene = None
+
+    @property
+    def peer_access(self) -> bool:
+        """True when the fused peer-memory exchange is available (every GPU maps every other
+        one's targets: after create() in one process, after resize() with one process per GPU)."""
+        peer = C.c_int()
+        _check(_ffi.lib().lp_multi_info(self._h, None, None, None, C.byref(peer)))
+        return bool(peer.value)
 
     @classmethod
     def create(cls, cuda_ordinals=None, n_devices: Optional[int] = None) -> "MultiRenderer":

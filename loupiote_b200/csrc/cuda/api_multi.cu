@@ -22,14 +22,18 @@
 //   LP_REDUCE_NCCL   ncclReduce(sum, fp32, root 0) in place on a dedicated communication
 //                    stream + a second tiny ncclReduce of the ray counters (12 x u64), then
 //                    tonemap on rank 0's communication stream.
-//   LP_REDUCE_PEER   (one process only) ONE kernel per GPU over NVLink peer memory: GPU g sums
+//   LP_REDUCE_PEER   ONE kernel per GPU over NVLink peer memory: GPU g sums
 //                    pixel slice g of every peer's accumulator with plain loads from the
 //                    peers' HBM (a reduce-scatter: (W-1)/W of the image crosses each GPU's
 //                    NVLink port instead of the whole image converging on rank 0), tone-maps
 //                    it and stores both the FP32 sum and the sRGB8 bytes of its slice straight
 //                    into rank 0's targets (the gather).  Sum, normalise, tone map and the
-//                    transfers are the same instructions of the same kernel; ordering against
-//                    the tracing streams is by CUDA events (no host synchronisation).
+//                    transfers are the same instructions of the same kernel.  One process:
+//                    the devices map each other (cudaDeviceEnablePeerAccess) and the streams
+//                    are ordered by CUDA events.  One process per GPU: the accumulators are
+//                    mapped through CUDA IPC handles (exchanged with an ncclAllGather when the
+//                    targets are made) and the ranks' streams are ordered by two one-word
+//                    ncclAllReduce barriers around the kernel.  No host synchronisation either way.
 // Either way a frame in flight may TRACE its next batch while the exchange runs; only its
 // accumulate kernel waits (lp_renderer::accum_guard).
 #include <cuda_runtime.h>
@@ -208,7 +212,13 @@ struct lp_multi {
   std::vector<std::unique_ptr<Lane>> lanes;
   lp_render_config cfg{};
   lp_multi_reduce_mode mode = LP_REDUCE_AUTO;
-  bool peer_ok = false;       // every pair of local devices can map the other's memory
+  bool peer_ok = false;       // every GPU of the job can map every other one's targets
+  // one process per GPU: the peers' targets mapped through CUDA IPC (index = global rank; the
+  // own entries are the local pointers), re-made by lp_multi_resize
+  std::vector<void *> ipc_accum, ipc_counters;
+  void *ipc_root_ldr = nullptr, *ipc_root_counters_red = nullptr;
+  std::vector<void *> ipc_opened;  // what cudaIpcCloseMemHandle has to see again
+  DevBuf<int> barrier_word;
   bool timed = false;         // ev_t0/ev_t1 of the last reduce are recorded
   double reduce_ms_total = 0.0;
   uint64_t reduce_count = 0;
@@ -290,8 +300,16 @@ void lane_destroy(Lane &l) {
   if (l.dev) lp_device_destroy(l.dev);
 }
 
+void ipc_close(lp_multi *m);
+
 void multi_free(lp_multi *m) {
   if (!m) return;
+  if (!m->lanes.empty() && m->lanes[0]->dev) {
+    cudaSetDevice(m->lanes[0]->ordinal);
+    if (m->lanes[0]->comm_stream) cudaStreamSynchronize(m->lanes[0]->comm_stream);
+    ipc_close(m);
+    m->barrier_word.release();
+  }
   for (auto &l : m->lanes) lane_destroy(*l);
   delete m;
 }
@@ -299,6 +317,98 @@ void multi_free(lp_multi *m) {
 // interleaved share of a call's samples: rank g traces indices g, g+W, ...
 uint32_t samples_for_rank(uint32_t total, uint32_t rank, uint32_t world) {
   return total > rank ? (total - rank + world - 1) / world : 0;
+}
+
+void ipc_close(lp_multi *m) {
+  for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
+  m->ipc_opened.clear();
+  m->ipc_accum.clear();
+  m->ipc_counters.clear();
+  m->ipc_root_ldr = m->ipc_root_counters_red = nullptr;
+}
+
+// One process per GPU: every rank publishes IPC handles of its SUM accumulator and ray counters
+// (rank 0 also of its sRGB8 target and reduced counters), the handles travel with one
+// ncclAllGather, every rank maps what it will read or write.  Collective.  peer_ok is the AND
+// over all ranks (an ncclAllReduce), so the ranks always agree on the exchange they run.
+lp_status ipc_exchange(lp_multi *m) {
+  Lane &l = *m->lanes[0];
+  CUDA_CHECK(cudaSetDevice(l.ordinal));
+  CUDA_CHECK(cudaStreamSynchronize(l.comm_stream));
+  ipc_close(m);
+  m->peer_ok = false;
+  if (m->world < 2) return LP_OK;
+  struct Handles {
+    cudaIpcMemHandle_t accum, counters, ldr, counters_red;
+    int device, ok;
+    char pad[8];
+  };
+  static_assert(sizeof(Handles) % 8 == 0, "gathered as bytes");
+  Handles mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.device = l.ordinal;
+  mine.ok = cudaIpcGetMemHandle(&mine.accum, l.r->accum.ptr) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.counters, l.r->counters.ptr) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.ldr, l.r->ldr.ptr) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.counters_red, l.counters_red.ptr) == cudaSuccess;
+  cudaGetLastError();
+  DevBuf<unsigned char> send, recv;
+  CUDA_CHECK(send.alloc(sizeof(Handles)));
+  CUDA_CHECK(recv.alloc(sizeof(Handles) * (size_t)m->world));
+  CUDA_CHECK(cudaMemcpyAsync(send.ptr, &mine, sizeof(mine), cudaMemcpyHostToDevice, l.comm_stream));
+  NCCL_CHECK(ncclAllGather(send.ptr, recv.ptr, sizeof(Handles), ncclUint8, l.comm, l.comm_stream));
+  std::vector<Handles> all((size_t)m->world);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), recv.ptr, sizeof(Handles) * (size_t)m->world,
+                             cudaMemcpyDeviceToHost, l.comm_stream));
+  CUDA_CHECK(cudaStreamSynchronize(l.comm_stream));
+  int ok = 1;
+  m->ipc_accum.assign((size_t)m->world, nullptr);
+  m->ipc_counters.assign((size_t)m->world, nullptr);
+  auto open = [&](const cudaIpcMemHandle_t &h) -> void * {
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      return nullptr;
+    }
+    m->ipc_opened.push_back(p);
+    return p;
+  };
+  for (int g = 0; g < m->world && ok; ++g) {
+    if (!all[(size_t)g].ok) ok = 0;
+    if (g == l.rank) {
+      m->ipc_accum[(size_t)g] = l.r->accum.ptr;
+      m->ipc_counters[(size_t)g] = l.r->counters.ptr;
+      continue;
+    }
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, l.ordinal, all[(size_t)g].device) != cudaSuccess || !can) ok = 0;
+    if (!ok) break;
+    m->ipc_accum[(size_t)g] = open(all[(size_t)g].accum);
+    m->ipc_counters[(size_t)g] = open(all[(size_t)g].counters);
+  }
+  if (ok) {
+    if (l.rank == 0) {
+      m->ipc_root_ldr = l.r->ldr.ptr;
+      m->ipc_root_counters_red = l.counters_red.ptr;
+    } else {
+      m->ipc_root_ldr = open(all[0].ldr);
+      m->ipc_root_counters_red = open(all[0].counters_red);
+    }
+  }
+  // every rank must have mapped everything, or all of them fall back to NCCL
+  CUDA_CHECK(m->barrier_word.alloc(1));
+  CUDA_CHECK(cudaMemcpyAsync(m->barrier_word.ptr, &ok, sizeof(int), cudaMemcpyHostToDevice,
+                             l.comm_stream));
+  NCCL_CHECK(ncclAllReduce(m->barrier_word.ptr, m->barrier_word.ptr, 1, ncclInt32, ncclMin, l.comm,
+                           l.comm_stream));
+  int all_ok = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&all_ok, m->barrier_word.ptr, sizeof(int), cudaMemcpyDeviceToHost,
+                             l.comm_stream));
+  CUDA_CHECK(cudaStreamSynchronize(l.comm_stream));
+  if (!all_ok) ipc_close(m);
+  m->peer_ok = all_ok != 0;
+  return LP_OK;
 }
 
 lp_status apply_config(lp_multi *m, Lane &l) {
@@ -429,7 +539,7 @@ LP_API lp_status lp_multi_info(const lp_multi *m, int *world, int *first_rank, i
   if (world) *world = m->world;
   if (first_rank) *first_rank = m->first_rank;
   if (local_devices) *local_devices = (int)m->lanes.size();
-  if (peer_access) *peer_access = m->peer_ok ? 1 : 0;
+  if (peer_access) *peer_access = m->peer_ok ? 1 : 0;  // the fused exchange is available
   return LP_OK;
 } LP_ABI_CATCH
 
@@ -510,6 +620,17 @@ LP_API lp_status lp_multi_set_probe(lp_multi *m, const uint8_t *rgbe8, uint32_t 
 LP_API lp_status lp_multi_resize(lp_multi *m, uint32_t width, uint32_t height,
                                  float downsample_factor) try {
   if (!m || !width || !height) return fail(LP_ERR_INVALID_ARG, "bad argument");
+  if (!m->single_process && m->world > 1 && !m->ipc_opened.empty()) {
+    // every rank drops its mappings of the peers' targets BEFORE any rank frees them
+    Lane &l0 = *m->lanes[0];
+    CUDA_CHECK(cudaSetDevice(l0.ordinal));
+    CUDA_CHECK(cudaStreamSynchronize(l0.comm_stream));
+    ipc_close(m);
+    m->peer_ok = false;
+    NCCL_CHECK(ncclAllReduce(m->barrier_word.ptr, m->barrier_word.ptr, 1, ncclInt32, ncclMin,
+                             l0.comm, l0.comm_stream));
+    CUDA_CHECK(cudaStreamSynchronize(l0.comm_stream));
+  }
   const lp_status st = run_all(m, [&](Lane &l) -> lp_status {
     CUDA_CHECK(cudaStreamSynchronize(l.comm_stream));  // peers may still read the old targets
     const lp_status ds = lp_renderer_set_downsample_factor(l.r, downsample_factor);
@@ -517,7 +638,10 @@ LP_API lp_status lp_multi_resize(lp_multi *m, uint32_t width, uint32_t height,
     l.r->accum_guard = nullptr;
     return lp_renderer_resize(l.r, l.sg, l.probe, width, height);
   });
-  return st;
+  if (st != LP_OK) return st;
+  // one process per GPU: the targets were re-made, so the peers' mappings are too (collective)
+  if (!m->single_process && m->world > 1) return ipc_exchange(m);
+  return LP_OK;
 } LP_ABI_CATCH
 
 // cfg.spp_per_call is the TOTAL number of samples per pixel one lp_multi_render traces over all
@@ -538,10 +662,10 @@ LP_API lp_status lp_multi_set_accumulate(lp_multi *m, int flag) try {
 
 LP_API lp_status lp_multi_set_reduce_mode(lp_multi *m, lp_multi_reduce_mode mode) try {
   if (!m) return fail(LP_ERR_INVALID_ARG, "NULL argument");
-  if (mode == LP_REDUCE_PEER && !(m->single_process && (m->peer_ok || m->world == 1)))
+  if (mode == LP_REDUCE_PEER && !(m->peer_ok || (m->single_process && m->world == 1)))
     return fail(LP_ERR_INVALID_ARG,
-                "LP_REDUCE_PEER needs one process driving all GPUs (lp_multi_create) and NVLink "
-                "peer access between every pair of them");
+                "LP_REDUCE_PEER needs NVLink peer access between every pair of GPUs (and, with "
+                "one process per GPU, lp_multi_resize to have mapped the peers' targets)");
   if (mode != LP_REDUCE_AUTO && mode != LP_REDUCE_NCCL && mode != LP_REDUCE_PEER)
     return fail(LP_ERR_INVALID_ARG, "unknown reduce mode");
   m->mode = mode;
@@ -578,8 +702,10 @@ LP_API lp_status lp_multi_render(lp_multi *m, const float view_transform[16]) tr
 // ordered after the tracing streams by events; lp_multi_read_* / lp_multi_synchronize wait.
 LP_API lp_status lp_multi_reduce(lp_multi *m) try {
   if (!m) return fail(LP_ERR_INVALID_ARG, "NULL argument");
-  const bool peer = m->mode == LP_REDUCE_PEER ||
-                    (m->mode == LP_REDUCE_AUTO && m->single_process && m->peer_ok && m->world > 1);
+  const bool peer = m->world > 1 && m->peer_ok &&
+                    (m->mode == LP_REDUCE_PEER || m->mode == LP_REDUCE_AUTO);
+  if (m->mode == LP_REDUCE_PEER && m->world > 1 && !m->peer_ok)
+    return fail(LP_ERR_INVALID_ARG, "LP_REDUCE_PEER: the peers' targets are not mapped");
   const uint32_t n_pixels = m->lanes[0]->r->width * m->lanes[0]->r->height;
   for (auto &l : m->lanes) {
     if (l->r->width * l->r->height != n_pixels)
@@ -588,7 +714,36 @@ LP_API lp_status lp_multi_reduce(lp_multi *m) try {
     CUDA_CHECK(cudaEventRecord(l->ev_rendered, l->dev->stream));
   }
   Lane *root = m->has_root() ? m->lanes[0].get() : nullptr;
-  if (peer && m->world > 1) {
+  if (peer && !m->single_process) {
+    // one process per GPU: same kernel over the IPC mappings; the ranks' communication streams
+    // meet in a one-word all-reduce before it (every accumulator is complete) and after it
+    // (every slice has landed on rank 0, every accumulator may be overwritten again)
+    Lane &l = *m->lanes[0];
+    CUDA_CHECK(cudaSetDevice(l.ordinal));
+    CUDA_CHECK(cudaStreamWaitEvent(l.comm_stream, l.ev_rendered, 0));
+    if (root) CUDA_CHECK(cudaEventRecord(l.ev_t0, l.comm_stream));
+    NCCL_CHECK(ncclAllReduce(m->barrier_word.ptr, m->barrier_word.ptr, 1, ncclInt32, ncclMin, l.comm,
+                             l.comm_stream));
+    PeerTable T{};
+    T.world = (uint32_t)m->world;
+    T.rank = (uint32_t)l.rank;
+    T.n_pixels = n_pixels;
+    for (int k = 0; k < m->world; ++k) {
+      T.accum[k] = static_cast<const float4 *>(m->ipc_accum[(size_t)k]);
+      T.counters[k] = static_cast<const Counters *>(m->ipc_counters[(size_t)k]);
+    }
+    T.root_accum = static_cast<float4 *>(m->ipc_accum[0]);
+    T.root_ldr = static_cast<uchar4 *>(m->ipc_root_ldr);
+    T.root_counters = static_cast<Counters *>(m->ipc_root_counters_red);
+    const uint32_t slice = n_pixels / (uint32_t)m->world + 1;
+    const int blocks = (int)std::min<uint32_t>((slice + 255) / 256, (uint32_t)l.dev->sm_count * 8);
+    peer_reduce_tonemap_kernel<<<blocks, 256, 0, l.comm_stream>>>(T);
+    NCCL_CHECK(ncclAllReduce(m->barrier_word.ptr, m->barrier_word.ptr, 1, ncclInt32, ncclMin, l.comm,
+                             l.comm_stream));
+    if (root) CUDA_CHECK(cudaEventRecord(l.ev_t1, l.comm_stream));
+    CUDA_CHECK(cudaEventRecord(l.ev_all_reduced, l.comm_stream));
+    l.r->accum_guard = l.ev_all_reduced;
+  } else if (peer && m->world > 1) {
     PeerTable T{};
     T.world = (uint32_t)m->world;
     T.n_pixels = n_pixels;

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256)
 #define LP_ATROUS_MIN_BLOCKS 3  // A/B knob: resident blocks the register budget is cut for
 #endif
 #ifndef LP_ATROUS_TMA_STAGES_WIDE
-#define LP_ATROUS_TMA_STAGES_WIDE 2  // A/B knob: tile buffers of the TMA kernel at strides 8, 16
+#define LP_ATROUS_TMA_STAGES_WIDE 1  // A/B knob: tile buffers of the TMA kernel at stride 16
 #endif
 constexpr int kTileX = 64;    // output columns per block (dense)
 constexpr int kTileY = 16;    // output lattice rows per block
@@ -381,8 +381,10 @@ constexpr int kTmaThreads = 256;
 template <int S>
 struct AtrousTmaTile {
   using T = AtrousTile<S>;
-  // stages the tile budget allows with >= 8 warps per SM: two below stride 8
-  static constexpr int kStages = S <= 4 ? 2 : LP_ATROUS_TMA_STAGES_WIDE;
+  // two tile buffers (prefetch of the next tile under the arithmetic of this one) up to stride
+  // 8; at stride 16 two buffers (174 KB) leave one block of 8 warps per SM, and ONE buffer with
+  // two resident blocks is faster (66.7 vs 73.5 us; two blocks of the plain tile kernel: 72.3)
+  static constexpr int kStages = S <= 8 ? 2 : LP_ATROUS_TMA_STAGES_WIDE;
   static constexpr size_t kStageBytes = (size_t)T::kPixels * 32;       // raw G-buffer + radiance
   static constexpr size_t kIdBytes = (size_t)T::kPixels * 4;           // mesh ids (decode pass)
   static constexpr size_t kBytes = kStages * kStageBytes + kIdBytes + 16;  // + two mbarriers
@@ -423,7 +425,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 
 template <int S, bool COMPOSITE>
-__global__ void __launch_bounds__(kTmaThreads, (S <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(kTmaThreads, (S <= 4 ? 2 : (S == 8 ? 1 : (LP_ATROUS_TMA_STAGES_WIDE == 1 ? 2 : 1))))
     svgf_atrous_tma_kernel(const __grid_constant__ CUtensorMap map_in,
                            const __grid_constant__ CUtensorMap map_gb, int w, int h,
                            const uint4 *__restrict__ gbuffer, float4 *__restrict__ out,
@@ -695,15 +697,14 @@ void launch_svgf_atrous(uint32_t w, uint32_t h, const float4 *in, const uint4 *g
     const char *e = std::getenv("LP_SVGF_GATHER");
     return e && std::atoi(e) != 0;
   }();
-  // The persistent TMA kernel needs two tile buffers: two blocks of it fit an SM up to stride
-  // 4, one block (8 warps) at 8 and 16; at stride 16 that one block no longer beats two blocks
-  // of the plain tile kernel (72 vs 74 us, profiles/r02_svgf_ab.txt).  LP_SVGF_TMA=0 / 1 forces none / every stride (A/B);
-  // the plain tile kernel is also the fallback when the driver offers no tensor maps.
+  // The persistent TMA kernel at every stride up to 16 (two tile buffers up to stride 8, one at
+  // 16: AtrousTmaTile).  LP_SVGF_TMA=0 selects the plain tile kernel (A/B), which is also the
+  // fallback when the driver offers no tensor maps.
   const int tma_mode = [] {
     const char *e = std::getenv("LP_SVGF_TMA");
     return e ? (std::atoi(e) != 0 ? 1 : 0) : 2;
   }();
-  const bool use_tma = tma_mode == 1 || (tma_mode == 2 && iteration <= 3);
+  const bool use_tma = tma_mode != 0;
   if (!gather_only && use_tma) {
     bool done = false;
     switch (iteration) {

@@ -9,7 +9,11 @@
 
 namespace lp {
 
-__global__ void __launch_bounds__(256) svgf_temporal_kernel(const SvgfTemporalParams P) {
+#ifndef LP_TEMPORAL_MIN_BLOCKS
+#define LP_TEMPORAL_MIN_BLOCKS 3  // A/B knob: 4 blocks (64 registers, spills) measured the same 61 us
+#endif
+
+__global__ void __launch_bounds__(256, LP_TEMPORAL_MIN_BLOCKS) svgf_temporal_kernel(const SvgfTemporalParams P) {
   const uint32_t n = P.w * P.h;
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -172,15 +172,19 @@ def test_two_gpus_accumulate_then_reduce_once(device):
 
 
 @needs_two
-def test_two_processes_one_gpu_each(device, tmp_path):
-    """lp_multi_create_rank: one process per GPU, NCCL id carried through a file."""
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_two_processes_one_gpu_each(device, tmp_path, mode):
+    """lp_multi_create_rank: one process per GPU, NCCL id carried through a file; NCCL reduce and
+    the fused peer-memory kernel over CUDA IPC mappings of the other process's targets."""
     want = single_gpu_frame(device, 6, sample_offset=6)  # the worker runs two batches
     worker = Path(__file__).resolve().parent / "_multi_rank_worker.py"
-    procs = [subprocess.Popen([sys.executable, str(worker), str(rank), "2", str(tmp_path), "6"],
+    procs = [subprocess.Popen([sys.executable, str(worker), str(rank), "2", str(tmp_path), "6", mode],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for rank in range(2)]
-    for p in procs:
-        out, _ = p.communicate(timeout=300)
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    if mode == "peer" and any(p.returncode == 77 for p in procs):
+        pytest.skip("no peer access between GPU 0 and 1")
+    for p, out in zip(procs, outs):
         assert p.returncode == 0, out
     res = np.load(tmp_path / "out.npz")
     assert_same_frame((res["accum"], res["pixels"], res["counters"].tolist()), want, 6,
