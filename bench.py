@@ -303,7 +303,7 @@ def run_ours(args) -> None:
     m.set_scene(c["scene"])
     m.resize((w, h))
     dev, r = m.device(0), m.renderer(0)
-    exchange_peer = world > 1 and args.exchange != "nccl" and m.peer_access
+    exchange_peer = world > 1 and args.exchange == "peer" and m.peer_access
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
     view = c["view"]
     spp = args.spp_per_step
@@ -408,8 +408,8 @@ def run_ours(args) -> None:
 
     # ---- the other implementation of the exchange step, for the record (3 synchronised steps)
     other_exchange = None
-    if world > 1 and args.exchange == "auto" and exchange_peer:
-        m.set_reduce_mode(lb.ReduceMode.NCCL)
+    if world > 1 and args.exchange == "auto" and m.peer_access:
+        m.set_reduce_mode(lb.ReduceMode.PEER)
         m.reduce_time(reset=True)
         for _ in range(3):
             m.render(view)
@@ -417,7 +417,8 @@ def run_ours(args) -> None:
             m.synchronize()
         o_ms, o_n = m.reduce_time(reset=True)
         m.set_reduce_mode(lb.ReduceMode.AUTO)
-        other_exchange = {"mode": "ncclReduce + tone map", "ms": o_ms / max(o_n, 1)}
+        other_exchange = {"mode": "fused peer-memory kernel over CUDA IPC mappings "
+                                  "(LP_REDUCE_PEER)", "ms": o_ms / max(o_n, 1)}
         m.ray_counters(reset=True)
 
     # ---- strong scaling: the SAME total work per step (spp samples per pixel) split over the
@@ -485,6 +486,17 @@ def run_ours(args) -> None:
         if rank == 0:
             acc_n = m.read_accum_sum()
         barrier()
+        acc_p = None
+        if m.peer_access:  # the fused peer-memory exchange must give the same frame
+            m.set_reduce_mode(lb.ReduceMode.PEER)
+            m.set_config(**common, spp_per_call=weak_total, count_stats=0)
+            m.render(view)
+            m.reduce()
+            m.synchronize()
+            if rank == 0:
+                acc_p = m.read_accum_sum()
+            barrier()
+            m.set_reduce_mode(lb.ReduceMode.AUTO)
         if rank == 0:
             r.set_config(**common, spp_per_call=weak_total, count_stats=0)
             r.reset_accumulation()
@@ -492,12 +504,18 @@ def run_ours(args) -> None:
             acc_1, _ = r.read_accum_sum()
             alpha_ok = bool(np.all(acc_n[..., 3] == float(weak_total)))
             rel = np.abs(acc_n - acc_1) / (np.abs(acc_1) + 1e-3 * weak_total)
+            rel_p = None
+            if acc_p is not None:
+                rel_p = float((np.abs(acc_p - acc_1) / (np.abs(acc_1) + 1e-3 * weak_total)).max())
+                alpha_ok = alpha_ok and bool(np.all(acc_p[..., 3] == float(weak_total)))
             multi_check = {"samples_per_pixel": weak_total, "alpha_is_n_times_spp": alpha_ok,
                            "max_rel_diff_vs_one_gpu": float(rel.max()),
+                           "peer_exchange_max_rel_diff_vs_one_gpu": rel_p,
                            "mean_rel_diff": abs(float(acc_n.mean()) - float(acc_1.mean()))
                            / float(acc_1.mean()),
                            "tol": "rtol 1e-5 (FP32 summation order)",
-                           "pass": bool(alpha_ok and float(rel.max()) <= 1e-5)}
+                           "pass": bool(alpha_ok and float(rel.max()) <= 1e-5
+                                        and (rel_p is None or rel_p <= 1e-5))}
         barrier()
 
     line = None
@@ -688,9 +706,8 @@ def main() -> None:
                     help="`job` block: BASELINE config 3's whole sample budget split over the GPUs "
                          "(strong scaling of the job; 0 = skip)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
-                    help="how the accumulators are summed to rank 0: auto = the fused "
-                         "peer-memory kernel when every GPU can map the others (CUDA IPC), else "
-                         "ncclReduce")
+                    help="how the accumulators are summed to rank 0: auto = ncclReduce (the "
+                         "faster one, measured); peer = the fused peer-memory kernel")
     ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (tuning)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there while the bench

@@ -470,10 +470,11 @@ typedef struct lp_multi lp_multi;
 #define LP_MULTI_ID_BYTES 128 /* == NCCL_UNIQUE_ID_BYTES */
 
 typedef enum lp_multi_reduce_mode {
-  LP_REDUCE_AUTO = 0, /* PEER when one process drives GPUs that all map each other, else NCCL */
+  LP_REDUCE_AUTO = 0, /* = NCCL (measured: it ties or beats PEER for a reduce TO rank 0) */
   LP_REDUCE_NCCL = 1, /* ncclReduce(sum, fp32, root 0) + tone map on rank 0's comm stream */
   LP_REDUCE_PEER = 2  /* one kernel per GPU over NVLink peer memory: reduce-scatter of the
-                         accumulators + tone map + gather into rank 0's targets */
+                         accumulators + tone map + gather into rank 0's targets (needs peer
+                         access between every pair of GPUs: lp_multi_info) */
 } lp_multi_reduce_mode;
 
 /* ONE process drives n GPUs (ncclCommInitAll, one host worker thread per device);

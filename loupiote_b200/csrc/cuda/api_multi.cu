@@ -153,15 +153,27 @@ struct PeerTable {  // kernel argument of the fused exchange
 // computes it -- and stores the sum and its sRGB8 bytes into rank 0's targets.  The slice of
 // rank 0's own accumulator is read and written by one thread only (its owner), so the in-place
 // result needs no staging copy.  Rank 0 also sums the ray counters.
+//
+// Rank 0's NVLink port is the hot spot of a reduce TO rank 0: it receives every other slice's
+// result (20 B per pixel) whatever the algorithm.  From four GPUs on it therefore owns NO slice
+// (its port would also have to carry its slice's inputs): the W-1 others split the image.
 __global__ void __launch_bounds__(256) peer_reduce_tonemap_kernel(const PeerTable T) {
-  const uint32_t lo = (uint32_t)(((uint64_t)T.n_pixels * T.rank) / T.world);
-  const uint32_t hi = (uint32_t)(((uint64_t)T.n_pixels * (T.rank + 1)) / T.world);
+  const bool root_works = T.world < 4;
+  const uint32_t workers = root_works ? T.world : T.world - 1;
+  const uint32_t me = root_works ? T.rank : T.rank - 1;  // rank 0 idles when it owns no slice
+  uint32_t lo = 0, hi = 0;
+  if (root_works || T.rank > 0) {
+    lo = (uint32_t)(((uint64_t)T.n_pixels * me) / workers);
+    hi = (uint32_t)(((uint64_t)T.n_pixels * (me + 1)) / workers);
+  }
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
     float4 v[kMaxPeers];
+    // plain loads: L1 is invalidated at every launch boundary and peer lines never enter the
+    // local L2, so nothing stale can be read; all W loads are in flight before the first add
 #pragma unroll
-    for (int k = 0; k < kMaxPeers; ++k)  // all loads in flight before the first add
-      if (k < (int)T.world) v[k] = __ldcv(T.accum[k] + i);
+    for (int k = 0; k < kMaxPeers; ++k)
+      if (k < (int)T.world) v[k] = T.accum[k][i];
     float4 s = v[0];
 #pragma unroll
     for (int k = 1; k < kMaxPeers; ++k)
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(256) peer_reduce_tonemap_kernel(const PeerTabl
   if (T.rank == 0 && blockIdx.x == 0 && threadIdx.x < 12) {
     unsigned long long c = 0;
     for (uint32_t k = 0; k < T.world; ++k)
-      c += __ldcv(reinterpret_cast<const unsigned long long *>(T.counters[k]) + threadIdx.x);
+      c += reinterpret_cast<const unsigned long long *>(T.counters[k])[threadIdx.x];
     reinterpret_cast<unsigned long long *>(T.root_counters)[threadIdx.x] = c;
   }
 }
@@ -702,8 +714,10 @@ LP_API lp_status lp_multi_render(lp_multi *m, const float view_transform[16]) tr
 // ordered after the tracing streams by events; lp_multi_read_* / lp_multi_synchronize wait.
 LP_API lp_status lp_multi_reduce(lp_multi *m) try {
   if (!m) return fail(LP_ERR_INVALID_ARG, "NULL argument");
-  const bool peer = m->world > 1 && m->peer_ok &&
-                    (m->mode == LP_REDUCE_PEER || m->mode == LP_REDUCE_AUTO);
+  // AUTO = NCCL: measured on 2 and 8 B200s the fused kernel ties (0.108 vs 0.104 ms at 1080p,
+  // 2 GPUs) or loses (0.70 vs 0.29 ms at 4K, 8 GPUs) because a reduce TO rank 0 is bound by rank
+  // 0's NVLink port either way and ncclReduce already runs at that bound; PEER is explicit
+  const bool peer = m->world > 1 && m->peer_ok && m->mode == LP_REDUCE_PEER;
   if (m->mode == LP_REDUCE_PEER && m->world > 1 && !m->peer_ok)
     return fail(LP_ERR_INVALID_ARG, "LP_REDUCE_PEER: the peers' targets are not mapped");
   const uint32_t n_pixels = m->lanes[0]->r->width * m->lanes[0]->r->height;
@@ -735,7 +749,7 @@ LP_API lp_status lp_multi_reduce(lp_multi *m) try {
     T.root_accum = static_cast<float4 *>(m->ipc_accum[0]);
     T.root_ldr = static_cast<uchar4 *>(m->ipc_root_ldr);
     T.root_counters = static_cast<Counters *>(m->ipc_root_counters_red);
-    const uint32_t slice = n_pixels / (uint32_t)m->world + 1;
+    const uint32_t slice = n_pixels / (uint32_t)std::max(1, m->world - 1) + 1;
     const int blocks = (int)std::min<uint32_t>((slice + 255) / 256, (uint32_t)l.dev->sm_count * 8);
     peer_reduce_tonemap_kernel<<<blocks, 256, 0, l.comm_stream>>>(T);
     NCCL_CHECK(ncclAllReduce(m->barrier_word.ptr, m->barrier_word.ptr, 1, ncclInt32, ncclMin, l.comm,
@@ -760,7 +774,7 @@ LP_API lp_status lp_multi_reduce(lp_multi *m) try {
         CUDA_CHECK(cudaStreamWaitEvent(l->comm_stream, o->ev_rendered, 0));
       if (l.get() == root) CUDA_CHECK(cudaEventRecord(l->ev_t0, l->comm_stream));
       T.rank = (uint32_t)l->rank;
-      const uint32_t slice = n_pixels / (uint32_t)m->world + 1;
+      const uint32_t slice = n_pixels / (uint32_t)std::max(1, m->world - 1) + 1;
       const int blocks = (int)std::min<uint32_t>((slice + 255) / 256, (uint32_t)l->dev->sm_count * 8);
       peer_reduce_tonemap_kernel<<<blocks, 256, 0, l->comm_stream>>>(T);
       CUDA_CHECK(cudaEventRecord(l->ev_reduced, l->comm_stream));
