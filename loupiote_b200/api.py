@@ -142,7 +142,7 @@ _ARRAY_DTYPES = {
     _ffi.SCENE_GPU_INSTANCES: np.dtype([("w2o", "<f4", 12), ("o2w", "<f4", 12), ("root", "<u4"),
                                         ("material", "<u4"), ("index_offset", "<u4"),
                                         ("vertex_offset", "<u4"), ("blas", "<u4"),
-                                        ("root4", "<u4"), ("pad", "<u4", 2)]),
+                                        ("root4", "<u4"), ("root8", "<u4"), ("pad", "<u4")]),
     _ffi.SCENE_GPU_NODES4: np.dtype([("lo", "<f4", (3, 4)), ("hi", "<f4", (3, 4)),
                                      ("child", "<u4", 4), ("pad", "<u4", 4)]),
     _ffi.SCENE_GPU_NODES4H: np.dtype([("box", "<f2", (6, 4)), ("child", "<u4", 4)]),

@@ -78,7 +78,8 @@ struct lp_device {
 
 struct lp_scene_gpu {
   lp_device *dev = nullptr;
-  lp::DevBuf<float4> nodes, nodes4, nodes4h, tris, instances, vertices, materials, emission, lights;
+  lp::DevBuf<float4> nodes, nodes4, nodes4h, nodes8h, tris, instances, vertices, materials, emission,
+      lights;
   lp::DevBuf<uint32_t> indices, active_lights;
   lp::DevBuf<uchar4> atlas;
   lp::DevBuf<uint4> tex_blocks;
@@ -99,7 +100,8 @@ struct lp_scene_gpu {
   // exchanges everything but the device with `o` (lp_scene_gpu_refit builds a fresh copy and
   // swaps it into the handle the renderer is bound to)
   void swap_contents(lp_scene_gpu &o) {
-    nodes.swap(o.nodes); nodes4.swap(o.nodes4); nodes4h.swap(o.nodes4h); tris.swap(o.tris);
+    nodes.swap(o.nodes); nodes4.swap(o.nodes4); nodes4h.swap(o.nodes4h); nodes8h.swap(o.nodes8h);
+    tris.swap(o.tris);
     instances.swap(o.instances); vertices.swap(o.vertices); materials.swap(o.materials);
     emission.swap(o.emission); lights.swap(o.lights); indices.swap(o.indices);
     active_lights.swap(o.active_lights); atlas.swap(o.atlas); tex_blocks.swap(o.tex_blocks);

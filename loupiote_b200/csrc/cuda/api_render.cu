@@ -343,6 +343,16 @@ void launch_trace(lp_renderer *r, const FrameParams &P, uint32_t b, bool any, in
         const char *e = std::getenv("LP_POOL_CHUNK");
         return e ? (uint32_t)std::max(32L, std::atol(e)) : 64u;
       }();
+      // LP_POOL_WIDE8=1 (A/B): the 8-wide collapse, where the scene carries one
+      static const bool wide8_env = [] {
+        const char *e = std::getenv("LP_POOL_WIDE8");
+        return e && std::atoi(e) != 0;
+      }();
+      if (wide8_env && il && P.sc.nodes8h) {
+        if (any) trace_pool_kernel<true, true, 8><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+        else trace_pool_kernel<false, true, 8><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
+        break;
+      }
       if (any && il) trace_pool_kernel<true, true><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
       else if (any) trace_pool_kernel<true, false><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
       else if (il) trace_pool_kernel<false, true><<<grid, 128, 0, st>>>(P, b, env, scratch, chunk_max);
@@ -609,6 +619,10 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   up(g->nodes, s.gpu_nodes.data(), s.gpu_nodes.size() * sizeof(GpuNode));
   up(g->nodes4, s.gpu_nodes4.data(), s.gpu_nodes4.size() * sizeof(GpuNode4));
   up(g->nodes4h, s.gpu_nodes4h.data(), s.gpu_nodes4h.size() * sizeof(GpuNode4h));
+  // 8-wide A/B variant of the ray-pool kernels (LP_POOL_WIDE8): only when its deepest stack fits
+  const bool wide8 = !s.gpu_nodes8h.empty() && s.half_boxes_ok &&
+                     s.gpu_max_stack8 <= (uint32_t)kStackSize4;
+  if (wide8) up(g->nodes8h, s.gpu_nodes8h.data(), s.gpu_nodes8h.size() * sizeof(GpuNode8h));
   // triangles: canonical 48-byte primitives padded to 64 bytes (two aligned 256-bit loads)
   std::vector<float> tris64(s.primitives.size() * 16, 0.0f);
   for (size_t i = 0; i < s.primitives.size(); ++i)
@@ -624,6 +638,8 @@ LP_API lp_status lp_scene_gpu_new_from_scene(lp_scene *scene, lp_device *dev, lp
   bind_scene(g, s, n_active, s.gpu_nodes.size(), s.gpu_nodes4.size());
   g->sc.tlas_root = s.gpu_tlas_root;
   g->sc.tlas_root4 = s.gpu_tlas_root4;
+  g->sc.nodes8h = wide8 ? g->nodes8h.ptr : nullptr;
+  g->sc.tlas_root8 = s.gpu_tlas_root8;
   g->max_depth = s.gpu_max_depth;
   g->half_boxes_ok = s.half_boxes_ok;
   g->layout_version = s.layout_version;
@@ -663,12 +679,20 @@ LP_API lp_status lp_scene_gpu_update_instances(lp_scene_gpu *sg, lp_scene *scene
                              cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaMemcpyAsync(sg->nodes4h.ptr, s.gpu_nodes4h.data(), cap * sizeof(GpuNode4h),
                              cudaMemcpyHostToDevice, st));
+  if (sg->sc.nodes8h) {
+    if (!s.gpu_nodes8h.empty() && s.half_boxes_ok && s.gpu_max_stack8 <= (uint32_t)kStackSize4)
+      CUDA_CHECK(cudaMemcpyAsync(sg->nodes8h.ptr, s.gpu_nodes8h.data(), cap * sizeof(GpuNode8h),
+                                 cudaMemcpyHostToDevice, st));
+    else
+      sg->sc.nodes8h = nullptr;  // the moved instances made the 8-wide TLAS unusable
+  }
   CUDA_CHECK(cudaMemcpyAsync(sg->instances.ptr, s.gpu_instances.data(),
                              s.gpu_instances.size() * sizeof(GpuInstance), cudaMemcpyHostToDevice, st));
   const lp_status rs = refresh_small_tables(sg, s, st);  // synchronises
   if (rs != LP_OK) return rs;
   sg->sc.tlas_root = s.gpu_tlas_root;
   sg->sc.tlas_root4 = s.gpu_tlas_root4;
+  sg->sc.tlas_root8 = s.gpu_tlas_root8;
   sg->max_depth = s.gpu_max_depth;
   sg->half_boxes_ok = s.half_boxes_ok;
   return LP_OK;

@@ -24,6 +24,9 @@ struct SceneDev {
   const float4 *nodes4h;    // 4 x float4 per 64-byte 4-wide node with fp16 boxes
   const float4 *nodes4;     // 8 x float4 per 128-byte 4-wide node (production traversal)
   uint32_t tlas_root4;      // child reference into nodes4
+  const float4 *nodes8h;    // 8 x float4 per 128-byte 8-wide node with fp16 boxes (A/B variant;
+                            // nullptr when the scene has none: device-built, or too deep)
+  uint32_t tlas_root8;
   const float4 *nodes;      // 4 x float4 per 64-byte node
   const float4 *tris;       // 3 x float4 per triangle (leaf order)
   const float4 *instances;  // 8 x float4 per 128-byte instance

@@ -52,7 +52,7 @@ constexpr int kRing = LP_POOL_RING;      // newest stack entries of a ray kept i
 #ifndef LP_POOL_PREFETCH
 #define LP_POOL_PREFETCH 0
 #endif
-template <bool HALF>
+template <bool HALF, int WIDE = 4>
 __device__ __forceinline__ void pool_prefetch(const SceneDev &sc, uint32_t ref, bool in_blas) {
 #if LP_POOL_PREFETCH
   const void *p;
@@ -96,7 +96,11 @@ struct PoolSmem {
 static_assert(sizeof(PoolSmem) * kPoolWarps + 1024 <= 228 * 1024 / LP_POOL_MIN_BLOCKS,
               "pool blocks per SM");
 
-template <bool ANY, bool HALF>
+// WIDE = 4: the production 4-wide nodes.  WIDE = 8 (A/B, LP_POOL_WIDE8=1; fp16 boxes only): the
+// 8-wide collapse of the same trees -- fewer scheduling rounds per ray, twice the box tests per
+// round; the nearest hit child is visited next, the other hit children are pushed unordered
+// (an 8-key sorting network costs more than the rounds it would save).
+template <bool ANY, bool HALF, int WIDE = 4>
 __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
     trace_pool_kernel(const __grid_constant__ FrameParams P, uint32_t bounce, int env,
                       uint32_t *__restrict__ stack_scratch, uint32_t chunk_max) {
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       }
       S.b[s].w = __uint_as_float(c);
       S.e[s].x = sp | (base << 16);
-      pool_prefetch<HALF>(sc, c, (flags & kFlagInBlas) != 0u);
+      pool_prefetch<HALF, WIDE>(sc, c, (flags & kFlagInBlas) != 0u);
       const uint32_t st = (c & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode;
       S.state[s] = st | (flags & kFlagInBlas);
       return;
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
         if (ok) {
           LaneRay r;
           lane_set_world<false>(r, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
-          const uint32_t root = sc.tlas_root4;
+          const uint32_t root = WIDE == 8 ? sc.tlas_root8 : sc.tlas_root4;
           S.a[s] = make_float4(r.o.x, r.o.y, r.o.z, tmax);
           S.b[s] = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(root));
           if (!ANY)
@@ -348,10 +352,38 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       r.o = mk3(a.x, a.y, a.z);
       r.idir = mk3(b.x, b.y, b.z);
       uint32_t spb = e.x;
+      uint32_t next = kNoChildRef;
+      if (WIDE == 8) {
+        uint32_t key[8], ref[8];
+        node8h_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
+        if (!ANY) {
+          // nearest hit child first; the others are pushed in slot order
+          uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) best = key[i] < best ? key[i] : best;
+          bool taken = false;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (key[i] != 0xFFFFFFFFu) {
+              if (!taken && key[i] == best) {
+                next = ref[i];
+                taken = true;
+              } else {
+                push(s, stk, spb, ref[i]);
+              }
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (key[i] != 0xFFFFFFFFu) {
+              if (next != kNoChildRef) push(s, stk, spb, next);
+              next = ref[i];
+            }
+        }
+      } else {
       uint32_t key[4], ref[4];
       if (HALF) node4h_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
       else node4_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
-      uint32_t next = kNoChildRef;
       if (!ANY) {
         LP_CSWAP(key[0], key[1], ref[0], ref[1])
         LP_CSWAP(key[2], key[3], ref[2], ref[3])
@@ -372,8 +404,9 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
             next = ref[i];
           }
       }
+      }
       if (next != kNoChildRef) {
-        pool_prefetch<HALF>(sc, next, (flags & kFlagInBlas) != 0u);
+        pool_prefetch<HALF, WIDE>(sc, next, (flags & kFlagInBlas) != 0u);
         S.b[s].w = __uint_as_float(next);
         if (spb != e.x) S.e[s].x = spb;
         S.state[s] =
@@ -389,7 +422,8 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       const uint32_t inst = __float_as_uint(S.b[s].w) & 0x0FFFFFFFu;
       const float4 *ip = sc.instances + 8u * (size_t)inst;
       const float4 r0 = ldg_keep(ip), r1 = ldg_keep(ip + 1), r2 = ldg_keep(ip + 2);
-      const uint32_t root = __float_as_uint(ldg_keep(ip + 7).y);
+      const float4 roots = ldg_keep(ip + 7);
+      const uint32_t root = __float_as_uint(WIDE == 8 ? roots.z : roots.y);
       float4 o4, d4;
       load_ray(e.y, o4, d4);
       LaneRay r;
@@ -401,7 +435,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       uint32_t spb = e.x;
       push(s, stk, spb, kSentinel);
       S.e[s].x = spb;
-      pool_prefetch<HALF>(sc, root, true);
+      pool_prefetch<HALF, WIDE>(sc, root, true);
       S.state[s] = ((root & kLeaf) ? kStTri : kStNode) | kFlagInBlas;
     } else {
       // -------------------------------------------------------------- the triangles of a leaf

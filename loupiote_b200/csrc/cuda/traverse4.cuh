@@ -80,6 +80,36 @@ __device__ __forceinline__ void node4h_test(const SceneDev &sc, uint32_t idx, co
 #undef LP_CHILDH
 }
 
+// 8-wide fp16 node (A/B variant of the ray-pool kernels): 4 x LDG.256; same conservative test.
+__device__ __forceinline__ void node8h_test(const SceneDev &sc, uint32_t idx, const LaneRay &r,
+                                            float tmax, uint32_t key[8], uint32_t ref[8]) {
+  const float4 *np = sc.nodes8h + 8u * (size_t)idx;
+  const f8 n0 = ldg256(np), n1 = ldg256(np + 2), n2 = ldg256(np + 4), n3 = ldg256(np + 6);
+  // planes of 8 halves (16 bytes each): lo_x lo_y | lo_z hi_x | hi_y hi_z | child[8]
+  const float4 plx = n0.lo, ply = n0.hi, plz = n1.lo, phx = n1.hi, phy = n2.lo, phz = n2.hi;
+  const float4 c0 = n3.lo, c1 = n3.hi;
+  float tn;
+  bool h;
+#define LP_CHILD8(i, w, m, cr)                                                                  \
+  {                                                                                             \
+    const float2 lx = unpack_half2(plx.w), ly = unpack_half2(ply.w), lz = unpack_half2(plz.w);  \
+    const float2 hx = unpack_half2(phx.w), hy = unpack_half2(phy.w), hz = unpack_half2(phz.w);  \
+    ref[i] = __float_as_uint(cr);                                                               \
+    h = lane_box<false>(r, mk3(lx.m, ly.m, lz.m), mk3(hx.m, hy.m, hz.m), tmax, tn) &&           \
+        ref[i] != kNoChildRef;                                                                  \
+    key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;                                             \
+  }
+  LP_CHILD8(0, x, x, c0.x)
+  LP_CHILD8(1, x, y, c0.y)
+  LP_CHILD8(2, y, x, c0.z)
+  LP_CHILD8(3, y, y, c0.w)
+  LP_CHILD8(4, z, x, c1.x)
+  LP_CHILD8(5, z, y, c1.y)
+  LP_CHILD8(6, w, x, c1.z)
+  LP_CHILD8(7, w, y, c1.w)
+#undef LP_CHILD8
+}
+
 // One ray per thread.  Returns true (ANY) as soon as an occluder is found.
 template <bool ANY, bool HALF>
 __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, float tmax, Hit &hit) {

@@ -4,6 +4,7 @@
 #include "scene.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -508,6 +509,103 @@ uint32_t relayout4(const lp_bvh_node *tree, const LeafEncoder &enc, std::vector<
   return max_depth;
 }
 
+// 8-wide collapse of the same canonical tree, boxes straight to fp16 (rounded outwards):
+// slots start as the two canonical children; while there is room, the interior slot with the
+// largest surface area is replaced by its own two children.  `base` = index of the tree's first
+// node in the final array.
+bool wide8_requested() {  // the 8-wide arrays are only made for the A/B run that asks for them
+  static const bool on = [] {
+    const char *e = std::getenv("LP_POOL_WIDE8");
+    return e && std::atoi(e) != 0;
+  }();
+  return on;
+}
+
+uint32_t relayout8h(const lp_bvh_node *tree, const LeafEncoder &enc, std::vector<GpuNode8h> &out,
+                    uint32_t &root_index) {
+  if (tree[0].count > 0) {
+    root_index = enc(tree[0]);
+    return 1;
+  }
+  if (tree[0].left_first == 0) {
+    root_index = kNoChild;
+    return 0;
+  }
+  root_index = (uint32_t)out.size();
+  const uint32_t base = root_index;
+  struct Item {
+    uint32_t canon, depth;
+  };
+  std::vector<Item> queue;
+  queue.push_back({0u, 1u});
+  uint32_t max_depth = 1;
+  auto half_area = [&](uint32_t i) {
+    const lp_bvh_node &n = tree[i];
+    const double dx = (double)n.aabb_max[0] - n.aabb_min[0], dy = (double)n.aabb_max[1] - n.aabb_min[1],
+                 dz = (double)n.aabb_max[2] - n.aabb_min[2];
+    return dx * dy + dy * dz + dz * dx;
+  };
+  for (size_t head = 0; head < queue.size(); ++head) {
+    const Item it = queue[head];
+    uint32_t slots[8];
+    int n_slots = 2;
+    slots[0] = tree[it.canon].left_first;
+    slots[1] = tree[it.canon].left_first + 1;
+    while (n_slots < 8) {
+      int best = -1;
+      double best_area = -1.0;
+      for (int s = 0; s < n_slots; ++s)
+        if (tree[slots[s]].count == 0) {
+          const double a = half_area(slots[s]);
+          if (a > best_area) {
+            best_area = a;
+            best = s;
+          }
+        }
+      if (best < 0) break;
+      const uint32_t c = tree[slots[best]].left_first;
+      slots[best] = c;
+      for (int s = n_slots; s > best + 1; --s) slots[s] = slots[s - 1];
+      slots[best + 1] = c + 1;
+      ++n_slots;
+    }
+    GpuNode8h g;
+    for (int s = 0; s < 8; ++s) {
+      g.lo_x[s] = g.lo_y[s] = g.lo_z[s] = 0x7C00u;  // +inf
+      g.hi_x[s] = g.hi_y[s] = g.hi_z[s] = 0xFC00u;  // -inf
+      g.child[s] = kNoChild;
+    }
+    for (int s = 0; s < n_slots; ++s) {
+      const lp_bvh_node &ch = tree[slots[s]];
+      g.lo_x[s] = float_to_half_down(ch.aabb_min[0]);
+      g.lo_y[s] = float_to_half_down(ch.aabb_min[1]);
+      g.lo_z[s] = float_to_half_down(ch.aabb_min[2]);
+      g.hi_x[s] = float_to_half_up(ch.aabb_max[0]);
+      g.hi_y[s] = float_to_half_up(ch.aabb_max[1]);
+      g.hi_z[s] = float_to_half_up(ch.aabb_max[2]);
+      if (ch.count > 0) {
+        g.child[s] = enc(ch);
+      } else {
+        g.child[s] = base + (uint32_t)queue.size();
+        queue.push_back({slots[s], it.depth + 1});
+      }
+      max_depth = std::max(max_depth, it.depth + 1);
+    }
+    out.push_back(g);
+  }
+  return max_depth;
+}
+
+GpuNode8h empty_node8h() {
+  GpuNode8h g;
+  for (int s = 0; s < 8; ++s) {
+    g.lo_x[s] = g.lo_y[s] = g.lo_z[s] = 0x7C00u;
+    g.hi_x[s] = g.hi_y[s] = g.hi_z[s] = 0xFC00u;
+    g.child[s] = kNoChild;
+  }
+  return g;
+}
+
 }  // namespace
 
 namespace {
@@ -591,7 +689,9 @@ void Scene::build_tlas() {
   std::vector<GpuNode4> t4;
   tlas_depth = relayout(tlas.data(), tenc, t2, gpu_tlas_root);
   tlas_depth4 = relayout4(tlas.data(), tenc, t4, gpu_tlas_root4);
-  if (t2.size() > tlas_capacity || t4.size() > tlas_capacity)
+  std::vector<GpuNode8h> t8;
+  if (wide8_requested()) tlas_depth8 = relayout8h(tlas.data(), tenc, t8, gpu_tlas_root8);
+  if (t2.size() > tlas_capacity || t4.size() > tlas_capacity || t8.size() > tlas_capacity)
     throw std::logic_error("TLAS larger than its reserved node region");
   GpuNode empty2{};
   put_box(empty2, 0, nullptr);
@@ -600,10 +700,12 @@ void Scene::build_tlas() {
   for (size_t i = 0; i < tlas_capacity; ++i) {
     gpu_nodes[i] = i < t2.size() ? t2[i] : empty2;
     gpu_nodes4[i] = i < t4.size() ? t4[i] : empty_node4();
+    if (wide8_requested()) gpu_nodes8h[i] = i < t8.size() ? t8[i] : empty_node8h();
   }
   to_half_nodes(gpu_nodes4.data(), gpu_nodes4h.data(), tlas_capacity);
   gpu_max_depth = tlas_depth + blas_depth + 1;
   gpu_max_stack4 = 3u * (tlas_depth4 + blas_depth4) + 2u;  // <= 3 pushes per visited node + sentinel
+  gpu_max_stack8 = 7u * (tlas_depth8 + blas_depth8) + 2u;
 
   // ---- are fp16 boxes good enough?  One criterion per tree root (TLAS and every BLAS, each
   // in its own space): the binary16 spacing at the root box's largest |coordinate| must be
@@ -644,6 +746,7 @@ void Scene::build_tlas() {
     const lp_blas_entry &e = entries[s.blas];
     g.root = blas_root[s.blas];
     g.root4 = blas_root4[s.blas];
+    g.root8 = wide8_requested() ? blas_root8[s.blas] : 0u;
     g.material = s.material;
     g.index_offset = e.index_offset;
     g.vertex_offset = e.vertex_offset;
@@ -675,9 +778,12 @@ void Scene::build_derived() {
   gpu_nodes.reserve(tlas_capacity + nodes.size());
   gpu_nodes4.assign(tlas_capacity, empty_node4());
   gpu_nodes4.reserve(tlas_capacity + nodes.size() / 2 + 1);
+  gpu_nodes8h.clear();
+  if (wide8_requested()) gpu_nodes8h.assign(tlas_capacity, empty_node8h());
   blas_root.assign(entries.size(), 0);
   blas_root4.assign(entries.size(), 0);
-  blas_depth = blas_depth4 = 0;
+  blas_root8.assign(entries.size(), 0);
+  blas_depth = blas_depth4 = blas_depth8 = 0;
   for (size_t e = 0; e < entries.size(); ++e) {
     if (entries[e].primitive_count == 0) continue;
     LeafEncoder benc{false, entries[e].primitive_offset};
@@ -686,6 +792,9 @@ void Scene::build_derived() {
     // 4-wide collapse of the same tree (production traversal layout)
     blas_depth4 = std::max(blas_depth4, relayout4(nodes.data() + entries[e].node_offset, benc,
                                                   gpu_nodes4, blas_root4[e]));
+    if (wide8_requested())
+      blas_depth8 = std::max(blas_depth8, relayout8h(nodes.data() + entries[e].node_offset, benc,
+                                                     gpu_nodes8h, blas_root8[e]));
   }
   gpu_nodes4h.resize(gpu_nodes4.size());
   to_half_nodes(gpu_nodes4.data() + tlas_capacity, gpu_nodes4h.data() + tlas_capacity,

@@ -43,6 +43,14 @@ struct GpuNode4h {
 };
 static_assert(sizeof(GpuNode4h) == 64, "GpuNode4h must be 64 bytes");
 
+// 128-byte 8-wide node, fp16 boxes rounded outwards (A/B variant of the ray-pool kernels,
+// LP_POOL_WIDE8): the 8-wide collapse of the same canonical tree.
+struct GpuNode8h {
+  uint16_t lo_x[8], lo_y[8], lo_z[8], hi_x[8], hi_y[8], hi_z[8];  // 96 bytes
+  uint32_t child[8];
+};
+static_assert(sizeof(GpuNode8h) == 128, "GpuNode8h must be 128 bytes");
+
 // 128-byte instance record: rows of world->object and object->world 3x4 + ids.
 struct GpuInstance {
   float w2o[12];
@@ -53,7 +61,8 @@ struct GpuInstance {
   uint32_t vertex_offset; // global offset into vertices
   uint32_t blas;
   uint32_t root4;         // child reference of the BLAS root in the 4-wide node array
-  uint32_t pad[2];
+  uint32_t root8;         // ... in the 8-wide node array (A/B variant)
+  uint32_t pad;
 };
 static_assert(sizeof(GpuInstance) == 128, "GpuInstance must be 128 bytes");
 
@@ -107,6 +116,10 @@ struct Scene {
   std::vector<GpuNode4h> gpu_nodes4h;
   uint32_t gpu_tlas_root4 = 0;
   uint32_t gpu_max_stack4 = 0;
+  // 8-wide A/B variant: same [TLAS region | BLAS trees] layout as the 4-wide arrays
+  std::vector<GpuNode8h> gpu_nodes8h;
+  uint32_t gpu_tlas_root8 = 0, gpu_max_stack8 = 0, tlas_depth8 = 0, blas_depth8 = 0;
+  std::vector<uint32_t> blas_root8;
   // false when some tree's root box sits so far from the origin that binary16 cannot resolve
   // 1/16 of its extent (or overflows): the renderer then traverses the fp32 4-wide nodes
   bool half_boxes_ok = true;
