@@ -138,6 +138,23 @@ impl Scene {
         check(unsafe { ffi::lp_scene_push_image(self.raw, img.data.as_ptr(), img.width, img.height, &mut out) })?;
         Ok(out)
     }
+    /// `scene.materials[i] = m` / `scene.lights[i] = l` (pub fields, scene.rs:30-35): edits of
+    /// existing entries; `SceneGPU::update_instances` carries them to the device.
+    pub fn set_material(&mut self, index: u32, m: &Material) -> Result<(), Error> {
+        check(unsafe { ffi::lp_scene_set_material(self.raw, index, m) })
+    }
+    pub fn set_light(&mut self, index: u32, l: &Light) -> Result<(), Error> {
+        check(unsafe { ffi::lp_scene_set_light(self.raw, index, l) })
+    }
+    /// Extension: a deforming mesh -- new positions (and normals) for the vertices of an
+    /// existing BLAS; the tree is refitted, not rebuilt.  `SceneGPU::refit` follows.
+    pub fn update_bvh_vertices(&mut self, blas: u32, mesh: MeshDescriptor) -> Result<(), Error> {
+        let n = mesh.normals.map_or(null(), |v| v.as_ptr() as *const _);
+        check(unsafe {
+            ffi::lp_scene_update_bvh_vertices(
+                self.raw, blas, mesh.positions.as_ptr() as *const _, 16, n, 12, mesh.positions.len())
+        })
+    }
 }
 
 /// crates/lib/src/loaders (gltf.rs:46-161, binary.rs:6-70).
@@ -172,6 +189,15 @@ impl SceneGPU {
         let mut raw = null_mut();
         check(unsafe { ffi::lp_scene_gpu_new_from_scene_lbvh(scene.raw, device.raw, &mut raw) })?;
         Ok(SceneGPU { raw })
+    }
+    /// After `Scene::set_instance_transform` / `set_material` / `set_light`: TLAS region,
+    /// instance records and small tables only.
+    pub fn update_instances(&mut self, scene: &Scene) -> Result<(), Error> {
+        check(unsafe { ffi::lp_scene_gpu_update_instances(self.raw, scene.raw) })
+    }
+    /// After `Scene::update_bvh_vertices`: in place, renderers keep their binding.
+    pub fn refit(&mut self, scene: &Scene) -> Result<(), Error> {
+        check(unsafe { ffi::lp_scene_gpu_refit(self.raw, scene.raw) })
     }
 }
 impl Drop for SceneGPU {
@@ -290,5 +316,68 @@ impl Renderer {
 impl Drop for Renderer {
     fn drop(&mut self) {
         unsafe { ffi::lp_renderer_destroy(self.raw) };
+    }
+}
+
+/// Extension (the reference renders on one device, standalone/src/lib.rs:220-231): the Renderer
+/// on several GPUs of one box.  The scene is replicated, the samples of a frame are split --
+/// rank g of W traces sample indices g, g+W, ... of the sequence one GPU would trace -- and the
+/// FP32 accumulators are summed to rank 0 (NCCL inside the library), where the tone map follows.
+pub struct MultiRenderer {
+    raw: *mut ffi::lp_multi,
+    size: (u32, u32),
+}
+impl MultiRenderer {
+    /// ONE process drives the GPUs `ordinals`.
+    pub fn new(ordinals: &[i32]) -> Result<Self, Error> {
+        let mut raw = null_mut();
+        check(unsafe { ffi::lp_multi_create(ordinals.as_ptr(), ordinals.len() as c_int, &mut raw) })?;
+        Ok(MultiRenderer { raw, size: (0, 0) })
+    }
+    /// One process per GPU: rank 0 calls `unique_id` and carries the bytes to the others.
+    pub fn unique_id() -> Result<[u8; 128], Error> {
+        let mut id = [0u8; 128];
+        check(unsafe { ffi::lp_multi_unique_id(id.as_mut_ptr()) })?;
+        Ok(id)
+    }
+    pub fn new_rank(ordinal: i32, id: &[u8; 128], world: i32, rank: i32) -> Result<Self, Error> {
+        let mut raw = null_mut();
+        check(unsafe { ffi::lp_multi_create_rank(ordinal, id.as_ptr(), world, rank, &mut raw) })?;
+        Ok(MultiRenderer { raw, size: (0, 0) })
+    }
+    /// `SceneGPU::new_from_scene` + `Renderer::set_resources` on every GPU.
+    pub fn set_scene(&mut self, scene: &Scene, device_build: bool) -> Result<(), Error> {
+        check(unsafe { ffi::lp_multi_set_scene(self.raw, scene.raw, device_build as c_int) })
+    }
+    pub fn resize(&mut self, size: (u32, u32), downsample_factor: f32) -> Result<(), Error> {
+        check(unsafe { ffi::lp_multi_resize(self.raw, size.0, size.1, downsample_factor) })?;
+        self.size = ((size.0 as f32 * downsample_factor) as u32, (size.1 as f32 * downsample_factor) as u32);
+        Ok(())
+    }
+    /// `cfg.spp_per_call` = total samples per pixel of one `raytrace` over all GPUs.
+    pub fn set_config(&mut self, cfg: &ffi::lp_render_config) -> Result<(), Error> {
+        check(unsafe { ffi::lp_multi_set_config(self.raw, cfg) })
+    }
+    pub fn set_accumulate(&mut self, flag: bool) -> Result<(), Error> {
+        check(unsafe { ffi::lp_multi_set_accumulate(self.raw, flag as c_int) })
+    }
+    /// `Renderer::raytrace` on every GPU (asynchronous).
+    pub fn raytrace(&mut self, view_transform: &glam::Mat4) -> Result<(), Error> {
+        check(unsafe { ffi::lp_multi_render(self.raw, view_transform.to_cols_array().as_ptr()) })
+    }
+    /// The exchange step: accumulators summed to rank 0, tone map behind it (asynchronous).
+    pub fn reduce(&mut self) -> Result<(), Error> {
+        check(unsafe { ffi::lp_multi_reduce(self.raw) })
+    }
+    /// `Renderer::read_pixels` of the reduced frame (rank 0).
+    pub fn read_pixels(&self) -> Result<Vec<u8>, Error> {
+        let mut out = vec![0u8; (self.size.0 * self.size.1 * 4) as usize];
+        check(unsafe { ffi::lp_multi_read_pixels(self.raw, out.as_mut_ptr(), out.len()) })?;
+        Ok(out)
+    }
+}
+impl Drop for MultiRenderer {
+    fn drop(&mut self) {
+        unsafe { ffi::lp_multi_destroy(self.raw) };
     }
 }
