@@ -886,7 +886,7 @@ LP_API lp_status lp_multi_read_pixels(lp_multi *m, uint8_t *out, size_t cap) try
                                   root->comm_stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(root->comm_stream);
   if (e != cudaSuccess) return fail(LP_ERR_READBACK, cudaGetErrorString(e));
-  return lp_multi_synchronize(m) == LP_OK ? LP_OK : LP_ERR_NCCL;
+  return lp_multi_synchronize(m);  // also polls the communicators (LP_ERR_NCCL)
 } LP_ABI_CATCH
 
 // The reduced FP32 SUM target (alpha = total sample count) of rank 0.

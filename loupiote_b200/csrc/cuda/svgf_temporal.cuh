@@ -4,6 +4,7 @@
 // Compiled in the uncontracted translation unit: the history length it produces is compared
 // EXACTLY with the CPU restatement (tests/test_gpu_svgf.py).  HBM-bound: 112 B per pixel.
 #pragma once
+#include <cstdlib>
 #include "frame.cuh"
 #include "svgf.cuh"
 
@@ -114,7 +115,14 @@ __global__ void __launch_bounds__(256, LP_TEMPORAL_MIN_BLOCKS) svgf_temporal_ker
 
 
 inline void launch_svgf_temporal(const SvgfTemporalParams &T, int sm_count, cudaStream_t stream) {
-  svgf_temporal_kernel<<<sm_count * 8, 256, 0, stream>>>(T);
+  // LP_TEMPORAL_GRID (A/B knob): blocks per SM of the grid-stride launch; 0 = one pixel per thread
+  static const int per_sm = [] {
+    const char *e = std::getenv("LP_TEMPORAL_GRID");
+    return e ? std::atoi(e) : 8;
+  }();
+  const uint32_t n = T.w * T.h;
+  const int grid = per_sm > 0 ? sm_count * per_sm : (int)((n + 255u) / 256u);
+  svgf_temporal_kernel<<<grid, 256, 0, stream>>>(T);
 }
 
 }  // namespace lp
