@@ -91,6 +91,25 @@ __device__ __forceinline__ float4 sample_block(const FrameParams &P, uint32_t pi
   return u;
 }
 
+// Which path slot the lane `lane` of the 32-lane batch starting at linear index `base` works
+// on, for the passes over ALL slots of a wave (bounce 0).  A wave holds S samples of every
+// pixel, slot = sample * slots_per_sample + tile * 32 + pixel-in-tile.  K = 1: the linear order
+// (a warp = one sample of an 8x4 tile).  K = 8 / 16 / 32: a warp = K SAMPLES of 32 / K adjacent
+// pixels -- the jittered rays of one pixel walk almost the same nodes, hit the same few
+// triangles and leave from the same surface; samples that do not fill a group of K keep the
+// linear order.  A permutation of the slots: results do not depend on it.
+template <uint32_t K>
+__device__ __forceinline__ uint32_t wave_slot(const FrameParams &P, uint32_t base, uint32_t lane) {
+  if (K <= 1) return base + lane;
+  constexpr uint32_t Q = 32u / (K ? K : 1u);
+  const uint32_t sps = P.slots_per_sample;
+  const uint32_t group_batches = sps / Q;  // batches per group of K samples
+  const uint32_t batch = base >> 5;
+  if (batch >= (P.samples_in_wave / K) * group_batches) return base + lane;
+  const uint32_t g = batch / group_batches, b = batch - g * group_batches;
+  return (g * K + lane / Q) * sps + b * Q + (lane % Q);
+}
+
 // Camera ray of path slot `slot` (RayPass).  Every operation is an explicitly rounded
 // intrinsic, so the three places that need the ray -- generate_kernel, the fused primary
 // extend kernel and the primary shade kernel -- compute bit-identical rays whatever the

@@ -234,6 +234,9 @@ constexpr int kShadeWarps = 4;
 #define LP_SHADE_SETTLE 2
 #endif
 constexpr int kSettle = LP_SHADE_SETTLE;
+#ifndef LP_SHADE_SPW
+#define LP_SHADE_SPW 1
+#endif
 
 template <bool PRIMARY>
 __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
@@ -312,7 +315,10 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
     if (PRIMARY) {
       if (!more) break;
       bool run_hit = false;
-      const uint32_t slot = base + lane;
+      // LP_SHADE_SPW (A/B): the primary shade pass in the same sample-major order as the primary
+      // extend kernel, so the queues it fills -- and the pools of the bounce kernels that drain
+      // them -- hold rays that leave from the same surface point
+      const uint32_t slot = wave_slot<LP_SHADE_SPW>(P, base, (uint32_t)lane);
       bool alive = slot < n;
       if (alive) alive = primary_ray(P, slot, in.o, in.d, in.pixel, in.sample, in.ls);
       if (alive) {

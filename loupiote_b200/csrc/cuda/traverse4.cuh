@@ -208,13 +208,8 @@ __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, floa
 // production primary pass: RayPass is fused in, the camera ray is computed here
 // (primary_ray) instead of being written by generate_kernel and read back (64 B per path).
 //
-// Which 32 primary rays share a warp (GEN): a wave holds S samples of every pixel, slot =
-// sample * slots_per_sample + tile * 32 + pixel-in-tile.  With LP_PRIMARY_SPW = K (8, 16 or 32) a
-// warp takes K SAMPLES of 32 / K adjacent pixels instead of one sample of a whole 8x4 tile: the
-// jittered rays of one pixel walk almost the same nodes, so more lanes are active per
-// instruction and a node fetch is one L1 wavefront for the lanes that share it.  The hits of a
-// sample's 32 / K pixels are adjacent slots (one or two full sectors per store); samples that do
-// not fill a group of K keep the tile order.  Same rays, same hits, other lanes.
+// GEN: which 32 primary rays share a warp is wave_slot<LP_PRIMARY_SPW> (frame.cuh): 16 samples of
+// 2 adjacent pixels instead of one sample of an 8x4 tile (+3.3 % on config 3).
 #ifndef LP_PRIMARY_SPW
 #define LP_PRIMARY_SPW 16  // measured on config 3: 1 / 8 / 16 / 32 = 4954 / 5079 / 5116 / 5102 Mrays/s
 #endif
@@ -225,20 +220,12 @@ __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ Fr
   const uint32_t *queue = bounce == 0 ? nullptr : P.queue[(bounce - 1) & 1u];
   uint32_t *work = P.counts + kCntWorkExtend + bounce;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t K = LP_PRIMARY_SPW, Q = 32u / K;
-  const uint32_t sps = P.slots_per_sample;
-  const uint32_t group_batches = sps / Q;                              // batches per K samples
-  const uint32_t full_batches = GEN && K > 1 ? (P.samples_in_wave / K) * group_batches : 0u;
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(work, 32u);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n) break;
-    uint32_t idx = base + lane;
-    if (GEN && K > 1 && (base >> 5) < full_batches) {
-      const uint32_t batch = base >> 5, g = batch / group_batches, b = batch - g * group_batches;
-      idx = (g * K + (uint32_t)lane / Q) * sps + b * Q + ((uint32_t)lane % Q);
-    }
+    const uint32_t idx = GEN ? wave_slot<LP_PRIMARY_SPW>(P, base, (uint32_t)lane) : base + lane;
     if (idx < n) {
       const uint32_t slot = queue ? queue[idx] : idx;
       f3 wo, wd;
