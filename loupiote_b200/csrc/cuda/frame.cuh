@@ -101,13 +101,24 @@ __device__ __forceinline__ float4 sample_block(const FrameParams &P, uint32_t pi
 template <uint32_t K>
 __device__ __forceinline__ uint32_t wave_slot(const FrameParams &P, uint32_t base, uint32_t lane) {
   if (K <= 1) return base + lane;
-  constexpr uint32_t Q = 32u / (K ? K : 1u);
   const uint32_t sps = P.slots_per_sample;
-  const uint32_t group_batches = sps / Q;  // batches per group of K samples
-  const uint32_t batch = base >> 5;
-  if (batch >= (P.samples_in_wave / K) * group_batches) return base + lane;
-  const uint32_t g = batch / group_batches, b = batch - g * group_batches;
-  return (g * K + lane / Q) * sps + b * Q + (lane % Q);
+  uint32_t batch = base >> 5;   // 32-slot batch index inside what is left of the wave
+  uint32_t first = 0;           // first sample of what is left
+  uint32_t left = P.samples_in_wave;
+  // groups of K samples first, then of K / 2 ... of 8 over the remainder (a 15-sample wave at
+  // 4K still gets one group of 8), the rest in linear order
+#pragma unroll
+  for (uint32_t k = K; k >= 8u; k >>= 1) {
+    const uint32_t q = 32u / k, group_batches = sps / q, groups = left / k;
+    if (batch < groups * group_batches) {
+      const uint32_t g = batch / group_batches, b = batch - g * group_batches;
+      return (first + g * k + lane / q) * sps + b * q + (lane % q);
+    }
+    batch -= groups * group_batches;
+    first += groups * k;
+    left -= groups * k;
+  }
+  return first * sps + batch * 32u + lane;
 }
 
 // Camera ray of path slot `slot` (RayPass).  Every operation is an explicitly rounded
