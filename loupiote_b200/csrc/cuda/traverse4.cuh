@@ -210,6 +210,9 @@ __device__ __forceinline__ bool traverse4(const SceneDev &sc, f3 wo, f3 wd, floa
 //
 // GEN: which 32 primary rays share a warp is wave_slot<LP_PRIMARY_SPW> (frame.cuh): 16 samples of
 // 2 adjacent pixels instead of one sample of an 8x4 tile (+3.3 % on config 3).
+#ifndef LP_PRIMARY_BATCHES
+#define LP_PRIMARY_BATCHES 4  // 32-ray batches per reservation of the primary extend kernel
+#endif
 #ifndef LP_PRIMARY_SPW
 #define LP_PRIMARY_SPW 16  // measured on config 3: 1 / 8 / 16 / 32 = 4954 / 5079 / 5116 / 5102 Mrays/s
 #endif
@@ -220,11 +223,21 @@ __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ Fr
   const uint32_t *queue = bounce == 0 ? nullptr : P.queue[(bounce - 1) & 1u];
   uint32_t *work = P.counts + kCntWorkExtend + bounce;
   const int lane = threadIdx.x & 31;
+  // 32-ray batches per cursor reservation: the warp waits for the atomic's round trip before
+  // every reservation (6 % of the primary kernel's warp samples at one batch per atomic); the
+  // primary rays cost about the same everywhere, so larger reservations leave no tail
+  constexpr uint32_t kBatches = GEN ? LP_PRIMARY_BATCHES : 1u;
+  uint32_t base = 0, batches_left = 0;
   for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(work, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= n) break;
+    if (batches_left == 0) {
+      if (lane == 0) base = atomicAdd(work, 32u * kBatches);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      batches_left = kBatches;
+    } else {
+      base += 32u;
+    }
+    --batches_left;
+    if (base >= n) break;  // reservations only grow: nothing is left beyond the first miss
     const uint32_t idx = GEN ? wave_slot<LP_PRIMARY_SPW>(P, base, (uint32_t)lane) : base + lane;
     if (idx < n) {
       const uint32_t slot = queue ? queue[idx] : idx;
