@@ -719,7 +719,7 @@ class MultiRenderer:
             n = len(cuda_ordinals)
             arr = (C.c_int * n)(*cuda_ordinals)
         else:
-            n, arr = int(n_devices or 1), None
+            n, arr = (1 if n_devices is None else int(n_devices)), None
         h = C.c_void_p()
         _check(_ffi.lib().lp_multi_create(arr, n, C.byref(h)))
         return cls(h)

@@ -50,6 +50,19 @@ def test_no_cpu_fallback_without_a_gpu():
         lb.Device(0)
     assert e.value.code == lb.Error.Cuda
     assert "no CPU fallback" in str(e.value)
+    # the multi-GPU half of the ABI fails the same way, in both of its shapes
+    with pytest.raises(lb.Error) as e:
+        lb.MultiRenderer.create(n_devices=2)
+    assert e.value.code == lb.Error.Cuda and "no CPU fallback" in str(e.value)
+    with pytest.raises(lb.Error) as e:
+        lb.MultiRenderer.create_rank(0, bytes(128), 1, 0)
+    assert e.value.code == lb.Error.Cuda
+    for bad in (lambda: lb.MultiRenderer.create(n_devices=0),
+                lambda: lb.MultiRenderer.create(n_devices=17),
+                lambda: lb.MultiRenderer.create_rank(0, bytes(128), 2, 2)):
+        with pytest.raises(lb.Error) as e:
+            bad()
+        assert e.value.code == lb.Error.InvalidArg
 
 
 def test_scene_default_has_dummy_index_zero():
