@@ -376,7 +376,12 @@ void launch_atrous_tile(uint32_t w, uint32_t h, const float4 *in, const uint4 *g
 // contiguous run of up to 2 KB.  Out-of-image columns / rows come back as zeros from the TMA unit (negative
 // and too-large coordinates are legal); rows q S + r >= H of the last q lie in the padding rows
 // every SVGF buffer carries (api_render.cu, kSvgfPadRows).
-constexpr int kTmaThreads = 256;
+#ifndef LP_ATROUS_R
+#define LP_ATROUS_R 4  // A/B knob: lattice outputs per thread of the TMA kernel (4: 256 threads per
+                       // tile, 10 shared-memory tap reads per output; 2: 512 threads, 15 reads)
+#endif
+constexpr int kTmaR = LP_ATROUS_R;
+constexpr int kTmaThreads = kTileX * kTileY / kTmaR;
 
 template <int S>
 struct AtrousTmaTile {
@@ -500,11 +505,11 @@ __global__ void __launch_bounds__(kTmaThreads, (S <= 4 ? 2 : (S == 8 ? 1 : (LP_A
     // ---- 4 lattice outputs per thread: column x, lattice rows rg * 4 + j
     const int x = tid & (kTileX - 1), rg = tid >> 6;
     const int col = x + 2 * S;
-    AtrousCentre c[kTileR];
-    float4 centre_b[kTileR];
+    AtrousCentre c[kTmaR];
+    float4 centre_b[kTmaR];
 #pragma unroll
-    for (int j = 0; j < kTileR; ++j) {
-      const int p = (rg * kTileR + j + 2) * T::kWidth + col;
+    for (int j = 0; j < kTmaR; ++j) {
+      const int p = (rg * kTmaR + j + 2) * T::kWidth + col;
       const float4 a = A[p], b = B[p];
       centre_b[j] = b;
       const float log2e = 1.4426950408889634f;
@@ -526,17 +531,17 @@ __global__ void __launch_bounds__(kTmaThreads, (S <= 4 ? 2 : (S == 8 ? 1 : (LP_A
     // a warp whose 128 outputs are all background (sky) has nothing to filter
     bool live = false;
 #pragma unroll
-    for (int j = 0; j < kTileR; ++j) live |= c[j].id != LP_INVALID_INDEX;
+    for (int j = 0; j < kTmaR; ++j) live |= c[j].id != LP_INVALID_INDEX;
     if (__any_sync(0xFFFFFFFFu, live))
 #pragma unroll
-    for (int tr = 0; tr < kTileR + 4; ++tr) {
+    for (int tr = 0; tr < kTmaR + 4; ++tr) {
 #pragma unroll
       for (int dx = -2; dx <= 2; ++dx) {
-        const int p = (rg * kTileR + tr) * T::kWidth + col + dx * S;
+        const int p = (rg * kTmaR + tr) * T::kWidth + col + dx * S;
         const float4 a = A[p], b = B[p];
         const float2 l = make_float2(luminance(mk3(b.x, b.y, b.z)), __uint_as_float(ID[p]));
 #pragma unroll
-        for (int j = 0; j < kTileR; ++j) {
+        for (int j = 0; j < kTmaR; ++j) {
           const int dy = tr - j - 2;
           if (dy < -2 || dy > 2 || (dx == 0 && dy == 0)) continue;
           const int adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
@@ -553,8 +558,8 @@ __global__ void __launch_bounds__(kTmaThreads, (S <= 4 ? 2 : (S == 8 ? 1 : (LP_A
     }
     const int gx = x0 + x;
 #pragma unroll
-    for (int j = 0; j < kTileR; ++j) {
-      const int gy = ybase + (rg * kTileR + j) * S;
+    for (int j = 0; j < kTmaR; ++j) {
+      const int gy = ybase + (rg * kTmaR + j) * S;
       if (gx >= w || gy >= h) continue;
       const int i = gy * w + gx;
       const float4 b = centre_b[j];
