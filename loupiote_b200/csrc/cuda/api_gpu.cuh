@@ -79,7 +79,7 @@ struct lp_device {
 struct lp_scene_gpu {
   lp_device *dev = nullptr;
   lp::DevBuf<float4> nodes, nodes4, nodes4h, nodes8h, tris, instances, vertices, materials, emission,
-      lights;
+      lights, shade_tris;
   lp::DevBuf<uint32_t> indices, active_lights;
   lp::DevBuf<uchar4> atlas;
   lp::DevBuf<uint4> tex_blocks;
@@ -101,7 +101,7 @@ struct lp_scene_gpu {
   // swaps it into the handle the renderer is bound to)
   void swap_contents(lp_scene_gpu &o) {
     nodes.swap(o.nodes); nodes4.swap(o.nodes4); nodes4h.swap(o.nodes4h); nodes8h.swap(o.nodes8h);
-    tris.swap(o.tris);
+    tris.swap(o.tris); shade_tris.swap(o.shade_tris);
     instances.swap(o.instances); vertices.swap(o.vertices); materials.swap(o.materials);
     emission.swap(o.emission); lights.swap(o.lights); indices.swap(o.indices);
     active_lights.swap(o.active_lights); atlas.swap(o.atlas); tex_blocks.swap(o.tex_blocks);

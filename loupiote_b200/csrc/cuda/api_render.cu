@@ -523,6 +523,21 @@ cudaError_t lp::upload_shading_data(lp_scene_gpu *g, Scene &s, cudaStream_t st, 
   up(g->emission, s.emission.data(), s.emission.size() * 16);
   up(g->lights, s.lights.data(), s.lights.size() * sizeof(lp_light));
   up(g->indices, s.indices.data(), s.indices.size() * sizeof(uint32_t));
+  // LP_SHADE_RECORDS=1 (A/B, profiles/r02_ab.txt): per-triangle shading records -- the three
+  // 32-byte vertices of every triangle, in original triangle order -- so that fetch_surface reads
+  // one contiguous 96-byte record instead of three indices and then three scattered vertices
+  std::vector<lp_vertex> recs;
+  static const bool want_records = [] {
+    const char *e = std::getenv("LP_SHADE_RECORDS");
+    return e && std::atoi(e) != 0;
+  }();
+  if (want_records) {
+    recs.resize(s.indices.size());
+    for (const lp_blas_entry &en : s.entries)
+      for (uint32_t i = 0; i < en.index_count; ++i)
+        recs[en.index_offset + i] = s.vertices[en.vertex_offset + s.indices[en.index_offset + i]];
+    up(g->shade_tris, recs.data(), recs.size() * sizeof(lp_vertex));
+  }
   // room for every light: lp_scene_set_light may switch one on later (refresh_small_tables)
   active.resize(s.lights.size(), 0u);
   up(g->active_lights, active.data(), active.size() * sizeof(uint32_t));
@@ -547,6 +562,7 @@ void lp::bind_scene(lp_scene_gpu *g, const Scene &s, uint32_t n_active, size_t n
   sc.tris = g->tris.ptr;
   sc.instances = g->instances.ptr;
   sc.vertices = g->vertices.ptr;
+  sc.shade_tris = g->shade_tris.count > 1 ? g->shade_tris.ptr : nullptr;
   sc.indices = g->indices.ptr;
   sc.materials = g->materials.ptr;
   sc.emission = g->emission.ptr;

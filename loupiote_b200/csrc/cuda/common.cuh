@@ -30,6 +30,8 @@ struct SceneDev {
   const float4 *nodes;      // 4 x float4 per 64-byte node
   const float4 *tris;       // 3 x float4 per triangle (leaf order)
   const float4 *instances;  // 8 x float4 per 128-byte instance
+  const float4 *shade_tris; // A/B (LP_SHADE_RECORDS=1): 6 x float4 per triangle in original order =
+                            // its three vertices, so shading skips the index gather; else nullptr
   const float4 *vertices;   // 2 x float4 per vertex
   const uint32_t *indices;
   const float4 *materials;  // 2 x float4 per material

@@ -92,12 +92,26 @@ __device__ __forceinline__ void fetch_surface(const SceneDev &sc, const Hit &hit
   const uint32_t material = __float_as_uint(ids.y);
   const uint32_t index_offset = __float_as_uint(ids.z);
   const uint32_t vertex_offset = __float_as_uint(ids.w);
-  const uint32_t *idx = sc.indices + index_offset + 3u * hit.prim;
-  const uint32_t i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
-  const float4 *vp = sc.vertices + 2u * (size_t)vertex_offset;
-  const float4 a0 = __ldg(vp + 2u * i0), a1 = __ldg(vp + 2u * i0 + 1);
-  const float4 b0 = __ldg(vp + 2u * i1), b1 = __ldg(vp + 2u * i1 + 1);
-  const float4 c0 = __ldg(vp + 2u * i2), c1 = __ldg(vp + 2u * i2 + 1);
+  float4 a0, a1, b0, b1, c0, c1;
+  if (sc.shade_tris) {  // A/B: one 96-byte record per triangle, no index gather
+    const float4 *rec = sc.shade_tris + 2u * ((size_t)index_offset + 3u * hit.prim);
+    a0 = __ldg(rec);
+    a1 = __ldg(rec + 1);
+    b0 = __ldg(rec + 2);
+    b1 = __ldg(rec + 3);
+    c0 = __ldg(rec + 4);
+    c1 = __ldg(rec + 5);
+  } else {
+    const uint32_t *idx = sc.indices + index_offset + 3u * hit.prim;
+    const uint32_t i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
+    const float4 *vp = sc.vertices + 2u * (size_t)vertex_offset;
+    a0 = __ldg(vp + 2u * i0);
+    a1 = __ldg(vp + 2u * i0 + 1);
+    b0 = __ldg(vp + 2u * i1);
+    b1 = __ldg(vp + 2u * i1 + 1);
+    c0 = __ldg(vp + 2u * i2);
+    c1 = __ldg(vp + 2u * i2 + 1);
+  }
   const float bu = hit.u, bv = hit.v, bw = 1.0f - hit.u - hit.v;
   const f3 po = mk3(__fmaf_rn(bw, a0.x, __fmaf_rn(bu, b0.x, bv * c0.x)),
                     __fmaf_rn(bw, a0.y, __fmaf_rn(bu, b0.y, bv * c0.y)),
