@@ -602,7 +602,7 @@ def run_ours(args) -> None:
         c4, w4, h4, b4 = build_workload("lattice-10M-4k-8b")
         m.set_scene(c4["scene"])
         m.resize((w4, h4))
-        spp4, k4 = 15, 3
+        spp4, k4 = 30, 3  # one wave of 249 M slots at 4K (LP_MAX_SLOTS = 256 M)
         cfg4 = dict(max_bounces=b4, jitter=1, seed=0, env_color=c4["env_color"], sample_offset=0,
                     sample_stride=1, count_stats=0, traversal_variant=args.variant)
         m.set_config(**cfg4, spp_per_call=spp4 * world)
@@ -638,6 +638,8 @@ def run_ours(args) -> None:
             one = (cc["primary"] + cc["bounce"] + cc["shadow"]) / (e0.elapsed_time(e1) * 1e-3) / 1e6
         barrier()
         view = keep
+        m.set_scene(c["scene"])  # back to the headline workload for the blocks that follow
+        m.resize((w, h))
         if rank == 0:
             mr4 = rays4 / (ms4 * 1e-3) / 1e6
             line["config4"] = {
@@ -688,15 +690,20 @@ def run_ours(args) -> None:
 
 
 def main() -> None:
+    # wave size of the renderer: up to 256 M path slots in flight (the library's default cap is
+    # 128 M = 25 GB of path state; the benchmark spends 50 GB of the 180 GB on it)
+    os.environ.setdefault("LP_MAX_SLOTS", str(256 << 20))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="spheres-1M-1080p-8b", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-per-step", type=int, default=64,
+    ap.add_argument("--spp-per-step", type=int, default=128,
                     help="samples per pixel every GPU traces per step (weak scaling); the "
-                         "`strong` block splits this same number over the GPUs")
+                         "`strong` block splits this same number over the GPUs.  128 = one wave "
+                         "of 265 M path slots (50 GB of path state, LP_MAX_SLOTS below): 5212 "
+                         "Mrays/s against 5150 with 64-sample waves (profiles/r02_ab.txt)")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the cpu_baseline + parity_check leg (N = 1)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-5 block (N = 1)")

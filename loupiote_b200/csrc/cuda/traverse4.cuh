@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(128) extend4_kernel(const __grid_constant__ Fr
   // 32-ray batches per cursor reservation: the warp waits for the atomic's round trip before
   // every reservation (6 % of the primary kernel's warp samples at one batch per atomic); the
   // primary rays cost about the same everywhere, so larger reservations leave no tail
-  constexpr uint32_t kBatches = GEN ? LP_PRIMARY_BATCHES : 1u;
+  // ... of a LARGE launch: with few rays (an interactive 1-spp frame is 12 batches per warp)
+  // reservations of 4 leave warps idle at the end (config 5: frame 2.31 -> 2.49 ms)
+  const uint32_t kBatches = (GEN && n >= (1u << 24)) ? LP_PRIMARY_BATCHES : 1u;
   uint32_t base = 0, batches_left = 0;
   for (;;) {
     if (batches_left == 0) {
