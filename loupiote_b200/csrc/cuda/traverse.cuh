@@ -94,6 +94,56 @@ __device__ __forceinline__ bool lane_box(const LaneRay &r, f3 lo, f3 hi, float t
   return tn <= __fmul_rn(tf, EXACT ? 1.0000004f : 1.000001f);
 }
 
+// The slab test of the production (4-wide) kernels: the same conservative decision with half
+// the arithmetic.  Per NODE visit: p = o * idir per axis, widened by 2^-22 |p| to either side
+// (pn >= o * idir >= pf whatever the rounding of the product), and which plane of a box the ray
+// enters through per axis (the sign of idir).  Per BOX: near_k = fma(plane_near_k, idir_k, -pn_k)
+// and far_k = fma(plane_far_k, idir_k, -pf_k) -- 6 FFMA instead of 6 FADD + 6 FMUL, and no
+// min / max between the two planes of an axis.  near is never above and far never below the
+// values of lane_box up to the relative rounding the 1e-6 padding of the far side already
+// covers, so a box lane_box<false> accepts is accepted here as well: the visited set can only
+// grow, and what is HIT is decided by the exact triangle test alone.
+#ifndef LP_SLAB_FMA
+#define LP_SLAB_FMA 1  // 0 = node tests through lane_box (A/B, profiles/r02_ab.txt)
+#endif
+struct SlabRay {
+  float ix, iy, iz;     // 1 / direction
+  float pnx, pny, pnz;  // o * idir rounded UP   (for the near planes)
+  float pfx, pfy, pfz;  // o * idir rounded DOWN (for the far planes)
+  bool nx, ny, nz;      // direction component negative: the ray enters through the hi plane
+};
+__device__ __forceinline__ SlabRay slab_ray(const LaneRay &r) {
+  SlabRay s;
+  s.ix = r.idir.x;
+  s.iy = r.idir.y;
+  s.iz = r.idir.z;
+  const float px = __fmul_rn(r.o.x, r.idir.x), py = __fmul_rn(r.o.y, r.idir.y),
+              pz = __fmul_rn(r.o.z, r.idir.z);
+  constexpr float kW = 2.3841858e-7f;  // 2^-22
+  s.pnx = __fmaf_rn(fabsf(px), kW, px);
+  s.pny = __fmaf_rn(fabsf(py), kW, py);
+  s.pnz = __fmaf_rn(fabsf(pz), kW, pz);
+  s.pfx = __fmaf_rn(fabsf(px), -kW, px);
+  s.pfy = __fmaf_rn(fabsf(py), -kW, py);
+  s.pfz = __fmaf_rn(fabsf(pz), -kW, pz);
+  s.nx = r.idir.x < 0.0f;
+  s.ny = r.idir.y < 0.0f;
+  s.nz = r.idir.z < 0.0f;
+  return s;
+}
+// (ex, ey, ez) = the planes the ray enters through, (lx, ly, lz) = the planes it leaves through
+__device__ __forceinline__ bool slab_box(const SlabRay &s, float ex, float ey, float ez, float lx,
+                                         float ly, float lz, float tmax, float &tnear) {
+  const float ax = __fmaf_rn(ex, s.ix, -s.pnx), ay = __fmaf_rn(ey, s.iy, -s.pny),
+              az = __fmaf_rn(ez, s.iz, -s.pnz);
+  const float bx = __fmaf_rn(lx, s.ix, -s.pfx), by = __fmaf_rn(ly, s.iy, -s.pfy),
+              bz = __fmaf_rn(lz, s.iz, -s.pfz);
+  const float tn = fmaxf(fmaxf(0.0f, ax), fmaxf(ay, az));
+  const float tf = fminf(fminf(tmax, bx), fminf(by, bz));
+  tnear = tn;
+  return tn <= __fmul_rn(tf, 1.000001f);
+}
+
 // Triangle i of the GPU triangle array: the 48-byte canonical primitive padded to 64 bytes so
 // that it is two aligned LDG.256 (two L1 wavefronts per lane instead of three LDG.128).
 template <bool NA = false>

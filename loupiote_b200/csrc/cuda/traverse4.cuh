@@ -35,11 +35,22 @@ __device__ __forceinline__ void node4_test(const SceneDev &sc, uint32_t idx, con
   const float4 cr = n3.lo;  // 128-byte node = 4 x LDG.256
   float tn;
   bool h;
+#if LP_SLAB_FMA
+  const SlabRay s = slab_ray(r);
+  const float4 ex = s.nx ? hx : lx, ox = s.nx ? lx : hx;
+  const float4 ey = s.ny ? hy : ly, oy = s.ny ? ly : hy;
+  const float4 ez = s.nz ? hz : lz, oz = s.nz ? lz : hz;
+#define LP_CHILD(i, c)                                                                     \
+  ref[i] = __float_as_uint(cr.c);                                                          \
+  h = slab_box(s, ex.c, ey.c, ez.c, ox.c, oy.c, oz.c, tmax, tn) && ref[i] != kNoChildRef;  \
+  key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
+#else
 #define LP_CHILD(i, c)                                                                     \
   ref[i] = __float_as_uint(cr.c);                                                          \
   h = lane_box<false>(r, mk3(lx.c, ly.c, lz.c), mk3(hx.c, hy.c, hz.c), tmax, tn) &&        \
       ref[i] != kNoChildRef;                                                               \
   key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
+#endif
   LP_CHILD(0, x)
   LP_CHILD(1, y)
   LP_CHILD(2, z)
@@ -58,21 +69,37 @@ __device__ __forceinline__ void node4h_test(const SceneDev &sc, uint32_t idx, co
                                             float tmax, uint32_t key[4], uint32_t ref[4]) {
   const float4 *np = sc.nodes4h + 4u * (size_t)idx;
   const f8 n0 = ldg256(np), n1 = ldg256(np + 2);
+  const float4 cr = n1.hi;
+  float tn;
+  bool h;
+#if LP_SLAB_FMA
+  // the planes are picked on the PACKED words (two children per select), then unpacked
+  const SlabRay s = slab_ray(r);
+  const float2 ex01 = unpack_half2(s.nx ? n0.hi.z : n0.lo.x), ex23 = unpack_half2(s.nx ? n0.hi.w : n0.lo.y);
+  const float2 ox01 = unpack_half2(s.nx ? n0.lo.x : n0.hi.z), ox23 = unpack_half2(s.nx ? n0.lo.y : n0.hi.w);
+  const float2 ey01 = unpack_half2(s.ny ? n1.lo.x : n0.lo.z), ey23 = unpack_half2(s.ny ? n1.lo.y : n0.lo.w);
+  const float2 oy01 = unpack_half2(s.ny ? n0.lo.z : n1.lo.x), oy23 = unpack_half2(s.ny ? n0.lo.w : n1.lo.y);
+  const float2 ez01 = unpack_half2(s.nz ? n1.lo.z : n0.hi.x), ez23 = unpack_half2(s.nz ? n1.lo.w : n0.hi.y);
+  const float2 oz01 = unpack_half2(s.nz ? n0.hi.x : n1.lo.z), oz23 = unpack_half2(s.nz ? n0.hi.y : n1.lo.w);
+#define LP_CHILDH(i, c, L, H, m)                                                              \
+  ref[i] = __float_as_uint(cr.c);                                                            \
+  h = slab_box(s, ex##L.m, ey##L.m, ez##L.m, ox##L.m, oy##L.m, oz##L.m, tmax, tn) &&        \
+      ref[i] != kNoChildRef;                                                                 \
+  key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
+#else
   const float2 lx01 = unpack_half2(n0.lo.x), lx23 = unpack_half2(n0.lo.y);
   const float2 ly01 = unpack_half2(n0.lo.z), ly23 = unpack_half2(n0.lo.w);
   const float2 lz01 = unpack_half2(n0.hi.x), lz23 = unpack_half2(n0.hi.y);
   const float2 hx01 = unpack_half2(n0.hi.z), hx23 = unpack_half2(n0.hi.w);
   const float2 hy01 = unpack_half2(n1.lo.x), hy23 = unpack_half2(n1.lo.y);
   const float2 hz01 = unpack_half2(n1.lo.z), hz23 = unpack_half2(n1.lo.w);
-  const float4 cr = n1.hi;
-  float tn;
-  bool h;
 #define LP_CHILDH(i, c, L, H, m)                                                             \
   ref[i] = __float_as_uint(cr.c);                                                            \
   h = lane_box<false>(r, mk3(lx##L.m, ly##L.m, lz##L.m), mk3(hx##L.m, hy##L.m, hz##L.m),     \
                       tmax, tn) &&                                                           \
       ref[i] != kNoChildRef;                                                                 \
   key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
+#endif
   LP_CHILDH(0, x, 01, 01, x)
   LP_CHILDH(1, y, 01, 01, y)
   LP_CHILDH(2, z, 23, 23, x)
