@@ -52,6 +52,9 @@ constexpr int kRing = LP_POOL_RING;      // newest stack entries of a ray kept i
 #ifndef LP_POOL_PREFETCH
 #define LP_POOL_PREFETCH 0
 #endif
+#ifndef LP_POOL_NODE_STEPS
+#define LP_POOL_NODE_STEPS 3  // node visits of a lane per scheduling round (1 / 2 / 3 / 4 / 6 / 16 = 5332 / 5485 / 5552 / 5539 / 5329 / 5374 Mrays/s)
+#endif
 template <bool HALF, int WIDE = 4>
 __device__ __forceinline__ void pool_prefetch(const SceneDev &sc, uint32_t ref, bool in_blas) {
 #if LP_POOL_PREFETCH
@@ -381,28 +384,39 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
             }
         }
       } else {
-      uint32_t key[4], ref[4];
-      if (HALF) node4h_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
-      else node4_test(sc, __float_as_uint(b.w), r, a.w, key, ref);
-      if (!ANY) {
-        LP_CSWAP(key[0], key[1], ref[0], ref[1])
-        LP_CSWAP(key[2], key[3], ref[2], ref[3])
-        LP_CSWAP(key[0], key[2], ref[0], ref[2])
-        LP_CSWAP(key[1], key[3], ref[1], ref[3])
-        LP_CSWAP(key[1], key[2], ref[1], ref[2])
-        if (key[0] != 0xFFFFFFFFu) {
-          if (key[3] != 0xFFFFFFFFu) push(s, stk, spb, ref[3]);
-          if (key[2] != 0xFFFFFFFFu) push(s, stk, spb, ref[2]);
-          if (key[1] != 0xFFFFFFFFu) push(s, stk, spb, ref[1]);
-          next = ref[0];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (key[i] != 0xFFFFFFFFu) {
-            if (next != kNoChildRef) push(s, stk, spb, next);
-            next = ref[i];
+      // LP_POOL_NODE_STEPS node visits per scheduling round: a lane whose next stop is an inner
+      // node again tests it right away instead of going back to the pool (the round's ballots,
+      // lists and state updates are 57 % of the kernel's instructions, ncu source page); the
+      // lanes that reached a leaf or found no child wait for it
+      uint32_t cur = __float_as_uint(b.w);
+#pragma unroll 1
+      for (int step = 0;; ++step) {
+        uint32_t key[4], ref[4];
+        if (HALF) node4h_test(sc, cur, r, a.w, key, ref);
+        else node4_test(sc, cur, r, a.w, key, ref);
+        next = kNoChildRef;
+        if (!ANY) {
+          LP_CSWAP(key[0], key[1], ref[0], ref[1])
+          LP_CSWAP(key[2], key[3], ref[2], ref[3])
+          LP_CSWAP(key[0], key[2], ref[0], ref[2])
+          LP_CSWAP(key[1], key[3], ref[1], ref[3])
+          LP_CSWAP(key[1], key[2], ref[1], ref[2])
+          if (key[0] != 0xFFFFFFFFu) {
+            if (key[3] != 0xFFFFFFFFu) push(s, stk, spb, ref[3]);
+            if (key[2] != 0xFFFFFFFFu) push(s, stk, spb, ref[2]);
+            if (key[1] != 0xFFFFFFFFu) push(s, stk, spb, ref[1]);
+            next = ref[0];
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (key[i] != 0xFFFFFFFFu) {
+              if (next != kNoChildRef) push(s, stk, spb, next);
+              next = ref[i];
+            }
+        }
+        if (step + 1 >= LP_POOL_NODE_STEPS || next == kNoChildRef || (next & kLeaf)) break;
+        cur = next;
       }
       }
       if (next != kNoChildRef) {
