@@ -180,20 +180,19 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
   // Traversal stack of a pool slot: entries [base, sp) live in the shared-memory ring, older
   // entries [0, base) in the global scratch.  The pop a node fetch depends on was the top
   // long-scoreboard stall when the whole stack was in global memory (ncu).
-  auto push = [&](uint32_t s, uint32_t *stk, uint32_t &spb, uint32_t x) {
-    uint32_t sp = spb & 0xFFFFu, base = spb >> 16;
+  // (sp and base stay unpacked through the pushes of a round: packing and unpacking them per
+  // push was 4 % of the bounce kernel's instructions, ncu source page)
+  auto push = [&](uint32_t s, uint32_t *stk, uint32_t &sp, uint32_t &base, uint32_t x) {
     if (sp - base == (uint32_t)kRing) {
       stk[base * SSTRIDE] = S.ring[(base & (kRing - 1)) * kPool + s];
       ++base;
     }
     S.ring[(sp & (kRing - 1)) * kPool + s] = x;
     ++sp;
-    spb = sp | (base << 16);
   };
   // pop the next reference of slot s (handles leaving an instance); writes cur/sp/state
-  auto pop = [&](uint32_t s, uint32_t *stk, uint32_t spb, uint32_t flags, uint32_t item,
-                 float tbest) {
-    uint32_t sp = spb & 0xFFFFu, base = spb >> 16;
+  auto pop = [&](uint32_t s, uint32_t *stk, uint32_t sp, uint32_t base, uint32_t flags,
+                 uint32_t item, float tbest) {
     for (;;) {
       if (sp == 0u) {
         finish(s, item, false, tbest);
@@ -354,7 +353,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       LaneRay r;
       r.o = mk3(a.x, a.y, a.z);
       r.idir = mk3(b.x, b.y, b.z);
-      uint32_t spb = e.x;
+      uint32_t sp = e.x & 0xFFFFu, base = e.x >> 16;
       uint32_t next = kNoChildRef;
       if (WIDE == 8) {
         uint32_t key[8], ref[8];
@@ -372,14 +371,14 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
                 next = ref[i];
                 taken = true;
               } else {
-                push(s, stk, spb, ref[i]);
+                push(s, stk, sp, base, ref[i]);
               }
             }
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (key[i] != 0xFFFFFFFFu) {
-              if (next != kNoChildRef) push(s, stk, spb, next);
+              if (next != kNoChildRef) push(s, stk, sp, base, next);
               next = ref[i];
             }
         }
@@ -402,16 +401,16 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
           LP_CSWAP(key[1], key[3], ref[1], ref[3])
           LP_CSWAP(key[1], key[2], ref[1], ref[2])
           if (key[0] != 0xFFFFFFFFu) {
-            if (key[3] != 0xFFFFFFFFu) push(s, stk, spb, ref[3]);
-            if (key[2] != 0xFFFFFFFFu) push(s, stk, spb, ref[2]);
-            if (key[1] != 0xFFFFFFFFu) push(s, stk, spb, ref[1]);
+            if (key[3] != 0xFFFFFFFFu) push(s, stk, sp, base, ref[3]);
+            if (key[2] != 0xFFFFFFFFu) push(s, stk, sp, base, ref[2]);
+            if (key[1] != 0xFFFFFFFFu) push(s, stk, sp, base, ref[1]);
             next = ref[0];
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (key[i] != 0xFFFFFFFFu) {
-              if (next != kNoChildRef) push(s, stk, spb, next);
+              if (next != kNoChildRef) push(s, stk, sp, base, next);
               next = ref[i];
             }
         }
@@ -422,13 +421,13 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       if (next != kNoChildRef) {
         pool_prefetch<HALF, WIDE>(sc, next, (flags & kFlagInBlas) != 0u);
         S.b[s].w = __uint_as_float(next);
-        if (spb != e.x) S.e[s].x = spb;
+        if (sp != (e.x & 0xFFFFu)) S.e[s].x = sp | (base << 16);
         S.state[s] =
             ((next & kLeaf) ? ((flags & kFlagInBlas) ? kStTri : kStEntry) : kStNode) | flags;
       } else {
         // (deferring this pop to the next leaf phase, where all lanes pop together, measured
         // -4.5 %: the ray waits a scheduling round for nothing; profiles/r01_ab.txt run r01i)
-        pop(s, stk, spb, flags, e.y, a.w);
+        pop(s, stk, sp, base, flags, e.y, a.w);
       }
     } else if (phase == kStEntry) {
       // -------------------------------------------------------------- enter an instance
@@ -446,9 +445,9 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       S.a[s] = make_float4(r.o.x, r.o.y, r.o.z, tbest);
       S.b[s] = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(root));
       S.c[s] = make_float4(r.sx, r.sy, r.sz, __uint_as_float((uint32_t)r.kxyz | (inst << 6)));
-      uint32_t spb = e.x;
-      push(s, stk, spb, kSentinel);
-      S.e[s].x = spb;
+      uint32_t sp = e.x & 0xFFFFu, base = e.x >> 16;
+      push(s, stk, sp, base, kSentinel);
+      S.e[s].x = sp | (base << 16);
       pool_prefetch<HALF, WIDE>(sc, root, true);
       S.state[s] = ((root & kLeaf) ? kStTri : kStNode) | kFlagInBlas;
     } else {
@@ -503,7 +502,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
         S.d[s] = hd;
       }
       if (ANY && occluded) finish(s, e.y, true, tbest);
-      else pop(s, stk, e.x, flags, e.y, tbest);
+      else pop(s, stk, e.x & 0xFFFFu, e.x >> 16, flags, e.y, tbest);
 #else
       float4 p0, p1, p2;
       load_tri<true>(sc, first, p0, p1, p2);
@@ -530,7 +529,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
       } else if (left) {
         S.b[s].w = __uint_as_float(kLeaf | ((left - 1u) << 28) | (first + 1u));
       } else {
-        pop(s, stk, e.x, flags, e.y, tbest);
+        pop(s, stk, e.x & 0xFFFFu, e.x >> 16, flags, e.y, tbest);
       }
 #endif
     }
