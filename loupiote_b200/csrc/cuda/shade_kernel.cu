@@ -284,10 +284,12 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
       }
     }
     // ---- converged: compact into the next queues (one atomic per warp and queue)
-    const uint32_t qi = warp_push(out.cont, P.counts + kCntNext + bounce);
+    uint32_t qi, li, ei;
+    warp_push3(out.cont, out.want_l, out.want_e, sc.n_active_lights != 0, sc.env_on != 0,
+               P.counts + kCntNext + bounce, P.counts + kCntLight + bounce,
+               P.counts + kCntEnv + bounce, qi, li, ei);
     if (out.cont) queue_out[qi] = in.slot;
     if (sc.n_active_lights) {
-      const uint32_t li = warp_push(out.want_l, P.counts + kCntLight + bounce);
       if (out.want_l) {
         P.sq_light.o_tmax[li] = make_float4(out.next_o.x, out.next_o.y, out.next_o.z, out.sl_tmax);
         P.sq_light.d_slot[li] =
@@ -296,7 +298,6 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
       }
     }
     if (sc.env_on) {
-      const uint32_t ei = warp_push(out.want_e, P.counts + kCntEnv + bounce);
       if (out.want_e) {
         P.sq_env.o_tmax[ei] = make_float4(out.next_o.x, out.next_o.y, out.next_o.z, INFINITY);
         P.sq_env.d_slot[ei] =
