@@ -234,6 +234,9 @@ constexpr int kShadeWarps = 4;
 #define LP_SHADE_SETTLE 2
 #endif
 constexpr int kSettle = LP_SHADE_SETTLE;
+#ifndef LP_SHADE_PREFETCH
+#define LP_SHADE_PREFETCH 1
+#endif
 #ifndef LP_SHADE_SPW
 #define LP_SHADE_SPW 1
 #endif
@@ -316,6 +319,18 @@ __global__ void __launch_bounds__(32 * kShadeWarps, LP_SHADE_MIN_BLOCKS)
     if (PRIMARY) {
       if (!more) break;
       bool run_hit = false;
+#if LP_SHADE_PREFETCH
+      {  // the hit records of this warp's NEXT batch into L1 (no registers held across the batch)
+        const uint32_t nb = base + n_warps * kRound;
+        if (nb < n) {
+          const uint32_t ns = wave_slot<LP_SHADE_SPW>(P, nb, (uint32_t)lane);
+          if (ns < n) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.ps.hit + ns));
+            if ((lane & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.ps.hit_inst + ns));
+          }
+        }
+      }
+#endif
       // LP_SHADE_SPW (A/B): the primary shade pass in the same sample-major order as the primary
       // extend kernel, so the queues it fills -- and the pools of the bounce kernels that drain
       // them -- hold rays that leave from the same surface point
