@@ -231,7 +231,7 @@ constexpr int kShadeWarps = 4;
 // queue -> hit_inst -> throughput / radiance -- at 37 % occupancy; ncu: 55 % of the kernel's
 // stall samples sat on them with one chunk per round)
 #ifndef LP_SHADE_SETTLE
-#define LP_SHADE_SETTLE 2
+#define LP_SHADE_SETTLE 3  // 2 / 3 / 4 chunks = shade 22.7 / 22.5 / 22.8 ms per step
 #endif
 constexpr int kSettle = LP_SHADE_SETTLE;
 #ifndef LP_SHADE_PREFETCH

@@ -31,8 +31,14 @@ constexpr int kPoolWarps = 4;            // warps per block
 #ifndef LP_POOL_RING
 #define LP_POOL_RING 8
 #endif
+// empty slots that trigger a refill round.  Round 1 (one node visit per round): 32 -> 16 +1.9 %.
+// With three visits per round the closest-hit kernels do better at 24 (8 / 16 / 24 / 32 = 5546 /
+// 5636 / 5660 / 5584 Mrays/s), the any-hit kernels stay at 16 (profiles/r02_ab.txt).
 #ifndef LP_POOL_REFILL
-#define LP_POOL_REFILL 16  // empty slots that trigger a refill round (32 -> 16: +1.9 %, r01j/k)
+#define LP_POOL_REFILL 24
+#endif
+#ifndef LP_POOL_REFILL_ANY
+#define LP_POOL_REFILL_ANY 16
 #endif
 #ifndef LP_POOL_MIN_BLOCKS
 #define LP_POOL_MIN_BLOCKS 8
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, LP_POOL_MIN_BLOCKS)
     unsigned m_lo, m_hi;
     uint32_t phase;
     bool tail = false;
-    if ((!exhausted && c_empty >= LP_POOL_REFILL) || (c_empty == kPool)) {
+    if ((!exhausted && c_empty >= (ANY ? LP_POOL_REFILL_ANY : LP_POOL_REFILL)) || (c_empty == kPool)) {
       if (exhausted) break;
       phase = kStEmpty;
       m_lo = e_lo;
