@@ -40,9 +40,12 @@ __device__ __forceinline__ void node4_test(const SceneDev &sc, uint32_t idx, con
   const float4 ex = s.nx ? hx : lx, ox = s.nx ? lx : hx;
   const float4 ey = s.ny ? hy : ly, oy = s.ny ? ly : hy;
   const float4 ez = s.nz ? hz : lz, oz = s.nz ? lz : hz;
+  // (an EMPTY slot carries the box [+inf, -inf] -- host relayout and device builder alike -- so
+  // its entry distance is +inf and its exit distance -inf: it fails the test without a look at
+  // its reference)
 #define LP_CHILD(i, c)                                                                     \
   ref[i] = __float_as_uint(cr.c);                                                          \
-  h = slab_box(s, ex.c, ey.c, ez.c, ox.c, oy.c, oz.c, tmax, tn) && ref[i] != kNoChildRef;  \
+  h = slab_box(s, ex.c, ey.c, ez.c, ox.c, oy.c, oz.c, tmax, tn);                           \
   key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
 #else
 #define LP_CHILD(i, c)                                                                     \
@@ -83,8 +86,7 @@ __device__ __forceinline__ void node4h_test(const SceneDev &sc, uint32_t idx, co
   const float2 oz01 = unpack_half2(s.nz ? n0.hi.x : n1.lo.z), oz23 = unpack_half2(s.nz ? n0.hi.y : n1.lo.w);
 #define LP_CHILDH(i, c, L, H, m)                                                              \
   ref[i] = __float_as_uint(cr.c);                                                            \
-  h = slab_box(s, ex##L.m, ey##L.m, ez##L.m, ox##L.m, oy##L.m, oz##L.m, tmax, tn) &&        \
-      ref[i] != kNoChildRef;                                                                 \
+  h = slab_box(s, ex##L.m, ey##L.m, ez##L.m, ox##L.m, oy##L.m, oz##L.m, tmax, tn);          \
   key[i] = h ? __float_as_uint(tn) : 0xFFFFFFFFu;
 #else
   const float2 lx01 = unpack_half2(n0.lo.x), lx23 = unpack_half2(n0.lo.y);
