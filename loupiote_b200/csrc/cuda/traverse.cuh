@@ -99,10 +99,13 @@ __device__ __forceinline__ bool lane_box(const LaneRay &r, f3 lo, f3 hi, float t
 // (pn >= o * idir >= pf whatever the rounding of the product), and which plane of a box the ray
 // enters through per axis (the sign of idir).  Per BOX: near_k = fma(plane_near_k, idir_k, -pn_k)
 // and far_k = fma(plane_far_k, idir_k, -pf_k) -- 6 FFMA instead of 6 FADD + 6 FMUL, and no
-// min / max between the two planes of an axis.  near is never above and far never below the
-// values of lane_box up to the relative rounding the 1e-6 padding of the far side already
-// covers, so a box lane_box<false> accepts is accepted here as well: the visited set can only
-// grow, and what is HIT is decided by the exact triangle test alone.
+// min / max between the two planes of an axis.  Conservative like lane_box<false>: against the
+// exact distances (with this idir) near is too large and far too small by at most one
+// rounding (2^-24) -- the widening of p only moves them the safe way -- and the MUFU
+// reciprocals add 2^-22 per axis, all inside the 1e-6 padding of the far side.  Every box
+// the ray really enters is visited (tests/test_cpu_slab.py checks the arithmetic against
+// float64 on millions of rays); the two tests can differ on boxes inside the padding band
+// only, and what is HIT is decided by the exact triangle test alone.
 #ifndef LP_SLAB_FMA
 #define LP_SLAB_FMA 1  // 0 = node tests through lane_box (A/B, profiles/r02_ab.txt)
 #endif
