@@ -47,6 +47,7 @@ struct lp_renderer {
   lp::DevBuf<uint32_t> hit_inst, queue0, queue1;
   lp::DevBuf<float4> sl_o, sl_d, sl_c, se_o, se_d, se_c;
   lp::DevBuf<uint32_t> counts;
+  lp::DevBuf<uint32_t> bins;  // LP_BIN_OCTANT experiment (bin_octant.cuh), made at first use
   lp::DevBuf<uint32_t> pool_scratch;  // traversal stacks of the ray-pool kernels
   lp::DevBuf<lp::Counters> counters;
   // render targets
